@@ -1,0 +1,335 @@
+"""CPU ORACLE for the EKS smoothing hot path -- TEST INFRASTRUCTURE ONLY.
+
+Thin ctypes wrapper over ``oracle/liboracle.so`` (built from ``oracle/eks_oracle.cpp``) plus
+NumPy restatements of the small host-side steps of the reference path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this module; the product package ``eks_b200`` never does.
+
+PARITY STATUS: **parity unpinned** at the dynamax boundary (dynamax<=1.0.1 / jax<=0.4.36 / optax
+are not installable here, see the header of eks_oracle.cpp).  Every function cites the reference
+file:line it restates (paths relative to /root/reference).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'liboracle.so')
+_lib = None
+
+CAM_STRIDE = 29
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the recipe in oracle/Makefile."""
+    src = os.path.join(_HERE, 'eks_oracle.cpp')
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(['make', '-C', _HERE, 'liboracle.so'], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _sfx(dtype) -> str:
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return 'f32'
+    if dtype == np.float64:
+        return 'f64'
+    raise TypeError(f'oracle supports float32/float64, got {dtype}')
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _real(dtype, x):
+    return (ctypes.c_float if np.dtype(dtype) == np.float32 else ctypes.c_double)(float(x))
+
+
+# ----------------------------------------------------------------------------- cameras
+def rodrigues(rvec) -> np.ndarray:
+    """rvec (3,) -> R (3,3); restates eks/multicam_smoother.py:771-793 (OpenCV convention)."""
+    rvec = np.asarray(rvec, dtype=np.float64).ravel()
+    theta = np.linalg.norm(rvec)
+    if theta < 1e-12:
+        rx, ry, rz = rvec
+        Km = np.array([[0.0, -rz, ry], [rz, 0.0, -rx], [-ry, rx, 0.0]])
+        return np.eye(3) + Km
+    rx, ry, rz = rvec / theta
+    Km = np.array([[0.0, -rz, ry], [rz, 0.0, -rx], [-ry, rx, 0.0]])
+    return np.eye(3) + np.sin(theta) * Km + (1.0 - np.cos(theta)) * (Km @ Km)
+
+
+def pack_camera(rvec_or_R, tvec, Kmat, dist) -> np.ndarray:
+    """Pack one camera into the 29-real layout used by the oracle.
+
+    dist follows OpenCV ordering [k1,k2,p1,p2,k3,k4,k5,k6,s1,s2,s3,s4,(tx,ty ignored)], padded with
+    zeros (parse_dist, eks/multicam_smoother.py:796-803).
+    """
+    r = np.asarray(rvec_or_R, dtype=np.float64)
+    Rm = r if r.shape == (3, 3) else rodrigues(r)
+    Kmat = np.asarray(Kmat, dtype=np.float64)
+    d = np.zeros(14)
+    dist = np.asarray(dist, dtype=np.float64).ravel()
+    d[:min(14, dist.size)] = dist[:14]
+    out = np.zeros(CAM_STRIDE)
+    out[0:9] = Rm.ravel()
+    out[9:12] = np.asarray(tvec, dtype=np.float64).ravel()
+    out[12:17] = [Kmat[0, 0], Kmat[1, 1], Kmat[0, 2], Kmat[1, 2], Kmat[0, 1]]
+    out[17:29] = d[:12]
+    return out
+
+
+def project(cams, X, dtype=np.float64, jac=False):
+    """h(x): (N,3) -> (N,2V) and optionally its Jacobian (N,2V,3)."""
+    cams = _c(np.asarray(cams).reshape(-1, CAM_STRIDE), dtype)
+    X = _c(np.asarray(X).reshape(-1, 3), dtype)
+    V, N = cams.shape[0], X.shape[0]
+    uv = np.empty((N, 2 * V), dtype=dtype)
+    J = np.empty((N, 2 * V, 3), dtype=dtype) if jac else None
+    getattr(lib(), f'eks_oracle_project_{_sfx(dtype)}')(V, _p(cams), N, _p(X), _p(uv), _p(J))
+    return (uv, J) if jac else uv
+
+
+# ----------------------------------------------------------------------------- ensemble
+def ensemble(raw, avg_mode='median', var_mode='confidence_weighted_var', nan_replacement=1000.0,
+             dtype=np.float32) -> np.ndarray:
+    """raw (M,V,T,K,3) -> (V,T,K,5) [x,y,var_x,var_y,likelihood]; eks/core.py:25-101."""
+    raw = _c(raw, dtype)
+    M, V, T, K, F = raw.shape
+    assert F == 3 and M <= 64
+    out = np.empty((V, T, K, 5), dtype=dtype)
+    vm = 1 if var_mode in ('conf_weighted_var', 'confidence_weighted_var') else 0
+    getattr(lib(), f'eks_oracle_ensemble_{_sfx(dtype)}')(
+        _p(raw), M, V, T, K, int(avg_mode == 'median'), vm, _real(dtype, nan_replacement), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- small host steps
+def crop_frames(y, s_frames):
+    """eks/utils.py:235-290 restated (validation + concatenation of [start,end) spans)."""
+    n = len(y)
+    if s_frames is None or len(s_frames) == 0 or (len(s_frames) == 1 and s_frames[0] == (None, None)):
+        return y
+    if not isinstance(s_frames, list):
+        raise TypeError('s_frames must be a list of (start, end) tuples or None.')
+    spans = []
+    for i, fr in enumerate(s_frames):
+        if not (isinstance(fr, tuple) and len(fr) == 2):
+            raise ValueError(f's_frames[{i}] must be a (start, end) tuple, got {fr!r}')
+        a, b = fr
+        if a is not None and not isinstance(a, int):
+            raise ValueError(f's_frames[{i}].start must be int or None, got {a!r}')
+        if b is not None and not isinstance(b, int):
+            raise ValueError(f's_frames[{i}].end must be int or None, got {b!r}')
+        a = 0 if a is None else a
+        b = n if b is None else b
+        if a < 0 or b > n:
+            raise ValueError(f'Range ({a}, {b}) out of bounds for length {n}.')
+        if a >= b:
+            raise ValueError(f'Invalid range ({a}, {b}).')
+        spans.append((a, b))
+    spans.sort(key=lambda s: s[0])
+    for i in range(1, len(spans)):
+        if spans[i][0] < spans[i - 1][1]:
+            raise ValueError(f'Overlapping or out-of-order intervals: {spans[i - 1]} and {spans[i]}')
+    return np.concatenate([y[a:b] for a, b in spans], axis=0)
+
+
+def compute_initial_guess(ensemble_vars_k) -> float:
+    """eks/core.py:104-133 + caller fallback core.py:235-236.  ensemble_vars_k: (T, obs)."""
+    ev = np.asarray(ensemble_vars_k)[:2000]
+    if ev.shape[0] < 2:
+        raise ValueError('Not enough frames to compute temporal differences.')
+    d = ev[1:] - ev[:-1]
+    g = float(round(np.nanstd(d), 5)) or 2.0
+    return g if (np.isfinite(g) and g > 0.0) else 2.0
+
+
+def constant_R(var_cropped, min_var=1e-4) -> np.ndarray:
+    """(T',obs) variances (already clipped at 1e-12) -> (obs,) ; eks/core.py:702-709."""
+    med = np.nanmedian(var_cropped, axis=0)
+    return np.clip(med, min_var, np.inf).astype(var_cropped.dtype)
+
+
+# ----------------------------------------------------------------------------- kernels of the path
+def _stack_model(m0s, S0s, As, Qs, Cs, cams, dtype):
+    m0s = _c(m0s, dtype)
+    K, D = m0s.shape
+    S0s = _c(S0s, dtype).reshape(K, D, D)
+    As = _c(As, dtype).reshape(K, D, D)
+    Qs = _c(Qs, dtype).reshape(K, D, D)
+    if cams is not None:
+        cams = _c(np.asarray(cams).reshape(-1, CAM_STRIDE), dtype)
+        ncam = cams.shape[0]
+        O = 2 * ncam
+        Cs_ = None
+        assert D == 3
+    else:
+        Cs_ = _c(Cs, dtype)
+        O = Cs_.shape[1]
+        ncam = 0
+    assert D <= lib().eks_oracle_dmax() and O <= lib().eks_oracle_omax()
+    return K, D, O, m0s, S0s, As, Qs, Cs_, ncam, cams
+
+
+def nll_grad(ys, m0s, S0s, As, Cs, Qs, Rdiag, s, cams=None, dtype=np.float64):
+    """Filter NLL and d NLL / d s per sequence.  ys (K,T,O); Rdiag (K,O) constant or (K,T,O)."""
+    K, D, O, m0s, S0s, As, Qs, Cs_, ncam, cams = _stack_model(m0s, S0s, As, Qs, Cs, cams, dtype)
+    ys = _c(ys, dtype)
+    T = ys.shape[1]
+    Rdiag = _c(Rdiag, dtype)
+    tv = int(Rdiag.ndim == 3)
+    s = _c(np.broadcast_to(np.asarray(s, dtype=dtype), (K,)), dtype)
+    nll = np.empty(K, dtype=dtype)
+    dn = np.empty(K, dtype=dtype)
+    getattr(lib(), f'eks_oracle_nll_grad_{_sfx(dtype)}')(
+        K, D, O, _p(m0s), _p(S0s), _p(As), _p(Qs), _p(Cs_), ncam, _p(cams), _p(ys), _p(Rdiag), tv, T,
+        _p(s), _p(nll), _p(dn))
+    return nll, dn
+
+
+def optimize(ys, m0s, S0s, As, Cs, Qs, Rconst, blocks, s_guess_per_k, lr=0.25, s_bounds_log=(-8.0, 8.0),
+             tol=1e-3, safety_cap=300, cams=None, dtype=np.float32, trace_cap=0):
+    """Adam on log s per block; eks/core.py:306-401, 403-559, 562-699.
+
+    ys (K,T',O) cropped; Rconst (K,O).  Returns dict(s_finals(K,), s_log(B,), loss(B,), iters(B,),
+    trace (B,trace_cap,3) [s_log, loss, lr*grad])."""
+    K, D, O, m0s, S0s, As, Qs, Cs_, ncam, cams = _stack_model(m0s, S0s, As, Qs, Cs, cams, dtype)
+    ys = _c(ys, dtype)
+    T = ys.shape[1]
+    Rconst = _c(Rconst, dtype)
+    if not blocks:
+        blocks = [[k] for k in range(K)]
+    order = [k for b in blocks for k in b]
+    off = np.zeros(len(blocks) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(b) for b in blocks])
+    idx = np.asarray(order, dtype=int)
+    s0 = np.array([np.clip(np.mean([s_guess_per_k[k] for k in b]), 1e-6, 1e3) for b in blocks])
+    s_log0 = np.log(s0).astype(np.float32).astype(dtype)  # core.py:441, 622 -- float32 seed
+    B = len(blocks)
+    s_log = np.empty(B, dtype=dtype)
+    loss = np.empty(B, dtype=dtype)
+    iters = np.empty(B, dtype=np.int32)
+    trace = np.full((B, max(trace_cap, 1), 3), np.nan, dtype=dtype) if trace_cap else None
+    getattr(lib(), f'eks_oracle_optimize_{_sfx(dtype)}')(
+        B, _p(off), D, O, _p(_c(m0s[idx], dtype)), _p(_c(S0s[idx], dtype)), _p(_c(As[idx], dtype)),
+        _p(_c(Qs[idx], dtype)), _p(None if Cs_ is None else _c(Cs_[idx], dtype)), ncam, _p(cams),
+        _p(_c(ys[idx], dtype)), _p(_c(Rconst[idx], dtype)), T, _p(s_log0), _real(dtype, lr),
+        _real(dtype, s_bounds_log[0]), _real(dtype, s_bounds_log[1]), _real(dtype, tol), int(safety_cap),
+        _p(s_log), _p(loss), _p(iters), _p(trace), int(trace_cap))
+    s_finals = np.empty(K, dtype=float)
+    for b, blk in enumerate(blocks):
+        s_star = float(np.exp(np.clip(s_log[b], s_bounds_log[0], s_bounds_log[1])))  # core.py:550, 694
+        for k in blk:
+            s_finals[k] = s_star
+    return dict(s_finals=s_finals, s_log=s_log, loss=loss, iters=iters, trace=trace, s_log0=s_log0)
+
+
+def smooth(ys, m0s, S0s, As, Cs, Qs, Rdiag, s, cams=None, dtype=np.float32, return_filtered=False):
+    """EKF filter + RTS smoother per sequence; eks/core.py:274-295.  Rdiag (K,T,O) or (K,O)."""
+    K, D, O, m0s, S0s, As, Qs, Cs_, ncam, cams = _stack_model(m0s, S0s, As, Qs, Cs, cams, dtype)
+    ys = _c(ys, dtype)
+    T = ys.shape[1]
+    Rdiag = _c(Rdiag, dtype)
+    tv = int(Rdiag.ndim == 3)
+    s = _c(np.broadcast_to(np.asarray(s, dtype=dtype), (K,)), dtype)
+    ms = np.empty((K, T, D), dtype=dtype)
+    Vs = np.empty((K, T, D, D), dtype=dtype)
+    mfs = np.empty((K, T, D), dtype=dtype) if return_filtered else None
+    Pfs = np.empty((K, T, D, D), dtype=dtype) if return_filtered else None
+    ll = np.empty(K, dtype=dtype)
+    bad = np.zeros(K, dtype=np.int32)
+    getattr(lib(), f'eks_oracle_smooth_{_sfx(dtype)}')(
+        K, D, O, _p(m0s), _p(S0s), _p(As), _p(Qs), _p(Cs_), ncam, _p(cams), _p(ys), _p(Rdiag), tv, T, _p(s),
+        _p(ms), _p(Vs), _p(mfs), _p(Pfs), _p(ll), _p(bad))
+    if return_filtered:
+        return ms, Vs, mfs, Pfs, ll
+    return ms, Vs
+
+
+# ----------------------------------------------------------------------------- the path, end to end
+def run_kalman_smoother(ys, m0s, S0s, As, Cs, Qs, ensemble_vars, s_frames=None, smooth_param=None,
+                        blocks=None, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
+                        cams=None, dtype=np.float32, min_R_var=1e-4, trace_cap=0):
+    """eks/core.py:159-302 restated.  ys (K,T,O); ensemble_vars (T,K,O).
+
+    Returns (s_finals (K,) float64, ms (K,T,D), Vs (K,T,D,D), info dict)."""
+    ys = np.asarray(ys, dtype=dtype)
+    K, T, O = ys.shape
+    ev = np.asarray(ensemble_vars, dtype=dtype)
+    var_kto = np.clip(np.swapaxes(ev, 0, 1), 1e-12, None)  # build_R_from_vars, utils.py:373
+    guesses = np.array([compute_initial_guess(ev[:, k, :]) for k in range(K)])
+    info = dict(guesses=guesses)
+    if smooth_param is not None:
+        s_finals = np.empty(K, dtype=float)
+        if isinstance(smooth_param, (int, float)):
+            s_finals[:] = float(smooth_param)
+        else:
+            s_finals[:] = np.asarray(smooth_param, dtype=float)
+    else:
+        y_c = np.stack([crop_frames(ys[k], s_frames) for k in range(K)])
+        R_c = np.stack([constant_R(crop_frames(var_kto[k], s_frames), min_R_var) for k in range(K)])
+        opt = optimize(y_c, m0s, S0s, As, Cs, Qs, R_c, blocks, guesses, lr=lr, s_bounds_log=s_bounds_log,
+                       tol=tol, safety_cap=safety_cap, cams=cams, dtype=dtype, trace_cap=trace_cap)
+        s_finals = opt['s_finals']
+        info.update(opt)
+        info['Rconst'] = R_c
+    ms, Vs = smooth(ys, m0s, S0s, As, Cs, Qs, var_kto, s_finals, cams=cams, dtype=dtype)
+    return s_finals, ms, Vs, info
+
+
+def singlecam(raw, smooth_param=None, s_frames=None, blocks=None, avg_mode='median',
+              var_mode='confidence_weighted_var', dtype=np.float32, trace_cap=0):
+    """ensemble_kalman_smoother_singlecam restated (eks/singlecam_smoother.py:105-284).
+
+    raw: (M,1,T,K,3).  Returns dict(out (T,K,9) float64 in the reference column order
+    [x,y,likelihood,x_ens_median,y_ens_median,x_ens_var,y_ens_var,x_posterior_var,y_posterior_var],
+    s_finals, info)."""
+    raw = np.asarray(raw)
+    M, V, T, K, _ = raw.shape
+    assert V == 1
+    ens = ensemble(raw, avg_mode, var_mode, dtype=dtype)[0]  # (T,K,5)
+    preds = ens[..., 0:2].astype(np.float64) if dtype == np.float64 else ens[..., 0:2]
+    # center_predictions(quantile 100): every frame is kept (utils.py:318-343) -> mean over all frames
+    means = np.mean(preds, axis=0, keepdims=True)  # (1,K,2)
+    centered = preds - means
+    ys = np.transpose(centered, (1, 0, 2))  # (K,T,2)
+    m0s = np.zeros((K, 2))
+    S0s = np.zeros((K, 2, 2))
+    for k in range(K):
+        S0s[k, 0, 0] = np.nanvar(centered[:, k, 0])
+        S0s[k, 1, 1] = np.nanvar(centered[:, k, 1])
+    eye = np.tile(np.eye(2), (K, 1, 1))
+    s_finals, ms, Vs, info = run_kalman_smoother(
+        ys, m0s, S0s, eye, eye, eye, ens[..., 2:4], s_frames=s_frames, smooth_param=smooth_param,
+        blocks=blocks, dtype=dtype, trace_cap=trace_cap)
+    out = np.empty((T, K, 9), dtype=np.float64)
+    out[..., 0] = ms[:, :, 0].T.astype(np.float64) + means[0, :, 0][None, :]
+    out[..., 1] = ms[:, :, 1].T.astype(np.float64) + means[0, :, 1][None, :]
+    out[..., 2] = ens[..., 4]
+    out[..., 3] = ens[..., 0]
+    out[..., 4] = ens[..., 1]
+    out[..., 5] = ens[..., 2]
+    out[..., 6] = ens[..., 3]
+    out[..., 7] = Vs[:, :, 0, 0].T
+    out[..., 8] = Vs[:, :, 1, 1].T
+    info['means'] = means
+    info['S0s'] = S0s
+    return dict(out=out, s_finals=s_finals, info=info, ms=ms, Vs=Vs)
