@@ -1,0 +1,270 @@
+// ensemble.cu -- per-frame ensemble statistics across seed predictions (reference:
+// eks/core.py:25-101, inner compute_stats :58-85).
+//
+// Input : raw[S][M][V][T][K][3]  (reference MarkerArray layout, fields innermost; f32 or f64)
+// Output: five frame-major planes per (session, camera, keypoint):
+//           out[s*sess_stride + v*cam_stride + k*kp_stride + plane_off[f] + t],  f in
+//           {0:x_avg, 1:y_avg, 2:var_x, 3:var_y, 4:mean likelihood}
+//         plus optional per-tile partial moments (sum x, sum y, sum x^2, sum y^2 of the averaged
+//         coordinates, fp64) so that centring / S0 need no extra pass over HBM.
+//
+// One CTA = one (session, camera, tile of TT frames) for all K keypoints.  Loads walk the AoS
+// input with keypoint fastest (fully coalesced), results are transposed through shared memory and
+// written with frame fastest (fully coalesced).  HBM-bound: 12*M bytes in, 20 bytes out per cell.
+#include "common.cuh"
+#include "../../include/eks_b200.h"
+
+namespace eks {
+
+struct EnsOut {
+    long long sess_stride, cam_stride, kp_stride;
+    long long plane_off[5];
+};
+
+template <class P> __device__ inline P pos_inf();
+template <> __device__ inline float pos_inf<float>() { return __int_as_float(0x7f800000); }
+template <> __device__ inline double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+template <class P> __device__ inline P real_max();
+template <> __device__ inline float real_max<float>() { return 3.402823466e+38f; }
+template <> __device__ inline double real_max<double>() { return 1.7976931348623157e+308; }
+
+// bitonic sorting network on N (power of two) register values, ascending
+template <class P, int N>
+__device__ inline void sort_network(P (&v)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = ((i & k) == 0);
+                    const P a = v[i], b = v[l];
+                    const bool sw = up ? (a > b) : (a < b);
+                    v[i] = sw ? b : a;
+                    v[l] = sw ? a : b;
+                }
+            }
+        }
+    }
+}
+
+// statistics of one coordinate over the M seeds (NaN-aware), reference core.py:64-79
+template <class P, int MAXM>
+__device__ inline void coord_stats(const P (&x)[MAXM], int M, bool avg_median, P& avg, P& var) {
+    int n = 0;
+    P sum = P(0);
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+        if (m < M && !isnan(x[m])) { sum += x[m]; ++n; }
+    if (n == 0) {
+        avg = nan("");
+        var = nan("");
+        return;
+    }
+    const P mean = sum / P(n);
+    P ss = P(0);
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m)
+        if (m < M && !isnan(x[m])) { const P d = x[m] - mean; ss += d * d; }
+    var = ss / P(n);
+    if (!avg_median) {
+        avg = mean;
+        return;
+    }
+    P s[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) s[m] = (m < M && !isnan(x[m])) ? x[m] : pos_inf<P>();
+    sort_network<P, MAXM>(s);
+    // nanmedian: middle element, or mean of the two middle elements, of the n valid values
+    const int hi = n >> 1, lo = (n & 1) ? hi : hi - 1;
+    P a = P(0), b = P(0);
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        if (m == lo) a = s[m];
+        if (m == hi) b = s[m];
+    }
+    avg = a * P(0.5) + b * P(0.5);
+    if (n & 1) avg = b;
+}
+
+template <class Tin, class P, int MAXM>
+__global__ void __launch_bounds__(256) ensemble_kernel(const Tin* __restrict__ raw, long long raw_sess_stride, int M,
+                                                       int V, int T, int K, int avg_median, int var_mode,
+                                                       P nan_repl, P* __restrict__ out, EnsOut eo,
+                                                       double* __restrict__ partials, int TT) {
+    extern __shared__ unsigned char smem_raw[];
+    P* tile = reinterpret_cast<P*>(smem_raw);  // [5][K][TT+1]
+    const int tile_idx = blockIdx.x, v = blockIdx.y, sess = blockIdx.z;
+    const int t0 = tile_idx * TT;
+    const int nt = min(TT, T - t0);
+    const int ld = TT + 1;
+    const Tin* base = raw + (long long)sess * raw_sess_stride;
+    const long long m_stride = (long long)V * T * K * 3;
+    const long long off0 = ((long long)v * T + t0) * K * 3;
+
+    for (int e = threadIdx.x; e < nt * K; e += blockDim.x) {
+        const int tl = e / K, k = e - tl * K;
+        P xs[MAXM], ys[MAXM];
+        P conf = P(0);
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                const Tin* p = base + (long long)m * m_stride + off0 + (long long)e * 3;
+                xs[m] = P(__ldg(p));       // cast to the compute precision first (core.py:90-92)
+                ys[m] = P(__ldg(p + 1));
+                conf += P(__ldg(p + 2));   // likelihood sum is NOT NaN-aware (core.py:67-68)
+            } else {
+                xs[m] = P(0);
+                ys[m] = P(0);
+            }
+        }
+        const P mean_conf = conf / P(M);
+        P ax, vx, ay, vy;
+        coord_stats<P, MAXM>(xs, M, avg_median != 0, ax, vx);
+        coord_stats<P, MAXM>(ys, M, avg_median != 0, ay, vy);
+        if (M == 1) {
+            vx = vy = P(1) / fmax(mean_conf, P(1e-5));
+        } else if (var_mode == 1) {
+            vx = vx / mean_conf;
+            vy = vy / mean_conf;
+        }
+        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
+        if (isnan(vx)) vx = nan_repl; else if (isinf(vx)) vx = vx > 0 ? real_max<P>() : -real_max<P>();
+        if (isnan(vy)) vy = nan_repl; else if (isinf(vy)) vy = vy > 0 ? real_max<P>() : -real_max<P>();
+        tile[(0 * K + k) * ld + tl] = ax;
+        tile[(1 * K + k) * ld + tl] = ay;
+        tile[(2 * K + k) * ld + tl] = vx;
+        tile[(3 * K + k) * ld + tl] = vy;
+        tile[(4 * K + k) * ld + tl] = mean_conf;
+    }
+    __syncthreads();
+    // coalesced plane writes: frame fastest
+    P* obase = out + (long long)sess * eo.sess_stride + (long long)v * eo.cam_stride;
+    for (int idx = threadIdx.x; idx < 5 * K * nt; idx += blockDim.x) {
+        const int tl = idx % nt, fk = idx / nt;
+        const int f = fk / K, k = fk - f * K;
+        obase[(long long)k * eo.kp_stride + eo.plane_off[f] + t0 + tl] = tile[(f * K + k) * ld + tl];
+    }
+    // per-tile partial moments of the averaged coordinates (deterministic: fixed lane tree)
+    if (partials != nullptr) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        const int ntiles = gridDim.x;
+        for (int k = warp; k < K; k += nwarp) {
+            double sx = 0, sy = 0, sxx = 0, syy = 0;
+            for (int tl = lane; tl < nt; tl += 32) {
+                const double x = (double)tile[(0 * K + k) * ld + tl];
+                const double y = (double)tile[(1 * K + k) * ld + tl];
+                sx += x; sy += y; sxx += x * x; syy += y * y;
+            }
+            sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); syy = warp_sum(syy);
+            if (lane == 0) {
+                double* pp = partials + ((((long long)sess * V + v) * K + k) * ntiles + tile_idx) * 4;
+                pp[0] = sx; pp[1] = sy; pp[2] = sxx; pp[3] = syy;
+            }
+        }
+    }
+}
+
+// reduce the per-tile partials in a fixed order: one warp per (session, camera, keypoint)
+template <class P>
+__global__ void moments_finalize_kernel(const double* __restrict__ partials, int nseq, int ntiles, long long T,
+                                        P* __restrict__ mean_out, P* __restrict__ var_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nseq) return;
+    const double* pp = partials + (long long)warp * ntiles * 4;
+    double a[4] = {0, 0, 0, 0};
+    for (int i = lane; i < ntiles; i += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] += pp[(long long)i * 4 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = warp_sum(a[q]);
+    if (lane == 0) {
+        const double n = (double)T;
+        const double mx = a[0] / n, my = a[1] / n;
+        // the centred data are formed in precision P (x - P(mean)); its variance about its own mean
+        // equals the variance of x, so S0 = E[x^2] - mean^2 in fp64 (utils.py:350-351,
+        // singlecam_smoother.py:262-266)
+        mean_out[warp * 2 + 0] = P(mx);
+        mean_out[warp * 2 + 1] = P(my);
+        var_out[warp * 2 + 0] = P(fmax(a[2] / n - mx * mx, 0.0));
+        var_out[warp * 2 + 1] = P(fmax(a[3] / n - my * my, 0.0));
+    }
+}
+
+template <class Tin, class P>
+int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int V, int T, int K, int avg_median,
+                    int var_mode, double nan_repl, P* out, const EnsOut& eo, double* partials, int TT,
+                    cudaStream_t st) {
+    const int ntiles = (T + TT - 1) / TT;
+    dim3 grid(ntiles, V, S), block(256);
+    const size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
+    EKS_REQUIRE(smem <= 200 * 1024, "ensemble: K=%d too large for the shared-memory tile", K);
+#define EKS_ENS_LAUNCH(MAXM)                                                                                      \
+    do {                                                                                                          \
+        auto kern = ensemble_kernel<Tin, P, MAXM>;                                                                \
+        if (smem > 48 * 1024)                                                                                     \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+        kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl, out, \
+                                        eo, partials, TT);                                                        \
+    } while (0)
+    if (M <= 4) EKS_ENS_LAUNCH(4);
+    else if (M <= 8) EKS_ENS_LAUNCH(8);
+    else if (M <= 16) EKS_ENS_LAUNCH(16);
+    else if (M <= 32) EKS_ENS_LAUNCH(32);
+    else EKS_REQUIRE(false, "ensemble: at most 32 seeds supported, got %d", M);
+#undef EKS_ENS_LAUNCH
+    return check_launch("ensemble_kernel");
+}
+
+}  // namespace eks
+
+using namespace eks;
+
+extern "C" int eks_ensemble_tile_frames(void) { return 64; }
+
+extern "C" int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_sess_stride, int n_sessions, int M,
+                                  int V, int T, int K, int avg_median, int var_mode, double nan_replacement,
+                                  void* out, int out_dtype, long long sess_stride, long long cam_stride,
+                                  long long kp_stride, const long long* plane_off, double* moment_partials,
+                                  void* stream) {
+    EKS_REQUIRE(raw && out && plane_off, "ensemble: null pointer");
+    EKS_REQUIRE(M >= 1 && V >= 1 && T >= 1 && K >= 1 && n_sessions >= 1, "ensemble: bad dims");
+    EKS_REQUIRE(!(raw_dtype == EKS_F32 && out_dtype == EKS_F64), "ensemble: f32 input with f64 output unsupported");
+    EnsOut eo;
+    eo.sess_stride = sess_stride; eo.cam_stride = cam_stride; eo.kp_stride = kp_stride;
+    for (int i = 0; i < 5; ++i) eo.plane_off[i] = plane_off[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int TT = eks_ensemble_tile_frames();
+    if (raw_dtype == EKS_F32 && out_dtype == EKS_F32)
+        return launch_ensemble<float, float>((const float*)raw, raw_sess_stride, n_sessions, M, V, T, K, avg_median,
+                                             var_mode, nan_replacement, (float*)out, eo, moment_partials, TT, st);
+    if (raw_dtype == EKS_F64 && out_dtype == EKS_F32)
+        return launch_ensemble<double, float>((const double*)raw, raw_sess_stride, n_sessions, M, V, T, K,
+                                              avg_median, var_mode, nan_replacement, (float*)out, eo,
+                                              moment_partials, TT, st);
+    if (raw_dtype == EKS_F64 && out_dtype == EKS_F64)
+        return launch_ensemble<double, double>((const double*)raw, raw_sess_stride, n_sessions, M, V, T, K,
+                                               avg_median, var_mode, nan_replacement, (double*)out, eo,
+                                               moment_partials, TT, st);
+    EKS_REQUIRE(false, "ensemble: unsupported dtype combination");
+}
+
+extern "C" int eks_center_moments(const double* moment_partials, int n_seq, int T, void* mean_out, void* var_out,
+                                  int dtype, void* stream) {
+    EKS_REQUIRE(moment_partials && mean_out && var_out, "center_moments: null pointer");
+    const int TT = eks_ensemble_tile_frames();
+    const int ntiles = (T + TT - 1) / TT;
+    const int threads = 128, warps_per_block = threads / 32;
+    const int blocks = (n_seq + warps_per_block - 1) / warps_per_block;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == EKS_F32)
+        moments_finalize_kernel<float><<<blocks, threads, 0, st>>>(moment_partials, n_seq, ntiles, T,
+                                                                   (float*)mean_out, (float*)var_out);
+    else
+        moments_finalize_kernel<double><<<blocks, threads, 0, st>>>(moment_partials, n_seq, ntiles, T,
+                                                                    (double*)mean_out, (double*)var_out);
+    return check_launch("moments_finalize_kernel");
+}

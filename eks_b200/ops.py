@@ -1,0 +1,187 @@
+"""Device-level operators: thin, typed wrappers over the C ABI (include/eks_b200.h).
+
+Every function takes CUDA tensors (allocated by torch: plumbing only), enqueues kernels on the current
+stream and returns device tensors.  Nothing here computes on the CPU.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from eks_b200 import _lib
+from eks_b200._lib import check, dt_code, i32_host, i64_host, lib, ptr, stream_ptr
+
+# plane order of the singlecam / per-camera output block: the reference's 9 output columns
+# (eks/singlecam_smoother.py:231-234, eks/multicam_smoother.py:515-520)
+OUT_COLS = ['x', 'y', 'likelihood', 'x_ens_median', 'y_ens_median', 'x_ens_var', 'y_ens_var',
+            'x_posterior_var', 'y_posterior_var']
+# where the ensemble kernel's (x_avg, y_avg, var_x, var_y, likelihood) land inside that block
+ENS_TO_OUT = [3, 4, 5, 6, 2]
+
+
+@dataclass
+class PlaneView:
+    """(base tensor, seq_stride, chan_off): element (b, o, t) = base.flatten()[b*seq_stride + chan_off[o] + t]."""
+    base: torch.Tensor
+    seq_stride: int
+    chan_off: list
+
+    @property
+    def n_chan(self) -> int:
+        return len(self.chan_off)
+
+
+@dataclass
+class Model:
+    """Per-sequence state-space model (params_nlgssm_for_keypoint, eks/core.py:136-155)."""
+    m0: torch.Tensor            # (B, D)
+    S0: torch.Tensor            # (B, D, D)
+    A: torch.Tensor             # (B, D, D)
+    Q: torch.Tensor             # (B, D, D)
+    C: torch.Tensor | None      # (B, O, D)  linear emission
+    cams: torch.Tensor | None = None  # (ncam, 29) pinhole emission
+
+    @property
+    def B(self) -> int:
+        return self.m0.shape[0]
+
+    @property
+    def D(self) -> int:
+        return self.m0.shape[1]
+
+    @property
+    def ncam(self) -> int:
+        return 0 if self.cams is None else self.cams.shape[0]
+
+    def O(self) -> int:
+        return 2 * self.ncam if self.cams is not None else self.C.shape[1]
+
+    def cast(self, dtype, device) -> 'Model':
+        f = lambda t: None if t is None else t.to(device=device, dtype=dtype).contiguous()
+        return Model(f(self.m0), f(self.S0), f(self.A), f(self.Q), f(self.C), f(self.cams))
+
+
+def _spans(spans, T):
+    if not spans:
+        return 0, None, None
+    s0 = i32_host([a for a, _ in spans])
+    s1 = i32_host([b for _, b in spans])
+    return len(spans), s0, s1
+
+
+def ensemble_stats(raw: torch.Tensor, out: torch.Tensor, sess_stride: int, cam_stride: int, kp_stride: int,
+                   plane_off, avg_mode: str = 'median', var_mode: str = 'confidence_weighted_var',
+                   nan_replacement: float = 1000.0, moments: bool = False):
+    """raw (S,M,V,T,K,3) device tensor -> 5 planes per (s,v,k) written into `out` (see eks_b200.h).
+
+    Returns the per-tile moment partials tensor (or None)."""
+    assert raw.is_cuda and raw.is_contiguous() and raw.dim() == 6 and raw.shape[-1] == 3
+    S, M, V, T, K, _ = raw.shape
+    TT = lib().eks_ensemble_tile_frames()
+    ntiles = (T + TT - 1) // TT
+    partials = torch.empty((S * V * K, ntiles, 4), dtype=torch.float64, device=raw.device) if moments else None
+    po = i64_host(plane_off)
+    vm = 1 if var_mode in ('conf_weighted_var', 'confidence_weighted_var') else 0
+    check(lib().eks_ensemble_stats(ptr(raw), dt_code(raw.dtype), M * V * T * K * 3, S, M, V, T, K,
+                                   int(avg_mode == 'median'), vm, float(nan_replacement), ptr(out),
+                                   dt_code(out.dtype), sess_stride, cam_stride, kp_stride, ptr(po), ptr(partials),
+                                   stream_ptr()), 'eks_ensemble_stats')
+    return partials
+
+
+def center_moments(partials: torch.Tensor, T: int, dtype):
+    n_seq = partials.shape[0]
+    mean = torch.empty((n_seq, 2), dtype=dtype, device=partials.device)
+    var = torch.empty((n_seq, 2), dtype=dtype, device=partials.device)
+    check(lib().eks_center_moments(ptr(partials), n_seq, T, ptr(mean), ptr(var), dt_code(dtype), stream_ptr()),
+          'eks_center_moments')
+    return mean, var
+
+
+def initial_guess(var: PlaneView, B: int, T: int):
+    """-> (guess (B,) float64, s_log0 (B,) real) on device."""
+    dev, dtype = var.base.device, var.base.dtype
+    guess = torch.empty(B, dtype=torch.float64, device=dev)
+    s_log0 = torch.empty(B, dtype=dtype, device=dev)
+    off = i64_host(var.chan_off)
+    check(lib().eks_initial_guess(ptr(var.base), var.seq_stride, ptr(off), dt_code(dtype), B, var.n_chan, T,
+                                  ptr(guess), ptr(s_log0), stream_ptr()), 'eks_initial_guess')
+    return guess, s_log0
+
+
+def const_R_median(var: PlaneView, B: int, T: int, spans=None, min_var: float = 1e-4) -> torch.Tensor:
+    dev, dtype = var.base.device, var.base.dtype
+    O = var.n_chan
+    out = torch.empty((B, O), dtype=dtype, device=dev)
+    nbytes = lib().eks_const_R_median_workspace_bytes(B, O)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    off = i64_host(var.chan_off)
+    n, s0, s1 = _spans(spans, T)
+    check(lib().eks_const_R_median(ptr(var.base), var.seq_stride, ptr(off), dt_code(dtype), B, O, T, n, ptr(s0),
+                                   ptr(s1), float(min_var), ptr(out), ptr(ws), nbytes, stream_ptr()),
+          'eks_const_R_median')
+    return out
+
+
+def nll_grad(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s: torch.Tensor, ymean=None, spans=None):
+    dtype, dev = model.m0.dtype, model.m0.device
+    B, D, O = model.B, model.D, model.O()
+    nll = torch.empty(B, dtype=dtype, device=dev)
+    dn = torch.empty(B, dtype=dtype, device=dev)
+    off = i64_host(y.chan_off)
+    n, s0, s1 = _spans(spans, T)
+    check(lib().eks_nll_grad(dt_code(dtype), B, D, O, T, ptr(model.m0), ptr(model.S0), ptr(model.A), ptr(model.Q),
+                             ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base), y.seq_stride, ptr(off),
+                             ptr(ymean), ptr(Rconst), n, ptr(s0), ptr(s1), ptr(s), ptr(nll), ptr(dn),
+                             stream_ptr()), 'eks_nll_grad')
+    return nll, dn
+
+
+def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0: torch.Tensor, blocks=None,
+               ymean=None, spans=None, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
+               trace_cap: int = 0, force_generic: bool = False):
+    """Device-resident Adam loop.  Returns dict of device tensors: s_log, loss, iters (+trace)."""
+    dtype, dev = model.m0.dtype, model.m0.device
+    B, D, O = model.B, model.D, model.O()
+    if not blocks:
+        blocks = [[k] for k in range(B)]
+    nb = len(blocks)
+    boff = np.zeros(nb + 1, dtype=np.int32)
+    boff[1:] = np.cumsum([len(b) for b in blocks])
+    members = np.asarray([k for b in blocks for k in b], dtype=np.int32)
+    d_boff = torch.from_numpy(boff).to(dev)
+    d_mem = torch.from_numpy(members).to(dev)
+    s_log = torch.empty(nb, dtype=dtype, device=dev)
+    loss = torch.empty(nb, dtype=dtype, device=dev)
+    iters = torch.empty(nb, dtype=torch.int32, device=dev)
+    trace = torch.full((nb, trace_cap, 3), float('nan'), dtype=dtype, device=dev) if trace_cap else None
+    nbytes = lib().eks_optimize_s_workspace_bytes(dt_code(dtype), nb, B, D, O, T)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    off = i64_host(y.chan_off)
+    n, s0, s1 = _spans(spans, T)
+    check(lib().eks_optimize_s(dt_code(dtype), B, D, O, T, ptr(model.m0), ptr(model.S0), ptr(model.A),
+                               ptr(model.Q), ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base), y.seq_stride,
+                               ptr(off), ptr(ymean), ptr(Rconst), n, ptr(s0), ptr(s1), nb, ptr(d_boff), ptr(d_mem),
+                               ptr(s_log0), float(lr), float(s_bounds_log[0]), float(s_bounds_log[1]), float(tol),
+                               int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
+                               int(force_generic), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
+    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
+
+
+def filter_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Tensor, ymean=None):
+    """-> ms (B,T,D), Vs (B,T,D,D) device tensors (reference return layout, eks/core.py:296-297)."""
+    dtype, dev = model.m0.dtype, model.m0.device
+    B, D, O = model.B, model.D, model.O()
+    ms = torch.empty((B, T, D), dtype=dtype, device=dev)
+    Vs = torch.empty((B, T, D, D), dtype=dtype, device=dev)
+    nbytes = lib().eks_filter_smooth_workspace_bytes(dt_code(dtype), B, D, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    yo, vo = i64_host(y.chan_off), i64_host(var.chan_off)
+    check(lib().eks_filter_smooth(dt_code(dtype), B, D, O, T, ptr(model.m0), ptr(model.S0), ptr(model.A),
+                                  ptr(model.Q), ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base),
+                                  y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base), var.seq_stride, ptr(vo),
+                                  ptr(s), ptr(ms), ptr(Vs), ptr(ws), nbytes, stream_ptr()), 'eks_filter_smooth')
+    return ms, Vs

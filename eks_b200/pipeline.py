@@ -1,0 +1,104 @@
+"""Device-resident single-camera EKS pipeline, batched over sessions.
+
+This is the B200-native form of ensemble_kalman_smoother_singlecam (eks/singlecam_smoother.py:105-243):
+the raw seed predictions of S sessions stay on the device as one tensor, every stage is a kernel of
+libeks_b200.so, and the result is ONE output block of frame-major planes
+
+    out[s][k][c][t],  c indexing ops.OUT_COLS = the reference's nine output columns,
+
+so that each input value is read once and each output value written once (data layout).
+Stages: ensemble statistics (+ fused centring moments) -> initial guess / median R -> Adam on log s
+(device-resident loop) -> filter + RTS smoother writing the smoothed / posterior-variance planes.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from eks_b200 import ops
+from eks_b200._lib import lib
+from eks_b200.ops import Model, PlaneView
+
+
+@dataclass
+class SinglecamResult:
+    out: torch.Tensor        # (S, K, 9, T) planes, see ops.OUT_COLS
+    s_finals: torch.Tensor   # (S, K) float64
+    iters: torch.Tensor | None    # (S, K) int32 (None when smooth_param was given)
+    loss: torch.Tensor | None     # (S, K) last evaluated NLL
+    means: torch.Tensor      # (S, K, 2) centring offsets
+
+
+def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, blocks=None,
+                              avg_mode='median', var_mode='confidence_weighted_var', dtype=torch.float32,
+                              lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300, min_R_var=1e-4,
+                              out: torch.Tensor | None = None, force_generic: bool = False,
+                              trace_cap: int = 0) -> SinglecamResult:
+    """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
+
+    spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks."""
+    assert raw.is_cuda and raw.dim() == 6 and raw.shape[2] == 1 and raw.shape[-1] == 3
+    raw = raw.contiguous()
+    S, M, _, T, K, _ = raw.shape
+    dev = raw.device
+    B = S * K
+    if out is None:
+        out = torch.empty((S, K, 9, T), dtype=dtype, device=dev)
+    assert out.shape == (S, K, 9, T) and out.dtype == dtype and out.is_contiguous()
+    # 1) ensemble statistics straight into the output planes + centring moments
+    plane_off = [c * T for c in ops.ENS_TO_OUT]
+    partials = ops.ensemble_stats(raw, out, K * 9 * T, 0, 9 * T, plane_off, avg_mode=avg_mode, var_mode=var_mode,
+                                  moments=True)
+    ymean, yvar = ops.center_moments(partials, T, dtype)          # (B,2) each
+    # 2) model: m0 = 0, S0 = diag(var), A = C = Q = I (singlecam_smoother.py:246-284)
+    eye = torch.eye(2, dtype=dtype, device=dev).expand(B, 2, 2).contiguous()
+    model = Model(torch.zeros((B, 2), dtype=dtype, device=dev), torch.diag_embed(yvar).contiguous(), eye, eye, eye)
+    yv = PlaneView(out, 9 * T, [3 * T, 4 * T])
+    vv = PlaneView(out, 9 * T, [5 * T, 6 * T])
+    iters = loss = None
+    if smooth_param is not None:
+        s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)
+        s_finals = (s.expand(K) if s.dim() == 0 or s.numel() == 1 else s).expand(S, K).contiguous()
+    else:
+        guess, s_log0 = ops.initial_guess(vv, B, T)
+        Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
+        all_blocks = None
+        if blocks:
+            all_blocks = [[s_ * K + k for k in blk] for s_ in range(S) for blk in blocks]
+            covered = {k for blk in blocks for k in blk}
+            all_blocks += [[s_ * K + k] for s_ in range(S) for k in range(K) if k not in covered]
+            g = guess.view(-1)
+            s0 = torch.stack([g[torch.as_tensor(b, device=dev)].mean() for b in all_blocks])
+            s_log0 = torch.log(s0.clamp(1e-6, 1e3)).float().to(dtype)
+        opt = ops.optimize_s(model, yv, T, Rconst, s_log0, blocks=all_blocks, ymean=ymean, spans=spans, lr=lr,
+                             s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
+                             force_generic=force_generic)
+        s_blk = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1]))
+        if all_blocks is None:
+            s_finals = s_blk.view(S, K)
+            iters, loss = opt['iters'].view(S, K), opt['loss'].view(S, K)
+        else:
+            s_flat = torch.empty(B, dtype=torch.float64, device=dev)
+            it_flat = torch.empty(B, dtype=torch.int32, device=dev)
+            lo_flat = torch.empty(B, dtype=dtype, device=dev)
+            for j, b in enumerate(all_blocks):
+                idx = torch.as_tensor(b, device=dev)
+                s_flat[idx] = s_blk[j]
+                it_flat[idx] = opt['iters'][j]
+                lo_flat[idx] = opt['loss'][j]
+            s_finals, iters, loss = s_flat.view(S, K), it_flat.view(S, K), lo_flat.view(S, K)
+        singlecam_smooth_sessions.last_opt = opt
+    # 3) final filter + RTS smoother (time-varying R_t), outputs into planes 0,1,7,8
+    s_dev = s_finals.reshape(B).to(dtype)
+    if not force_generic and hasattr(lib(), 'eks_diag_smooth'):
+        ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T])
+    else:
+        ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev, ymean=ymean)
+        o = out.view(B, 9, T)
+        o[:, 0, :] = ms[:, :, 0] + ymean[:, 0:1]
+        o[:, 1, :] = ms[:, :, 1] + ymean[:, 1:2]
+        o[:, 7, :] = Vs[:, :, 0, 0]
+        o[:, 8, :] = Vs[:, :, 1, 1]
+    return SinglecamResult(out, s_finals, iters, loss, ymean.view(S, K, 2))

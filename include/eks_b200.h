@@ -1,0 +1,122 @@
+/* eks_b200.h -- C ABI of libeks_b200.so: the B200-native (sm_100a) EKS smoothing hot path.
+ *
+ * The reference (paninski-lab/eks v4.6.2) has no native/FFI layer: its seam is the Python call
+ * signatures of eks/core.py.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in _host or the comment says "host".
+ *  - dtype arguments take EKS_F32 / EKS_F64 ("real" below = that type).  Production precision of the
+ *    reference is float32; float64 is the parity mode.
+ *  - The caller owns every buffer; the library never allocates or frees caller memory.  Scratch is
+ *    passed as (workspace, workspace_bytes); sizes come from the *_workspace_bytes queries.
+ *  - All calls only ENQUEUE work on `stream` (a cudaStream_t cast to void*) and return immediately;
+ *    the caller synchronises.  No global state.
+ *  - Return value: 0 ok; <0 invalid argument; >0 a cudaError_t.  eks_last_error() returns a
+ *    thread-local message for the last non-zero return.
+ *  - Per-frame data are "channel planes": element (sequence b, channel o, frame t) of a view
+ *    (base, seq_stride, chan_off[O]) lives at base[b*seq_stride + chan_off[o] + t], i.e. frames are
+ *    contiguous (frame-major), strides/offsets are in ELEMENTS.  chan_off is a HOST array.
+ */
+#ifndef EKS_B200_H
+#define EKS_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKS_F32 0
+#define EKS_F64 1
+#define EKS_MAX_CHAN 16    /* max observation channels (2 x cameras) */
+#define EKS_MAX_STATE 6    /* max latent dimension */
+#define EKS_CAM_STRIDE 29  /* R(9 row-major) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 */
+
+const char* eks_last_error(void);
+int eks_version(void);
+
+/* ---- ensemble statistics: replaces eks.core.ensemble / compute_stats (eks/core.py:25-101) --------
+ * raw: [n_sessions][M][V][T][K][3] in the reference MarkerArray layout (eks/marker_array.py:15-30),
+ * raw_dtype f32|f64 (values are cast to out_dtype before any arithmetic, as core.py:90-92 does).
+ * Writes 5 planes [x_avg, y_avg, var_x, var_y, likelihood] per (session, camera, keypoint) at
+ *   out[s*sess_stride + v*cam_stride + k*kp_stride + plane_off[f] + t].
+ * moment_partials (nullable): [n_sessions*V*K][ceil(T/eks_ensemble_tile_frames())][4] doubles
+ * receiving per-tile sums (x, y, x^2, y^2) of the averaged coordinates, consumed by eks_center_moments.
+ * avg_median: 1 median | 0 mean.  var_mode: 1 confidence_weighted_var | 0 var. */
+int eks_ensemble_tile_frames(void);
+int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_sess_stride, int n_sessions, int M, int V,
+                       int T, int K, int avg_median, int var_mode, double nan_replacement, void* out, int out_dtype,
+                       long long sess_stride, long long cam_stride, long long kp_stride,
+                       const long long* plane_off_host, double* moment_partials, void* stream);
+
+/* ---- centring moments: the all-frames case of center_predictions (eks/utils.py:293-365 with
+ * quantile 100, eks/singlecam_smoother.py:155-157) and S0 = diag(nanvar) (singlecam_smoother.py:262-266).
+ * mean_out/var_out: [n_seq][2] real. */
+int eks_center_moments(const double* moment_partials, int n_seq, int T, void* mean_out, void* var_out, int dtype,
+                       void* stream);
+
+/* ---- initial guess: compute_initial_guesses + caller fallback (eks/core.py:104-133, :233-236) and
+ * the float32 log seed (core.py:612-613, :622).  var view = raw ensemble variances (unclipped).
+ * guess_out: [B] double.  s_log0_out (nullable): [B] real. */
+int eks_initial_guess(const void* var_base, long long seq_stride, const long long* chan_off_host, int dtype, int B,
+                      int O, int T, double* guess_out, void* s_log0_out, void* stream);
+
+/* ---- constant R for the loss path: constant_R_from_timevarying on cropped frames
+ * (eks/core.py:599-602, :702-709; crop_frames eks/utils.py:235-290).  Exact nanmedian over the
+ * frames in the spans (n_spans == 0: all frames; spans sorted, non-overlapping, host arrays),
+ * floored at max(1e-12, min_var).  Rconst_out: [B][O] real. */
+size_t eks_const_R_median_workspace_bytes(int B, int O);
+int eks_const_R_median(const void* var_base, long long seq_stride, const long long* chan_off_host, int dtype, int B,
+                       int O, int T, int n_spans, const int* span_start_host, const int* span_end_host,
+                       double min_var, void* Rconst_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- state-space model shared by the calls below (params_nlgssm_for_keypoint, eks/core.py:136-155)
+ * Per-sequence arrays, real, row-major: m0 [B][D], S0 [B][D][D], A [B][D][D], Q [B][D][D] (scaled by s
+ * inside), C [B][O][D] (linear emission; ignored when ncam > 0).  ncam > 0 selects the calibrated
+ * pinhole emission of make_projection_from_camgroup (eks/multicam_smoother.py:806-885): cams is
+ * [ncam][EKS_CAM_STRIDE] real, O must equal 2*ncam and D 3.
+ * Observations: y view (+ optional per-sequence offset ymean [B][O] subtracted on load, i.e. the
+ * centring of center_predictions) and either Rconst [B][O] or a var view (clipped at 1e-12 on load,
+ * build_R_from_vars eks/utils.py:368-377). */
+
+/* NLL of the EKF filter and d NLL / d s for each sequence at s[b]: the loss of
+ * _vmap_optimize_singletons._optimize_one.loss (eks/core.py:640-650) incl. the non-finite -> 1e12 rule.
+ * Frames restricted to the spans (n_spans == 0: all).  nll_out, dnll_ds_out: [B] real. */
+int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A, const void* Q,
+                 const void* C, int ncam, const void* cams, const void* y_base, long long y_seq_stride,
+                 const long long* y_chan_off_host, const void* ymean, const void* Rconst, int n_spans,
+                 const int* span_start_host, const int* span_end_host, const void* s, void* nll_out,
+                 void* dnll_ds_out, void* stream);
+
+/* Device-resident Adam loop on log s: replaces optimize_smooth_param / _vmap_optimize_singletons and
+ * the block slow path (eks/core.py:306-401, 403-559, 562-699).  Block j owns members
+ * members[block_off[j] .. block_off[j+1]) (sequence indices; device int arrays) and shares one s;
+ * loss = sum of member NLLs.  s_log0: [n_blocks] real (float32-rounded seed).  Outputs [n_blocks]:
+ * s_log_out (real, the value AFTER the last update, core.py:675), last_loss_out (real), iters_out (int).
+ * The caller forms s = exp(clip(s_log, lo, hi)) (core.py:694).  trace (nullable): [n_blocks][trace_cap][3]
+ * real rows (s_log, loss, lr*grad) per iteration. */
+size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T);
+int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
+                   const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
+                   long long y_seq_stride, const long long* y_chan_off_host, const void* ymean, const void* Rconst,
+                   int n_spans, const int* span_start_host, const int* span_end_host, int n_blocks,
+                   const int* block_off, const int* members, const void* s_log0, double lr, double s_log_lo,
+                   double s_log_hi, double tol, int safety_cap, void* s_log_out, void* last_loss_out,
+                   int* iters_out, void* trace, int trace_cap, int force_generic, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Final pass: EKF filter + RTS smoother over ALL frames with time-varying diagonal R_t from the var
+ * view: replaces vmap(_smooth_one) / extended_kalman_smoother (eks/core.py:274-295).
+ * s: [B] real.  ms_out [B][T][D], Vs_out [B][T][D][D] real (reference return layout, core.py:296-297). */
+size_t eks_filter_smooth_workspace_bytes(int dtype, int B, int D, int T);
+int eks_filter_smooth(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
+                      const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
+                      long long y_seq_stride, const long long* y_chan_off_host, const void* ymean,
+                      const void* var_base, long long var_seq_stride, const long long* var_chan_off_host,
+                      const void* s, void* ms_out, void* Vs_out, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKS_B200_H */

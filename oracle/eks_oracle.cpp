@@ -468,13 +468,13 @@ inline void ensemble(const R* raw, int M, int V, int T, int K, int avg_median, i
                     if (n == 0) { avg = NaN; var = NaN; }
                     else {
                         R mean = sum / R(n);
+                        R ss = 0;  // nanvar, ddof 0, accumulated in seed order
+                        for (int i = 0; i < n; ++i) ss += (buf[i] - mean) * (buf[i] - mean);
+                        var = ss / R(n);
                         if (avg_median) {
                             std::sort(buf, buf + n);
                             avg = (n & 1) ? buf[n / 2] : (buf[n / 2 - 1] * R(0.5) + buf[n / 2] * R(0.5));
                         } else avg = mean;
-                        R ss = 0;
-                        for (int i = 0; i < n; ++i) ss += (buf[i] - mean) * (buf[i] - mean);
-                        var = ss / R(n);
                     }
                     if (M == 1) var = R(1) / std::max(mean_conf, R(1e-5));
                     else if (var_mode == 1) var = var / mean_conf;
