@@ -33,19 +33,32 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _obj_stale(src_path: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    hdrs.append(os.path.join(HERE, '..', 'include', 'eks_b200.h'))
+    return any(os.path.getmtime(d) > t for d in [src_path, *hdrs])
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile stale translation units (in parallel) and relink libeks_b200.so."""
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
+        src_path = os.path.join(CSRC, src)
         obj = os.path.join(LIB_DIR, src.replace('.cu', '.o'))
-        cmd = [_nvcc(), *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        objs.append(obj)
+        if not force and not _obj_stale(src_path, obj):
+            continue
+        cmd = [_nvcc(), *NVCC_FLAGS, '-c', src_path, '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:

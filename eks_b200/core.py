@@ -113,6 +113,21 @@ def constant_R_from_timevarying(R_t_np: np.ndarray, min_var: float = 1e-4) -> np
 
 
 # ----------------------------------------------------------------------------- device staging
+def _is_diag_model(m0s, S0s, As, Cs, Qs, h_fn) -> bool:
+    """True for the decoupled single-camera structure: D == O == 2, diagonal A, C, Q, S0 (checked on
+    the host copies of the tiny parameter arrays before upload)."""
+    if h_fn is not None or isinstance(S0s, torch.Tensor) and S0s.is_cuda:
+        return False
+    try:
+        S0, A, C, Q = (np.asarray(x, dtype=np.float64) for x in (S0s, As, Cs, Qs))
+    except Exception:
+        return False
+    if A.shape[-2:] != (2, 2) or C.shape[-2:] != (2, 2):
+        return False
+    off = lambda x: np.all(x[..., 0, 1] == 0) and np.all(x[..., 1, 0] == 0)
+    return bool(off(S0) and off(A) and off(C) and off(Q))
+
+
 def _stage(ys, m0s, S0s, As, Cs, Qs, h_fn, dev, dtype):
     """(K,T,O) observations -> frame-major planes [K][O][T] + per-sequence model on the device."""
     y = _to_device(ys, dtype, dev)
@@ -171,6 +186,7 @@ def run_kalman_smoother(
     dev = require_cuda()
     dtype = get_precision()
     model, yv, K, T, O = _stage(ys, m0s, S0s, As, Cs, Qs, h_fn, dev, dtype)
+    structure = ops.STRUCT_DIAG if _is_diag_model(m0s, S0s, As, Cs, Qs, h_fn) else ops.STRUCT_GENERAL
     if not blocks:
         blocks = [[k] for k in range(K)]
     logger.debug(f'correlated keypoint blocks: {blocks}')
@@ -194,7 +210,7 @@ def run_kalman_smoother(
         spans = normalize_spans(T, s_frames)
         guess, s_log0 = ops.initial_guess(vv, K, T)
         _optimize_on_device(model, yv, vv, T, spans, blocks, guess, s_log0, lr, s_bounds_log, tol, safety_cap,
-                            1e-4, s_finals)
+                            1e-4, s_finals, structure=structure)
         logger.debug(f'[profile]   optimize_smooth_param: {time.perf_counter() - t0:.3f}s')
 
     t0 = time.perf_counter()
@@ -206,7 +222,7 @@ def run_kalman_smoother(
 
 
 def _optimize_on_device(model, yv, vv, T, spans, blocks, guess, s_log0, lr, s_bounds_log, tol, safety_cap,
-                        min_R_var, s_finals, trace_cap=0):
+                        min_R_var, s_finals, trace_cap=0, structure=0):
     K = model.B
     Rconst = ops.const_R_median(vv, K, T, spans=spans, min_var=min_R_var)
     if all(len(b) == 1 for b in blocks) and [b[0] for b in blocks] == list(range(K)):
@@ -216,7 +232,8 @@ def _optimize_on_device(model, yv, vv, T, spans, blocks, guess, s_log0, lr, s_bo
         s0_host = np.array([np.log(np.clip(np.mean([g[k] for k in b]), 1e-6, 1e3)) for b in blocks])
         s0 = torch.as_tensor(s0_host.astype(np.float32), device=guess.device).to(model.m0.dtype)
     opt = ops.optimize_s(model, yv, T, Rconst, s0, blocks=blocks, spans=spans, lr=lr, s_bounds_log=s_bounds_log,
-                         tol=tol, safety_cap=safety_cap, trace_cap=trace_cap)
+                         tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
+                         structure=structure if (spans is None or len(spans) == 1) else ops.STRUCT_GENERAL)
     s_out, iters, loss = _finalize_s(opt, K, s_bounds_log)
     covered = sorted(k for b in blocks for k in b)
     for k in covered:
@@ -243,6 +260,7 @@ def optimize_smooth_param(
     dev = require_cuda()
     dtype = get_precision()
     model, yv, K, T, O = _stage(ys, m0s, S0s, As, Cs, Qs, h_fn_combined, dev, dtype)
+    structure = ops.STRUCT_DIAG if _is_diag_model(m0s, S0s, As, Cs, Qs, h_fn_combined) else ops.STRUCT_GENERAL
     if not blocks:
         blocks = [[k] for k in range(K)]
     R = _to_device(Rs, dtype, dev)
@@ -253,4 +271,4 @@ def optimize_smooth_param(
     s0 = np.log(np.clip(np.asarray(s_guess_per_k, dtype=np.float64), 1e-6, 1e3)).astype(np.float32)
     s_log0 = torch.as_tensor(s0, device=dev).to(dtype)
     _optimize_on_device(model, yv, vv, T, spans, blocks, guess, s_log0, lr, s_bounds_log, tol, safety_cap,
-                        min_R_var, s_finals)
+                        min_R_var, s_finals, structure=structure)

@@ -308,11 +308,24 @@ extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void*
                               int n_spans, const int* s0, const int* s1, int n_blocks, const int* block_off,
                               const int* members, const void* s_log0, double lr, double lo, double hi, double tol,
                               int cap, void* s_log_out, void* last_loss_out, int* iters_out, void* trace,
-                              int trace_cap, int force_generic, void* workspace, size_t workspace_bytes,
+                              int trace_cap, int model_structure, void* workspace, size_t workspace_bytes,
                               void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     (void)workspace; (void)workspace_bytes;
-    (void)force_generic;
+    // model_structure == EKS_STRUCT_DIAG: the caller asserts D == O == 2 with diagonal A, C, Q, S0
+    // (single-camera model) -> time-parallel persistent kernel (diag.cu); one contiguous span only
+    if (model_structure == EKS_STRUCT_DIAG && D == 2 && O == 2 && ncam == 0 && n_spans <= 1) {
+        EKS_REQUIRE(y_base && y_off && Rconst && block_off && members && s_log0 && s_log_out && last_loss_out &&
+                        iters_out && m0 && S0 && A && Q && C, "optimize_s: null pointer");
+        int t_begin = 0, n = T;
+        if (n_spans == 1) {
+            EKS_REQUIRE(s0[0] >= 0 && s1[0] <= T && s0[0] < s1[0], "bad span 0");
+            t_begin = s0[0]; n = s1[0] - s0[0];
+        }
+        return diag_optimize(dtype, B, T, m0, S0, A, Q, C, y_base, y_seq_stride, y_off, ymean, Rconst, t_begin, n,
+                             n_blocks, block_off, members, s_log0, lr, lo, hi, tol, cap, s_log_out, last_loss_out,
+                             iters_out, trace, trace_cap, st);
+    }
     if (dtype == EKS_F32)
         return optimize_impl<float>(B, D, O, T, m0, S0, A, Q, C, ncam, cams, y_base, y_seq_stride, y_off, ymean,
                                     Rconst, n_spans, s0, s1, n_blocks, block_off, members, s_log0, lr, lo, hi, tol,

@@ -20,6 +20,14 @@ OUT_COLS = ['x', 'y', 'likelihood', 'x_ens_median', 'y_ens_median', 'x_ens_var',
             'x_posterior_var', 'y_posterior_var']
 # where the ensemble kernel's (x_avg, y_avg, var_x, var_y, likelihood) land inside that block
 ENS_TO_OUT = [3, 4, 5, 6, 2]
+STRUCT_GENERAL, STRUCT_DIAG = 0, 1
+# number of kernels of libeks_b200.so launched through this module (bench.py reports it)
+LAUNCH_COUNT = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += n
 
 
 @dataclass
@@ -89,6 +97,7 @@ def ensemble_stats(raw: torch.Tensor, out: torch.Tensor, sess_stride: int, cam_s
                                    int(avg_mode == 'median'), vm, float(nan_replacement), ptr(out),
                                    dt_code(out.dtype), sess_stride, cam_stride, kp_stride, ptr(po), ptr(partials),
                                    stream_ptr()), 'eks_ensemble_stats')
+    _count(1)
     return partials
 
 
@@ -98,6 +107,7 @@ def center_moments(partials: torch.Tensor, T: int, dtype):
     var = torch.empty((n_seq, 2), dtype=dtype, device=partials.device)
     check(lib().eks_center_moments(ptr(partials), n_seq, T, ptr(mean), ptr(var), dt_code(dtype), stream_ptr()),
           'eks_center_moments')
+    _count(1)
     return mean, var
 
 
@@ -109,6 +119,7 @@ def initial_guess(var: PlaneView, B: int, T: int):
     off = i64_host(var.chan_off)
     check(lib().eks_initial_guess(ptr(var.base), var.seq_stride, ptr(off), dt_code(dtype), B, var.n_chan, T,
                                   ptr(guess), ptr(s_log0), stream_ptr()), 'eks_initial_guess')
+    _count(1)
     return guess, s_log0
 
 
@@ -123,6 +134,7 @@ def const_R_median(var: PlaneView, B: int, T: int, spans=None, min_var: float = 
     check(lib().eks_const_R_median(ptr(var.base), var.seq_stride, ptr(off), dt_code(dtype), B, O, T, n, ptr(s0),
                                    ptr(s1), float(min_var), ptr(out), ptr(ws), nbytes, stream_ptr()),
           'eks_const_R_median')
+    _count(6 if dtype == torch.float32 else 12)  # (histogram + scan) per radix level
     return out
 
 
@@ -137,12 +149,13 @@ def nll_grad(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s: torch.
                              ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base), y.seq_stride, ptr(off),
                              ptr(ymean), ptr(Rconst), n, ptr(s0), ptr(s1), ptr(s), ptr(nll), ptr(dn),
                              stream_ptr()), 'eks_nll_grad')
+    _count(1)
     return nll, dn
 
 
 def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0: torch.Tensor, blocks=None,
                ymean=None, spans=None, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
-               trace_cap: int = 0, force_generic: bool = False):
+               trace_cap: int = 0, structure: int = 0):
     """Device-resident Adam loop.  Returns dict of device tensors: s_log, loss, iters (+trace)."""
     dtype, dev = model.m0.dtype, model.m0.device
     B, D, O = model.B, model.D, model.O()
@@ -167,7 +180,8 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                ptr(off), ptr(ymean), ptr(Rconst), n, ptr(s0), ptr(s1), nb, ptr(d_boff), ptr(d_mem),
                                ptr(s_log0), float(lr), float(s_bounds_log[0]), float(s_bounds_log[1]), float(tol),
                                int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
-                               int(force_generic), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
+                               int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
+    _count(1)
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
 
@@ -184,4 +198,24 @@ def filter_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.T
                                   ptr(model.Q), ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base),
                                   y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base), var.seq_stride, ptr(vo),
                                   ptr(s), ptr(ms), ptr(Vs), ptr(ws), nbytes, stream_ptr()), 'eks_filter_smooth')
+    _count(1)
     return ms, Vs
+
+
+def diag_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Tensor, ymean, out: torch.Tensor,
+                out_seq_stride: int, out_off):
+    """Decoupled (singlecam) final pass: filter + RTS + reprojection straight into the output planes.
+
+    out_off: element offsets (within a sequence's block) of [x plane, y plane, x post-var plane,
+    y post-var plane]."""
+    dtype, dev = model.m0.dtype, model.m0.device
+    B = model.B
+    nbytes = lib().eks_diag_smooth_workspace_bytes(dt_code(dtype), B, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    yo, vo, oo = i64_host(y.chan_off), i64_host(var.chan_off), i64_host(out_off)
+    check(lib().eks_diag_smooth(dt_code(dtype), B, T, ptr(model.m0), ptr(model.S0), ptr(model.A), ptr(model.Q),
+                                ptr(model.C), ptr(y.base), y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base),
+                                var.seq_stride, ptr(vo), ptr(s), ptr(out), out_seq_stride, ptr(oo), ptr(ws), nbytes,
+                                stream_ptr()), 'eks_diag_smooth')
+    _count(2)
+    return ws

@@ -35,11 +35,26 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
                               avg_mode='median', var_mode='confidence_weighted_var', dtype=torch.float32,
                               lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300, min_R_var=1e-4,
                               out: torch.Tensor | None = None, force_generic: bool = False,
-                              trace_cap: int = 0) -> SinglecamResult:
+                              trace_cap: int = 0, timers: dict | None = None) -> SinglecamResult:
     """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
 
     spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks."""
     assert raw.is_cuda and raw.dim() == 6 and raw.shape[2] == 1 and raw.shape[-1] == 3
+
+    class _Stage:  # optional CUDA-event bracket per stage on the launching stream (bench.py)
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            if timers is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *exc):
+            if timers is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                timers.setdefault(self.name, []).append((self.e0, e1))
     raw = raw.contiguous()
     S, M, _, T, K, _ = raw.shape
     dev = raw.device
@@ -49,9 +64,11 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
     assert out.shape == (S, K, 9, T) and out.dtype == dtype and out.is_contiguous()
     # 1) ensemble statistics straight into the output planes + centring moments
     plane_off = [c * T for c in ops.ENS_TO_OUT]
-    partials = ops.ensemble_stats(raw, out, K * 9 * T, 0, 9 * T, plane_off, avg_mode=avg_mode, var_mode=var_mode,
-                                  moments=True)
-    ymean, yvar = ops.center_moments(partials, T, dtype)          # (B,2) each
+    with _Stage('ensemble'):
+        partials = ops.ensemble_stats(raw, out, K * 9 * T, 0, 9 * T, plane_off, avg_mode=avg_mode,
+                                      var_mode=var_mode, moments=True)
+    with _Stage('center_moments'):
+        ymean, yvar = ops.center_moments(partials, T, dtype)      # (B,2) each
     # 2) model: m0 = 0, S0 = diag(var), A = C = Q = I (singlecam_smoother.py:246-284)
     eye = torch.eye(2, dtype=dtype, device=dev).expand(B, 2, 2).contiguous()
     model = Model(torch.zeros((B, 2), dtype=dtype, device=dev), torch.diag_embed(yvar).contiguous(), eye, eye, eye)
@@ -62,8 +79,10 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
         s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)
         s_finals = (s.expand(K) if s.dim() == 0 or s.numel() == 1 else s).expand(S, K).contiguous()
     else:
-        guess, s_log0 = ops.initial_guess(vv, B, T)
-        Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
+        with _Stage('initial_guess'):
+            guess, s_log0 = ops.initial_guess(vv, B, T)
+        with _Stage('const_R_median'):
+            Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
         all_blocks = None
         if blocks:
             all_blocks = [[s_ * K + k for k in blk] for s_ in range(S) for blk in blocks]
@@ -72,9 +91,10 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
             g = guess.view(-1)
             s0 = torch.stack([g[torch.as_tensor(b, device=dev)].mean() for b in all_blocks])
             s_log0 = torch.log(s0.clamp(1e-6, 1e3)).float().to(dtype)
-        opt = ops.optimize_s(model, yv, T, Rconst, s_log0, blocks=all_blocks, ymean=ymean, spans=spans, lr=lr,
-                             s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
-                             force_generic=force_generic)
+        with _Stage('optimize_s'):
+            opt = ops.optimize_s(model, yv, T, Rconst, s_log0, blocks=all_blocks, ymean=ymean, spans=spans, lr=lr,
+                                 s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
+                                 structure=ops.STRUCT_GENERAL if force_generic else ops.STRUCT_DIAG)
         s_blk = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1]))
         if all_blocks is None:
             s_finals = s_blk.view(S, K)
@@ -93,7 +113,8 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
     # 3) final filter + RTS smoother (time-varying R_t), outputs into planes 0,1,7,8
     s_dev = s_finals.reshape(B).to(dtype)
     if not force_generic and hasattr(lib(), 'eks_diag_smooth'):
-        ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T])
+        with _Stage('filter_smooth'):
+            ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T])
     else:
         ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev, ymean=ymean)
         o = out.view(B, 9, T)

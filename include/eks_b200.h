@@ -30,6 +30,8 @@ extern "C" {
 #define EKS_F64 1
 #define EKS_MAX_CHAN 16    /* max observation channels (2 x cameras) */
 #define EKS_MAX_STATE 6    /* max latent dimension */
+#define EKS_STRUCT_GENERAL 0 /* model_structure: no assumption */
+#define EKS_STRUCT_DIAG 1    /* caller asserts D == O == 2 and diagonal A, C, Q, S0 (singlecam model) */
 #define EKS_CAM_STRIDE 29  /* R(9 row-major) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 */
 
 const char* eks_last_error(void);
@@ -94,7 +96,8 @@ int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const vo
  * loss = sum of member NLLs.  s_log0: [n_blocks] real (float32-rounded seed).  Outputs [n_blocks]:
  * s_log_out (real, the value AFTER the last update, core.py:675), last_loss_out (real), iters_out (int).
  * The caller forms s = exp(clip(s_log, lo, hi)) (core.py:694).  trace (nullable): [n_blocks][trace_cap][3]
- * real rows (s_log, loss, lr*grad) per iteration. */
+ * real rows (s_log, loss, lr*grad) per iteration.  model_structure: EKS_STRUCT_GENERAL (one block per thread,
+ * sequential in time) or EKS_STRUCT_DIAG (persistent CTA per block, exact time-parallel scan; needs <= 1 span). */
 size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T);
 int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
                    const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
@@ -102,7 +105,7 @@ int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const 
                    int n_spans, const int* span_start_host, const int* span_end_host, int n_blocks,
                    const int* block_off, const int* members, const void* s_log0, double lr, double s_log_lo,
                    double s_log_hi, double tol, int safety_cap, void* s_log_out, void* last_loss_out,
-                   int* iters_out, void* trace, int trace_cap, int force_generic, void* workspace,
+                   int* iters_out, void* trace, int trace_cap, int model_structure, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* Final pass: EKF filter + RTS smoother over ALL frames with time-varying diagonal R_t from the var
