@@ -29,11 +29,11 @@ class EksB200Error(RuntimeError):
 _SIGS = {
     'eks_last_error': (ctypes.c_char_p, []),
     'eks_version': (c_int, []),
-    'eks_ensemble_tile_frames': (c_int, []),
+    'eks_ensemble_tile_frames': (c_int, [c_int, c_int, c_int, c_int]),
     'eks_ensemble_stats': (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_double, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_void_p,
                                    c_void_p, c_void_p]),
-    'eks_center_moments': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'eks_center_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'eks_initial_guess': (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
     'eks_const_R_median_workspace_bytes': (c_size_t, [c_int, c_int]),

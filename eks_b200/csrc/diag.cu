@@ -49,28 +49,47 @@ struct ChanConst {
     P aW, bW;        // Phi^(32 L)
 };
 
+// shared-memory tile ring: every thread's chunk is CHUNK_BYTES of frames, padded to PAD_BYTES so that the
+// per-thread 16-byte reads are bank-conflict free (stride 144 B = 9 x 16 B)
+constexpr int OPT_CHUNK_BYTES = 128;
+constexpr int OPT_PAD_BYTES = 144;
+constexpr int OPT_STAGES = 3;
+constexpr int OPT_STAGE_BYTES = DIAG_NT * OPT_PAD_BYTES;
+
+// ---- device-resident optimiser state -----------------------------------------------------------------
 template <class P>
-struct DiagShared {
-    ChanConst<P> ch[2];
-    P z_tile[2][2][2];        // [buf][chan][m,dm]
-    P agg[2][DIAG_NW][2][2];  // [buf][warp][chan][m,dm]
-    double tsum[2][5];        // transient sums per channel: logS, dlogS, e2 iS, e2 diS, cc e dm iS
-    double red[DIAG_NW][4];
-    int t_c;
-    int done;
-    P s, dsdlog;
-    double loss_acc, grad_acc;
+struct BlockState {          // one per block (group of sequences sharing one s)
     AdamState<P> adam;
+    P s, dsdlog;
+    int done;
+    int pad;
+};
+template <class P>
+struct ChanState {           // one per (sequence, channel): produced by diag_adam_kernel for the current s
+    ChanConst<P> k;
+    P z0[2];                 // (m, dm) at frame t_c
+    double tsum[5];          // transient sums: logS, dlogS, e2 iS, e2 diS, cc e dm iS
+    int t_c;                 // first steady-state frame (multiple of 4)
+    int warm;                // frames after which a zero carry-in is forgotten below rounding
+};
+
+template <class P>
+struct OptShared {
+    ChanConst<P> ch;
+    P z_tile[2][2];        // [buf][m,dm]
+    P agg[2][DIAG_NW][2];  // [buf][warp][m,dm]
+    double red[DIAG_NW][2];
 };
 
 template <class P>
 struct DiagOptArgs {
-    int B, t_begin, n;
+    int B, t_begin, n, nseg;
     const P *m0, *S0, *A, *Q, *C;
     PlaneView y;
     const P *ymean, *Rconst;
     int n_blocks;
     const int *block_off, *members;
+    const int* seq_block;        // [B] block index of every sequence
     const P* s_log0;
     P lr, lo, hi, tol;
     int cap;
@@ -78,15 +97,65 @@ struct DiagOptArgs {
     int* iters_out;
     P* trace;
     int trace_cap;
+    BlockState<P>* bstate;       // [n_blocks]
+    ChanState<P>* cstate;        // [B][2]
+    double* partials;            // [B][2][nseg][2]  (sum e^2, sum e dm) per segment
+    int* n_active;
 };
 
-// ---- transient: sequential scalar filter with s-sensitivities until the variance recursion has
-// converged (or the sequence ends).  Executed by lane c (< 2) of warp 0; all 32 lanes vote.
+__device__ inline void cp_async_16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ inline void cp_async_8(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ inline void cp_async_4(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Issue the asynchronous copy of frames [t0, t0 + DIAG_NT*L) of one plane into a ring stage; frames
+// outside [e_min, n) are zero-filled without touching memory.  Consecutive lanes fetch consecutive
+// 16-byte granules (fully coalesced 512-byte requests); the destination is the padded per-thread chunk
+// layout (conflict-free 16-byte reads at stride 144 B).
 template <class P>
-__device__ void diag_transient(const DiagOptArgs<P>& a, int b, P s, DiagShared<P>& sh) {
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < 2;
-    const int c = act ? lane : 0;
+__device__ inline void opt_issue_tile(unsigned char* stage, const P* __restrict__ plane, int t0, int e_min, int n,
+                                      bool vec) {
+    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
+    if (vec) {
+        constexpr int EPG = 16 / (int)sizeof(P);       // elements per 16-byte granule
+        constexpr int GPC = OPT_CHUNK_BYTES / 16;      // granules per chunk
+#pragma unroll
+        for (int i = 0; i < GPC; ++i) {
+            const int v = i * DIAG_NT + threadIdx.x;
+            const int j = v / GPC, q = v - j * GPC;
+            const int e = t0 + j * L + q * EPG;
+            int valid = max(0, min(EPG, n - e)) * (int)sizeof(P);
+            if (e < e_min) valid = 0;                  // e_min is chunk aligned: whole granules
+            cp_async_16(stage + j * OPT_PAD_BYTES + q * 16, plane + (valid > 0 ? e : 0), valid);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < L; ++i) {
+            const int v = i * DIAG_NT + threadIdx.x;
+            const int j = v / L, q = v - j * L;
+            const int e = t0 + j * L + q;
+            const int valid = (e < n && e >= e_min) ? (int)sizeof(P) : 0;
+            if (sizeof(P) == 4) cp_async_4(stage + j * OPT_PAD_BYTES + q * 4, plane + (valid > 0 ? e : 0), valid);
+            else cp_async_8(stage + j * OPT_PAD_BYTES + q * 8, plane + (valid > 0 ? e : 0), valid);
+        }
+    }
+}
+
+// ---- transient: sequential scalar filter with s-sensitivities until the variance recursion has reached
+// its floating-point fixed point (or the sequence ends).  One thread per (sequence, channel).
+template <class P>
+__device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanState<P>& out) {
     const P av = a.A[(long long)b * 4 + c * 3], cc = a.C[(long long)b * 4 + c * 3], Qc = a.Q[(long long)b * 4 + c * 3];
     const P r = a.Rconst[(long long)b * 2 + c];
     const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
@@ -94,25 +163,28 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, P s, DiagShared<P
     P Pv = a.S0[(long long)b * 4 + c * 3], dP = P(0), m = a.m0[(long long)b * 2 + c], dm = P(0);
     double sl = 0, sdl = 0, se = 0, sde = 0, sg = 0;
     const P tol = P(8) * DiagTraits<P>::eps();
+    const P BOOST = P(1e-9);
     P prevdP_chg = P(INFINITY), prevP_chg = P(INFINITY);
     int stall = 0;
     int t = 0;
     const int n = a.n;
-    P S, iS, dS, diS, K, dK;
+    P S, iS, dS, diS, K, dK, alpha;
     while (true) {
         S = cc * cc * Pv + r;
         iS = P(1) / S;
+        const P iSb = P(1) / (S + BOOST);       // psd_solve boosts the gain solve only
         dS = cc * cc * dP;
         diS = -dS * iS * iS;
-        K = Pv * cc / (S + P(1e-9));
-        dK = cc * (dP * iS + Pv * diS);
-        const P Pf = Pv - K * K * S;
+        K = Pv * cc * iSb;
+        dK = cc * (dP * iSb - Pv * dS * iSb * iSb);
+        // P_f = P - K S K and alpha = a (1 - K c), written without cancellation (identical algebra)
+        const P Pf = Pv * iSb * (r + BOOST * (P(1) + cc * K));
         const P dPf = r * (dP * iS + Pv * diS);
         const P Pn = av * av * Pf + s * Qc;
         const P dPn = av * av * dPf + Qc;
+        alpha = av * iSb * (r + BOOST);
         // convergence of (P, dP): relative step below tol * (1 - rho), rho = alpha^2 the contraction
         // factor, or the iteration has hit its rounding floor (steps no longer shrinking)
-        const P alpha = av * (P(1) - K * cc);
         const P gap = P(1) - alpha * alpha;
         const P chgP = fabs(Pn - Pv), chgd = fabs(dPn - dP);
         bool conv = (chgP <= tol * gap * fabs(Pn)) && (chgd <= tol * gap * fabs(dPn));
@@ -120,278 +192,361 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, P s, DiagShared<P
         if (stall >= 24) conv = true;
         prevP_chg = chgP;
         prevdP_chg = chgd;
-        const unsigned all_conv = __all_sync(0xffffffffu, conv || !act);
-        if ((all_conv && (t & 3) == 0) || t >= n) break;
-        if (act) {
-            const P y = yp[t] - mean;
-            const P e = y - cc * m;
-            sl += (double)log_(S);
-            sdl += (double)(dS * iS);
-            se += (double)(e * e * iS);
-            sde += (double)(e * e * diS);
-            sg += (double)(cc * e * dm * iS);
-            const P mf = m + K * e;
-            const P dmf = dm + dK * e - K * cc * dm;
-            m = av * mf;
-            dm = av * dmf;
-            Pv = Pn;
-            dP = dPn;
-        }
+        if ((conv && (t & 3) == 0) || t >= n) break;
+        const P y = yp[t] - mean;
+        const P e = y - cc * m;
+        sl += (double)log_(S);
+        sdl += (double)(dS * iS);
+        se += (double)(e * e * iS);
+        sde += (double)(e * e * diS);
+        sg += (double)(cc * e * dm * iS);
+        const P mf = m + K * e;
+        const P dmf = dm + dK * e - K * cc * dm;
+        m = av * mf;
+        dm = av * dmf;
+        Pv = Pn;
+        dP = dPn;
         ++t;
     }
-    if (act) {
-        ChanConst<P>& k = sh.ch[c];
-        k.a = av; k.cc = cc;
-        k.alpha = av * (P(1) - K * cc);
-        k.beta = av * K;
-        k.dalpha = -av * cc * dK;
-        k.dbeta = av * dK;
-        k.iS = iS; k.diS = diS;
-        k.logS = log_(S);
-        k.dlogS = dS * iS;
-        constexpr int L = DiagTraits<P>::L;
-        P aL = pow_(k.alpha, P(L));
-        P bL = P(L) * pow_(k.alpha, P(L - 1)) * k.dalpha;
+    ChanConst<P>& k = out.k;
+    k.a = av; k.cc = cc;
+    k.alpha = alpha;
+    k.beta = av * K;
+    k.dalpha = -av * cc * dK;
+    k.dbeta = av * dK;
+    k.iS = iS; k.diS = diS;
+    k.logS = log_(S);
+    k.dlogS = dS * iS;
+    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
+    P aL = pow_(k.alpha, P(L));
+    P bL = P(L) * pow_(k.alpha, P(L - 1)) * k.dalpha;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            k.aL[i] = aL; k.bL[i] = bL;
-            bL = P(2) * aL * bL;
-            aL = aL * aL;
-        }
-        k.aW = aL; k.bW = bL;
-        sh.z_tile[0][c][0] = m;
-        sh.z_tile[0][c][1] = dm;
-        sh.tsum[c][0] = sl; sh.tsum[c][1] = sdl; sh.tsum[c][2] = se; sh.tsum[c][3] = sde; sh.tsum[c][4] = sg;
-        if (c == 0) sh.t_c = t;
+    for (int i = 0; i < 5; ++i) {
+        k.aL[i] = aL; k.bL[i] = bL;
+        bL = P(2) * aL * bL;
+        aL = aL * aL;
     }
+    k.aW = aL; k.bW = bL;
+    out.z0[0] = m;
+    out.z0[1] = dm;
+    out.tsum[0] = sl; out.tsum[1] = sdl; out.tsum[2] = se; out.tsum[3] = sde; out.tsum[4] = sg;
+    out.t_c = t;
+    // frames after which the response to the state at their start has decayed below rounding:
+    // alpha^W (and W alpha^(W-1)) negligible against 1 -> W = ln(eps_w) / ln(alpha), eps_w far below eps
+    const double la = log((double)fmin(fmax(alpha, P(1e-30)), P(1)));
+    const double lw = (sizeof(P) == 4) ? -32.0 : -64.0;  // ln(1.3e-14) / ln(1.6e-28)
+    double w = (la < -1e-12) ? lw / la : 2.0e9;
+    w = fmin(w + 64.0, 2.0e9);
+    out.warm = (int)w;
 }
 
-template <class P, int L>
-__device__ inline void load_chunk(const P* __restrict__ p, bool vec, int nvalid, P mean, P (&out)[L]) {
-    using V = typename DiagTraits<P>::vec_t;
-    constexpr int VW = DiagTraits<P>::VW;
-    if (vec && nvalid == L) {
-        const V* pv = reinterpret_cast<const V*>(p);
-#pragma unroll
-        for (int i = 0; i < L / VW; ++i) {
-            const V v = __ldg(pv + i);
-            const P* e = reinterpret_cast<const P*>(&v);
-#pragma unroll
-            for (int q = 0; q < VW; ++q) out[i * VW + q] = e[q] - mean;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < L; ++i) out[i] = (i < nvalid) ? (__ldg(p + i) - mean) : P(0);
-    }
-}
-
-// One tile of DIAG_NT * L frames for both channels.  E2/G are this thread's fp64 accumulators.
-template <class P, bool FULL>
-__device__ inline void diag_tile(const P* __restrict__ y0, const P* __restrict__ y1, P mean0, P mean1, bool vec,
-                                 int t0, int n, int buf, DiagShared<P>& sh, const P (&a_lane)[2],
-                                 const P (&b_lane)[2], double (&E2)[2], double (&G)[2]) {
-    constexpr int L = DiagTraits<P>::L;
+// One tile of DIAG_NT * L frames of one channel; y[] is the thread's register-resident chunk (already
+// centred).  E2/G are this thread's fp64 accumulators.  ACC = false: warm-up tile (carry only).
+template <class P, int L, bool FULL, bool ACC>
+__device__ inline void diag_tile(const P (&y)[L], int nvalid, int buf, OptShared<P>& sh, P a_lane, P b_lane,
+                                 double& E2, double& G) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int start = t0 + threadIdx.x * L;
-    const int nvalid = FULL ? L : max(0, min(L, n - start));
-    P y[2][L];
-    load_chunk<P, L>(y0 + start, vec, nvalid, mean0, y[0]);
-    load_chunk<P, L>(y1 + start, vec, nvalid, mean1, y[1]);
-    P zm[2], zd[2];
+    const ChanConst<P>& k = sh.ch;
+    const P alpha = k.alpha;
     // phase 1: zero-state response of the chunk.  U = sum alpha^(L-1-i) y_i, W = dU/dalpha
+    P U = P(0), W = P(0);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const P alpha = sh.ch[c].alpha;
-        P U = P(0), W = P(0);
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            W = fma(alpha, W, U);
-            U = fma(alpha, U, y[c][i]);
-        }
-        zm[c] = sh.ch[c].beta * U;
-        zd[c] = sh.ch[c].dbeta * U + sh.ch[c].beta * sh.ch[c].dalpha * W;
+    for (int i = 0; i < L; ++i) {
+        W = fma(alpha, W, U);
+        U = fma(alpha, U, y[i]);
     }
+    P zm = k.beta * U;
+    P zd = k.dbeta * U + k.beta * k.dalpha * W;
     // warp inclusive scan with the closed-form powers of Phi
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int d = 1 << k;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const P pm = __shfl_up_sync(0xffffffffu, zm[c], d);
-            const P pd = __shfl_up_sync(0xffffffffu, zd[c], d);
-            if (lane >= d) {
-                zd[c] = fma(sh.ch[c].aL[k], pd, fma(sh.ch[c].bL[k], pm, zd[c]));
-                zm[c] = fma(sh.ch[c].aL[k], pm, zm[c]);
-            }
+    for (int q = 0; q < 5; ++q) {
+        const int d = 1 << q;
+        const P pm = __shfl_up_sync(0xffffffffu, zm, d);
+        const P pd = __shfl_up_sync(0xffffffffu, zd, d);
+        if (lane >= d) {
+            zd = fma(k.aL[q], pd, fma(k.bL[q], pm, zd));
+            zm = fma(k.aL[q], pm, zm);
         }
     }
-    if (lane == 31) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) { sh.agg[buf][warp][c][0] = zm[c]; sh.agg[buf][warp][c][1] = zd[c]; }
-    }
-    P em[2], ed[2];  // exclusive prefix inside the warp
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        em[c] = __shfl_up_sync(0xffffffffu, zm[c], 1);
-        ed[c] = __shfl_up_sync(0xffffffffu, zd[c], 1);
-        if (lane == 0) { em[c] = P(0); ed[c] = P(0); }
-    }
+    if (lane == 31) { sh.agg[buf][warp][0] = zm; sh.agg[buf][warp][1] = zd; }
+    P em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
+    if (lane == 0) { em = P(0); ed = P(0); }
     __syncthreads();
     // carry at the start of this warp: tile carry pushed through the preceding warps' aggregates
-    P m_in[2], d_in[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        P cm = sh.z_tile[buf][c][0], cd = sh.z_tile[buf][c][1];
-        const P aW = sh.ch[c].aW, bW = sh.ch[c].bW;
-        for (int w = 0; w < warp; ++w) {
-            const P nm = fma(aW, cm, sh.agg[buf][w][c][0]);
-            cd = fma(aW, cd, fma(bW, cm, sh.agg[buf][w][c][1]));
-            cm = nm;
-        }
-        m_in[c] = fma(a_lane[c], cm, em[c]);
-        d_in[c] = fma(a_lane[c], cd, fma(b_lane[c], cm, ed[c]));
-        if (warp == DIAG_NW - 1 && lane == 0) {  // carry for the next tile (other buffer)
-            const P nm = fma(aW, cm, sh.agg[buf][warp][c][0]);
-            const P nd = fma(aW, cd, fma(bW, cm, sh.agg[buf][warp][c][1]));
-            sh.z_tile[buf ^ 1][c][0] = nm;
-            sh.z_tile[buf ^ 1][c][1] = nd;
-        }
+    P cm = sh.z_tile[buf][0], cd = sh.z_tile[buf][1];
+    const P aW = k.aW, bW = k.bW;
+    for (int w = 0; w < warp; ++w) {
+        const P nm = fma(aW, cm, sh.agg[buf][w][0]);
+        cd = fma(aW, cd, fma(bW, cm, sh.agg[buf][w][1]));
+        cm = nm;
     }
+    if (warp == DIAG_NW - 1 && lane == 0) {  // carry for the next tile (other buffer)
+        sh.z_tile[buf ^ 1][0] = fma(aW, cm, sh.agg[buf][warp][0]);
+        sh.z_tile[buf ^ 1][1] = fma(aW, cd, fma(bW, cm, sh.agg[buf][warp][1]));
+    }
+    if (!ACC) return;
+    P m = fma(a_lane, cm, em);
+    P dm = fma(a_lane, cd, fma(b_lane, cm, ed));
     // phase 3: innovations with the true carry-in; e = y - cc m, m' = a m + beta e, dm' = alpha dm + dbeta e
+    const P beta = k.beta, dbeta = k.dbeta, av = k.a, cc = k.cc;
+    P e2 = P(0), g = P(0);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const P alpha = sh.ch[c].alpha, beta = sh.ch[c].beta, dbeta = sh.ch[c].dbeta, av = sh.ch[c].a,
-                cc = sh.ch[c].cc;
-        P m = m_in[c], dm = d_in[c], e2 = P(0), g = P(0);
-#pragma unroll
-        for (int i = 0; i < L; ++i) {
-            const P e = fma(-cc, m, y[c][i]);
-            if (FULL || i < nvalid) {
-                e2 = fma(e, e, e2);
-                g = fma(e, dm, g);
-            }
-            dm = fma(alpha, dm, dbeta * e);
-            m = fma(beta, e, av * m);
+    for (int i = 0; i < L; ++i) {
+        const P e = fma(-cc, m, y[i]);
+        if (FULL || i < nvalid) {
+            e2 = fma(e, e, e2);
+            g = fma(e, dm, g);
         }
-        E2[c] += (double)e2;
-        G[c] += (double)g;
+        dm = fma(alpha, dm, dbeta * e);
+        m = fma(beta, e, av * m);
+    }
+    E2 += (double)e2;
+    G += (double)g;
+}
+
+// ---- kernel A: one NLL(+d/ds) evaluation.  grid = (nseg, 2 * B): CTA (k, 2b+c) handles segment k of
+// channel c of sequence b.  A segment is a run of tiles; it starts from the exact state at t_c (segment 0
+// or slow forgetting) or from a zero state `warm` frames earlier, which is exact to rounding because the
+// steady-state filter forgets its initial state geometrically (alpha^warm < 1e-14 / 1e-28).
+template <class P>
+__global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
+    __shared__ OptShared<P> sh;
+    extern __shared__ __align__(16) unsigned char ring[];
+    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
+    constexpr int TILE = DIAG_NT * L;
+    using V = typename DiagTraits<P>::vec_t;
+    constexpr int VW = DiagTraits<P>::VW;
+    const int seg = blockIdx.x, b = blockIdx.y >> 1, c = blockIdx.y & 1;
+    const int blk = a.seq_block[b];
+    if (blk < 0 || a.bstate[blk].done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
+    double* part = a.partials + (((long long)b * 2 + c) * a.nseg + seg) * 2;
+    const int t_c = cs.t_c;
+    const int ntile = (a.n - t_c + TILE - 1) / TILE;
+    const int tps = (ntile + a.nseg - 1) / a.nseg;
+    const int tile_lo = seg * tps, tile_hi = min(ntile, tile_lo + tps);
+    if (tile_lo >= tile_hi) {
+        if (threadIdx.x == 0) { part[0] = 0.0; part[1] = 0.0; }
+        return;
+    }
+    // warm-up: whole chunks, starting `warm` frames before the segment
+    const int warm_chunks = (cs.warm + L - 1) / L;
+    long long e_min_ll = (long long)t_c + (long long)tile_lo * TILE - (long long)warm_chunks * L;
+    int first_tile, e_min;
+    bool exact_start;
+    if (tile_lo == 0 || e_min_ll <= (long long)t_c) {
+        first_tile = 0; e_min = 0; exact_start = true;
+    } else {
+        e_min = (int)e_min_ll;
+        first_tile = (e_min - t_c) / TILE;
+        exact_start = false;
+    }
+    if (threadIdx.x == 0) {
+        sh.ch = cs.k;
+        sh.z_tile[0][0] = exact_start ? cs.z0[0] : P(0);
+        sh.z_tile[0][1] = exact_start ? cs.z0[1] : P(0);
+    }
+    __syncthreads();
+    const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
+    const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
+    const bool vec = (reinterpret_cast<uintptr_t>(yc + t_c) & 15) == 0;
+    // per-thread powers Phi^(L lane) for folding the warp carry into the exclusive prefix
+    const P alpha = sh.ch.alpha;
+    const P nl = P(L * lane);
+    const P a_lane = lane == 0 ? P(1) : pow_(alpha, nl);
+    const P b_lane = lane == 0 ? P(0) : nl * pow_(alpha, nl - P(1)) * sh.ch.dalpha;
+    double E2 = 0, G = 0;
+    const int nt = tile_hi - first_tile;
+#pragma unroll
+    for (int st = 0; st < OPT_STAGES - 1; ++st) {
+        if (st < nt) opt_issue_tile<P>(ring + st * OPT_STAGE_BYTES, yc, t_c + (first_tile + st) * TILE, e_min, a.n, vec);
+        cp_async_commit();
+    }
+    int buf = 0;
+    for (int it = 0; it < nt; ++it, buf ^= 1) {
+        cp_async_wait<OPT_STAGES - 2>();
+        __syncthreads();  // tile `it` has landed for everyone; the stage read in iteration it-1 is free again
+        const int nx = it + OPT_STAGES - 1;
+        if (nx < nt)
+            opt_issue_tile<P>(ring + (nx % OPT_STAGES) * OPT_STAGE_BYTES, yc, t_c + (first_tile + nx) * TILE, e_min, a.n, vec);
+        cp_async_commit();
+        const unsigned char* mine = ring + (it % OPT_STAGES) * OPT_STAGE_BYTES + threadIdx.x * OPT_PAD_BYTES;
+        const int t0 = t_c + (first_tile + it) * TILE;
+        const int cstart = t0 + (int)threadIdx.x * L;
+        // centred observations; masked (warm-up prefix / beyond the end) frames stay exactly zero
+        P y[L];
+#pragma unroll
+        for (int i = 0; i < L / VW; ++i) {
+            const V v = *reinterpret_cast<const V*>(mine + i * 16);
+            const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) {
+                const int fr = cstart + i * VW + q;
+                y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
+            }
+        }
+        const bool acc = (first_tile + it) >= tile_lo;
+        if (!acc) diag_tile<P, L, true, false>(y, L, buf, sh, a_lane, b_lane, E2, G);
+        else if (t0 + TILE <= a.n) diag_tile<P, L, true, true>(y, L, buf, sh, a_lane, b_lane, E2, G);
+        else diag_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), buf, sh, a_lane, b_lane, E2, G);
+    }
+    cp_async_wait<0>();
+    E2 = warp_sum(E2);
+    G = warp_sum(G);
+    if (lane == 0) { sh.red[warp][0] = E2; sh.red[warp][1] = G; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double te = 0, tg = 0;
+        for (int w = 0; w < DIAG_NW; ++w) { te += sh.red[w][0]; tg += sh.red[w][1]; }
+        part[0] = te;
+        part[1] = tg;
     }
 }
 
+// ---- kernel B: one warp per block.  Consumes the partial sums of the previous evaluation (Adam step,
+// stop rule of eks/core.py:654-681), then prepares the next one (new s; per-channel transient + constants).
 template <class P>
-__global__ void __launch_bounds__(DIAG_NT, 2) diag_optimize_kernel(const __grid_constant__ DiagOptArgs<P> a) {
-    __shared__ DiagShared<P> sh;
-    constexpr int L = DiagTraits<P>::L;
-    constexpr int TILE = DIAG_NT * L;
-    const int j = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        adam_init(sh.adam, a.s_log0[j]);
-        sh.done = (a.cap <= 0);
-    }
-    __syncthreads();
-    const double HALF_LOG2PI = 0.91893853320467274178;
-    while (true) {
-        if (threadIdx.x == 0 && !sh.done) {
-            P dsdlog;
-            sh.s = adam_current_s(sh.adam, a.lo, a.hi, &dsdlog);
-            sh.dsdlog = dsdlog;
-            sh.loss_acc = 0.0;
-            sh.grad_acc = 0.0;
+__global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ DiagOptArgs<P> a, int iter) {
+    const int j = blockIdx.x, lane = threadIdx.x;
+    BlockState<P>& bs = a.bstate[j];
+    const int m_lo = a.block_off[j], m_hi = a.block_off[j + 1];
+    if (iter == 0) {
+        if (lane == 0) {
+            adam_init(bs.adam, a.s_log0[j]);
+            bs.done = (a.cap <= 0);
+            if (bs.done) {
+                a.s_log_out[j] = bs.adam.s_log; a.last_loss_out[j] = bs.adam.prev; a.iters_out[j] = 0;
+                atomicSub(a.n_active, 1);
+            }
         }
-        __syncthreads();
-        if (sh.done) break;
-        const P s = sh.s;
-        for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
-            const int b = a.members[mi];
-            if (warp == 0) diag_transient<P>(a, b, s, sh);
-            __syncthreads();
-            const int t_c = sh.t_c;
-            const P* ybase = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin;
-            const P* y0 = ybase + a.y.chan_off[0];
-            const P* y1 = ybase + a.y.chan_off[1];
-            const P mean0 = a.ymean ? a.ymean[(long long)b * 2] : P(0);
-            const P mean1 = a.ymean ? a.ymean[(long long)b * 2 + 1] : P(0);
-            const bool vec = ((reinterpret_cast<uintptr_t>(y0 + t_c) | reinterpret_cast<uintptr_t>(y1 + t_c)) & 15) == 0;
-            // per-thread powers Phi^(L lane) for folding the warp carry into the exclusive prefix
-            P a_lane[2], b_lane[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const P alpha = sh.ch[c].alpha;
-                const P nl = P(L * lane);
-                a_lane[c] = lane == 0 ? P(1) : pow_(alpha, nl);
-                b_lane[c] = lane == 0 ? P(0) : nl * pow_(alpha, nl - P(1)) * sh.ch[c].dalpha;
-            }
-            double E2[2] = {0, 0}, G[2] = {0, 0};
-            int buf = 0;
-            for (int t0 = t_c; t0 < a.n; t0 += TILE, buf ^= 1) {
-                if (t0 + TILE <= a.n) diag_tile<P, true>(y0, y1, mean0, mean1, vec, t0, a.n, buf, sh, a_lane, b_lane, E2, G);
-                else diag_tile<P, false>(y0, y1, mean0, mean1, vec, t0, a.n, buf, sh, a_lane, b_lane, E2, G);
-            }
-            // deterministic block reduction of the four fp64 sums
-            double v4[4] = {E2[0], E2[1], G[0], G[1]};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v4[q] = warp_sum(v4[q]);
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) sh.red[warp][q] = v4[q];
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double tot[4] = {0, 0, 0, 0};
-                for (int w = 0; w < DIAG_NW; ++w)
-                    for (int q = 0; q < 4; ++q) tot[q] += sh.red[w][q];
-                const double nB = (double)(a.n - t_c);
+    } else {
+        if (bs.done) return;
+        if (lane == 0) {
+            const double HALF_LOG2PI = 0.91893853320467274178;
+            P loss = P(0), grad = P(0);
+            for (int mi = m_lo; mi < m_hi; ++mi) {
+                const int b = a.members[mi];
                 double nll = 0, dnll = 0;
                 for (int c = 0; c < 2; ++c) {
-                    const ChanConst<P>& k = sh.ch[c];
-                    nll += (double)a.n * HALF_LOG2PI + 0.5 * sh.tsum[c][0] + 0.5 * sh.tsum[c][2] +
-                           0.5 * nB * (double)k.logS + 0.5 * (double)k.iS * tot[c];
-                    dnll += 0.5 * sh.tsum[c][1] + 0.5 * sh.tsum[c][3] - sh.tsum[c][4] + 0.5 * nB * (double)k.dlogS +
-                            0.5 * (double)k.diS * tot[c] - (double)k.cc * (double)k.iS * tot[2 + c];
+                    const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
+                    const double* part = a.partials + ((long long)b * 2 + c) * a.nseg * 2;
+                    double te = 0, tg = 0;
+                    for (int q = 0; q < a.nseg; ++q) { te += part[2 * q]; tg += part[2 * q + 1]; }
+                    const double nB = (double)(a.n - cs.t_c);
+                    const ChanConst<P>& k = cs.k;
+                    nll += (double)a.n * HALF_LOG2PI + 0.5 * cs.tsum[0] + 0.5 * cs.tsum[2] + 0.5 * nB * (double)k.logS +
+                           0.5 * (double)k.iS * te;
+                    dnll += 0.5 * cs.tsum[1] + 0.5 * cs.tsum[3] - cs.tsum[4] + 0.5 * nB * (double)k.dlogS +
+                            0.5 * (double)k.diS * te - (double)k.cc * (double)k.iS * tg;
                 }
                 P v = (P)nll, g = (P)dnll;
                 if (!isfinite(nll) || !isfinite((double)v)) { v = P(1e12); g = P(0); }  // core.py:650
-                sh.loss_acc += (double)v;
-                sh.grad_acc += (double)(g * sh.dsdlog);
+                loss += v;
+                grad += g * bs.dsdlog;
             }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            const P loss = (P)sh.loss_acc, g = (P)sh.grad_acc;
-            if (a.trace && sh.adam.iters < a.trace_cap) {
-                P* tr = a.trace + ((long long)j * a.trace_cap + sh.adam.iters) * 3;
-                tr[0] = sh.adam.s_log; tr[1] = loss; tr[2] = g * a.lr;
+            if (a.trace && bs.adam.iters < a.trace_cap) {
+                P* tr = a.trace + ((long long)j * a.trace_cap + bs.adam.iters) * 3;
+                tr[0] = bs.adam.s_log; tr[1] = loss; tr[2] = grad * a.lr;
             }
-            adam_step(sh.adam, loss, g, a.lr, a.tol, a.cap);
-            sh.done = sh.adam.done;
+            adam_step(bs.adam, loss, grad, a.lr, a.tol, a.cap);
+            if (bs.adam.done) {
+                bs.done = 1;
+                a.s_log_out[j] = bs.adam.s_log;
+                a.last_loss_out[j] = bs.adam.prev;
+                a.iters_out[j] = bs.adam.iters;
+                atomicSub(a.n_active, 1);
+            }
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        a.s_log_out[j] = sh.adam.s_log;
-        a.last_loss_out[j] = sh.adam.prev;
-        a.iters_out[j] = sh.adam.iters;
+    __syncwarp();
+    if (bs.done) return;
+    if (lane == 0) {
+        P dsdlog;
+        bs.s = adam_current_s(bs.adam, a.lo, a.hi, &dsdlog);
+        bs.dsdlog = dsdlog;
+    }
+    __syncwarp();
+    const P s = bs.s;
+    const int npair = (m_hi - m_lo) * 2;  // (member, channel) pairs, one per lane
+    for (int p0 = 0; p0 < npair; p0 += 32) {
+        const int p = p0 + lane;
+        if (p < npair) {
+            const int b = a.members[m_lo + (p >> 1)], c = p & 1;
+            diag_transient<P>(a, b, c, s, a.cstate[(long long)b * 2 + c]);
+        }
     }
 }
 
-size_t diag_optimize_workspace_bytes(int dtype, int n_blocks) {
-    (void)dtype; (void)n_blocks;
-    return 16;
+// sequence -> block index table + active-block counter
+__global__ void diag_seq_block_kernel(int n_blocks, const int* __restrict__ block_off, const int* __restrict__ members,
+                                      int* __restrict__ seq_block, int* __restrict__ n_active) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *n_active = n_blocks;
+    if (j >= n_blocks) return;
+    for (int mi = block_off[j]; mi < block_off[j + 1]; ++mi) seq_block[members[mi]] = j;
+}
+
+static int diag_nseg(int dtype, int n) {
+    const int L = OPT_CHUNK_BYTES / (dtype == EKS_F32 ? 4 : 8);
+    const int ntile = (n + DIAG_NT * L - 1) / (DIAG_NT * L);
+    int nseg = ntile / 12;  // >= 12 tiles per segment keeps the one-tile warm-up below ~3% of the traffic
+    if (nseg < 1) nseg = 1;
+    if (nseg > 16) nseg = 16;
+    return nseg;
+}
+
+size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
+    const size_t real = dtype == EKS_F32 ? 4 : 8;
+    (void)real;
+    const int nseg = diag_nseg(dtype, T);
+    size_t bytes = 256;
+    bytes += (size_t)n_blocks * 128;                   // BlockState
+    bytes += (size_t)B * 2 * 512;                      // ChanState (generous bound)
+    bytes += (size_t)B * 2 * nseg * 2 * sizeof(double);
+    bytes += (size_t)B * sizeof(int) + 256;
+    return bytes;
 }
 
 template <class P>
-static int diag_optimize_launch(const DiagOptArgs<P>& a, cudaStream_t st) {
-    diag_optimize_kernel<P><<<a.n_blocks, DIAG_NT, 0, st>>>(a);
-    return check_launch("diag_optimize_kernel");
+static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspace_bytes, int dtype, int T,
+                             cudaStream_t st) {
+    static_assert(sizeof(BlockState<P>) <= 128 && sizeof(ChanState<P>) <= 512, "workspace bound");
+    a.nseg = diag_nseg(dtype, a.n);
+    EKS_REQUIRE(workspace && workspace_bytes >= diag_optimize_workspace_bytes(dtype, a.n_blocks, a.B, T),
+                "optimize_s: workspace too small");
+    unsigned char* w = (unsigned char*)workspace;
+    a.n_active = (int*)w; w += 256;
+    a.bstate = (BlockState<P>*)w; w += (size_t)a.n_blocks * 128;
+    a.cstate = (ChanState<P>*)w; w += (size_t)a.B * 2 * 512;
+    a.partials = (double*)w; w += (size_t)a.B * 2 * a.nseg * 2 * sizeof(double);
+    int* seq_block = (int*)w;
+    a.seq_block = seq_block;
+    const int smem = OPT_STAGES * OPT_STAGE_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(diag_nll_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        set_error("diag_nll_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);  // -1: sequence belongs to no block
+    diag_seq_block_kernel<<<(a.n_blocks + 127) / 128, 128, 0, st>>>(a.n_blocks, a.block_off, a.members, seq_block,
+                                                                    a.n_active);
+    // Every evaluation is one (tiny) Adam/transient launch + one streaming launch.  The loop is unrolled
+    // on the stream without host synchronisation: finished blocks make their CTAs exit immediately.
+    const dim3 grid(a.nseg, 2 * a.B);
+    for (int it = 0; it <= a.cap; ++it) {
+        diag_adam_kernel<P><<<a.n_blocks, 32, 0, st>>>(a, it);
+        if (it < a.cap) diag_nll_kernel<P><<<grid, DIAG_NT, smem, st>>>(a);
+    }
+    return check_launch("diag optimise kernels");
 }
 
 int diag_optimize(int dtype, int B, int T, const void* m0, const void* S0, const void* A, const void* Q, const void* C,
                   const void* y_base, long long y_seq_stride, const long long* y_off, const void* ymean,
                   const void* Rconst, int t_begin, int n, int n_blocks, const int* block_off, const int* members,
                   const void* s_log0, double lr, double lo, double hi, double tol, int cap, void* s_log_out,
-                  void* last_loss_out, int* iters_out, void* trace, int trace_cap, cudaStream_t st) {
-    (void)T;
+                  void* last_loss_out, int* iters_out, void* trace, int trace_cap, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
 #define EKS_FILL(PT)                                                                                        \
     DiagOptArgs<PT> a;                                                                                      \
     a.B = B; a.t_begin = t_begin; a.n = n;                                                                  \
@@ -403,7 +558,7 @@ int diag_optimize(int dtype, int B, int T, const void* m0, const void* S0, const
     a.lr = (PT)lr; a.lo = (PT)lo; a.hi = (PT)hi; a.tol = (PT)tol; a.cap = cap;                              \
     a.s_log_out = (PT*)s_log_out; a.last_loss_out = (PT*)last_loss_out; a.iters_out = iters_out;            \
     a.trace = (PT*)trace; a.trace_cap = trace_cap;                                                          \
-    return diag_optimize_launch<PT>(a, st);
+    return diag_optimize_run<PT>(a, workspace, workspace_bytes, dtype, T, st);
     if (dtype == EKS_F32) { EKS_FILL(float) }
     EKS_FILL(double)
 #undef EKS_FILL
@@ -476,6 +631,25 @@ __device__ inline Mob<P> mob_shfl_up(const Mob<P>& m, int d) {
     o.c = __shfl_up_sync(0xffffffffu, m.c, d);
     o.d = __shfl_up_sync(0xffffffffu, m.d, d);
     return o;
+}
+
+template <class P, int L>
+__device__ inline void load_chunk(const P* __restrict__ p, bool vec, int nvalid, P mean, P (&out)[L]) {
+    using V = typename DiagTraits<P>::vec_t;
+    constexpr int VW = DiagTraits<P>::VW;
+    if (vec && nvalid == L) {
+        const V* pv = reinterpret_cast<const V*>(p);
+#pragma unroll
+        for (int i = 0; i < L / VW; ++i) {
+            const V v = __ldg(pv + i);
+            const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) out[i * VW + q] = e[q] - mean;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; ++i) out[i] = (i < nvalid) ? (__ldg(p + i) - mean) : P(0);
+    }
 }
 
 template <class P, int L>
@@ -572,10 +746,13 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_filter_kernel(const __grid_co
         P Aacc = P(1), bacc = P(0);
 #pragma unroll
         for (int i = 0; i < L; ++i) {
+            // gain with the 1e-9 boost of psd_solve; P_f = P - K S K and 1 - K c in their cancellation-free
+            // (algebraically identical) forms
             const P S = fma(c2, Pv, r[i]);
-            const P K = Pv * cc / (S + P(1e-9));
-            const P Pfi = Pv - K * K * S;
-            const P alpha = av * (P(1) - K * cc), beta = av * K;
+            const P iSb = P(1) / (S + P(1e-9));
+            const P K = Pv * cc * iSb;
+            const P Pfi = Pv * iSb * (r[i] + P(1e-9) * (P(1) + cc * K));
+            const P alpha = av * iSb * (r[i] + P(1e-9)), beta = av * K;
             bacc = fma(alpha, bacc, beta * y[i]);
             Aacc *= alpha;
             r[i] = K;      // r is dead from here on: reuse its registers for the gain
@@ -648,13 +825,18 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_rts_kernel(const __grid_const
 #pragma unroll
         for (int ii = 0; ii < L; ++ii) {
             const int i = L - 1 - ii;
+            // G = a P_f / (S_p + 1e-9);  offsets (1 - G a) m_f and P_f - G^2 S_p in cancellation-free form
             const P Sp = fma(a2, Pf[i], q);
-            P g = av * Pf[i] / (Sp + P(1e-9));
-            if (start + i >= a.T - 1) g = P(0);  // last frame: smoothed = filtered; padding frames: inert
+            const P iSpb = P(1) / (Sp + P(1e-9));
+            P g = av * Pf[i] * iSpb;
+            P om = mf[i] * iSpb * (q + P(1e-9));
+            P oP = Pf[i] * iSpb * (q + P(1e-9) * (P(1) + av * g));
+            if (start + i >= a.T - 1) { g = P(0); om = mf[i]; oP = Pf[i]; }  // last frame: smoothed = filtered
             G[i] = g;
-            const P g2 = g * g;
-            bm = fma(g, bm, fma(-g * av, mf[i], mf[i]));
-            bP = fma(g2, bP, fma(-g2, Sp, Pf[i]));
+            mf[i] = om;   // keep the offsets: phase 3 reuses them
+            Pf[i] = oP;
+            bm = fma(g, bm, om);
+            bP = fma(g * g, bP, oP);
             Ag *= g;
         }
 #pragma unroll
@@ -690,10 +872,9 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_rts_kernel(const __grid_const
 #pragma unroll
         for (int ii = 0; ii < L; ++ii) {
             const int i = L - 1 - ii;
-            const P g = G[i], g2 = g * g;
-            const P Sp = fma(a2, Pf[i], q);
-            ms = fma(g, ms, fma(-g * av, mf[i], mf[i]));
-            Ps = fma(g2, Ps, fma(-g2, Sp, Pf[i]));
+            const P g = G[i];
+            ms = fma(g, ms, mf[i]);
+            Ps = fma(g * g, Ps, Pf[i]);
             mf[i] = fma(cc, ms, mean);  // x = C m + mean   (singlecam_smoother.py:190-197)
             Pf[i] = c2 * Ps;            // diag(C V C^T)    (singlecam_smoother.py:191, 210-211)
         }

@@ -167,6 +167,112 @@ __global__ void __launch_bounds__(256) ensemble_kernel(const Tin* __restrict__ r
     }
 }
 
+// ---- staged variant (default): the tile's raw values are brought into shared memory with fully
+// coalesced 16-byte cp.async requests (one contiguous chunk per seed), then every (cell, coordinate) work
+// item reads its M values from shared memory.  Compared with direct strided loads this cuts the L1
+// wavefronts per request from 12 sectors to 4 and halves the register footprint.
+__device__ inline void ens_cp_async_16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+template <int BYTES>
+__device__ inline void ens_cp_async_small(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(gmem), "n"(BYTES) : "memory");
+}
+
+template <class Tin, class P, int MAXM>
+__global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restrict__ raw, long long raw_sess_stride,
+                                                              int M, int V, int T, int K, int avg_median,
+                                                              int var_mode, P nan_repl, P* __restrict__ out, EnsOut eo,
+                                                              double* __restrict__ partials, int TT) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile_idx = blockIdx.x, v = blockIdx.y, sess = blockIdx.z;
+    const int t0 = tile_idx * TT;
+    const int nt = min(TT, T - t0);
+    const int ld = TT + 1;
+    const int chunk = TT * K * 3;                     // elements per seed in a full tile
+    const int chunk_pad = (chunk * (int)sizeof(Tin) + 15) / 16 * 16;  // bytes, keeps every seed 16-B aligned
+    Tin* stage = reinterpret_cast<Tin*>(smem_raw);
+    P* tile = reinterpret_cast<P*>(smem_raw + (size_t)M * chunk_pad);  // [5][K][TT+1]
+    const Tin* base = raw + (long long)sess * raw_sess_stride;
+    const long long m_stride = (long long)V * T * K * 3;
+    const long long off0 = ((long long)v * T + t0) * K * 3;
+    const int nel = nt * K * 3;
+    constexpr int EPG = 16 / (int)sizeof(Tin);
+    const bool vec = ((reinterpret_cast<uintptr_t>(base + off0) & 15) == 0) && ((m_stride * (int)sizeof(Tin)) % 16 == 0);
+    const int ngran = vec ? nel / EPG : 0;
+    for (int m = 0; m < M; ++m) {
+        const Tin* src = base + (long long)m * m_stride + off0;
+        unsigned char* dst = smem_raw + (size_t)m * chunk_pad;
+        for (int g = threadIdx.x; g < ngran; g += blockDim.x) ens_cp_async_16(dst + g * 16, src + g * EPG);
+        for (int e = ngran * EPG + threadIdx.x; e < nel; e += blockDim.x)
+            ens_cp_async_small<(int)sizeof(Tin)>(dst + e * sizeof(Tin), src + e);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    // work item = (cell e, coordinate c); neighbouring lanes share a cell
+    const int nitems = nt * K * 2;
+    const int nround = (nitems + blockDim.x - 1) / blockDim.x;
+    for (int rnd = 0; rnd < nround; ++rnd) {
+        const int idx = rnd * blockDim.x + threadIdx.x;
+        const bool valid = idx < nitems;
+        const int e = valid ? idx >> 1 : 0, c = idx & 1;
+        const int tl = e / K, k = e - tl * K;
+        P xs[MAXM];
+        P conf = P(0);
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                const Tin* sp = reinterpret_cast<const Tin*>(smem_raw + (size_t)m * chunk_pad) + e * 3;
+                xs[m] = P(sp[c]);                    // cast to the compute precision first (core.py:90-92)
+                if (c == 0) conf += P(sp[2]);        // likelihood sum is NOT NaN-aware (core.py:67-68)
+            } else {
+                xs[m] = P(0);
+            }
+        }
+        conf = __shfl_sync(0xffffffffu, conf, threadIdx.x & 30);  // even lane of the pair owns the sum
+        const P mean_conf = conf / P(M);
+        P avg, var;
+        coord_stats<P, MAXM>(xs, M, avg_median != 0, avg, var);
+        if (M == 1) var = P(1) / fmax(mean_conf, P(1e-5));
+        else if (var_mode == 1) var = var / mean_conf;
+        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
+        if (isnan(var)) var = nan_repl; else if (isinf(var)) var = var > 0 ? real_max<P>() : -real_max<P>();
+        if (valid) {
+            tile[(c * K + k) * ld + tl] = avg;
+            tile[((2 + c) * K + k) * ld + tl] = var;
+            if (c == 0) tile[(4 * K + k) * ld + tl] = mean_conf;
+        }
+    }
+    __syncthreads();
+    // coalesced plane writes: frame fastest
+    P* obase = out + (long long)sess * eo.sess_stride + (long long)v * eo.cam_stride;
+    for (int idx = threadIdx.x; idx < 5 * K * nt; idx += blockDim.x) {
+        const int tl = idx % nt, fk = idx / nt;
+        const int f = fk / K, k = fk - f * K;
+        obase[(long long)k * eo.kp_stride + eo.plane_off[f] + t0 + tl] = tile[(f * K + k) * ld + tl];
+    }
+    if (partials != nullptr) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        const int ntiles = gridDim.x;
+        for (int k = warp; k < K; k += nwarp) {
+            double sx = 0, sy = 0, sxx = 0, syy = 0;
+            for (int tl = lane; tl < nt; tl += 32) {
+                const double x = (double)tile[(0 * K + k) * ld + tl];
+                const double y = (double)tile[(1 * K + k) * ld + tl];
+                sx += x; sy += y; sxx += x * x; syy += y * y;
+            }
+            sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); syy = warp_sum(syy);
+            if (lane == 0) {
+                double* pp = partials + ((((long long)sess * V + v) * K + k) * ntiles + tile_idx) * 4;
+                pp[0] = sx; pp[1] = sy; pp[2] = sxx; pp[3] = syy;
+            }
+        }
+    }
+}
+
 // reduce the per-tile partials in a fixed order: one warp per (session, camera, keypoint)
 template <class P>
 __global__ void moments_finalize_kernel(const double* __restrict__ partials, int nseq, int ntiles, long long T,
@@ -194,27 +300,51 @@ __global__ void moments_finalize_kernel(const double* __restrict__ partials, int
     }
 }
 
+// frames per tile: the largest of {64,32,16,8} whose staged tile (M seed chunks + output tile) fits the
+// shared-memory budget that still allows ~4 CTAs per SM; 0 -> use the direct kernel (64 frames per tile)
+static int staged_tile_frames(int M, int K, int in_bytes, int out_bytes) {
+    const int cand[4] = {64, 32, 16, 8};
+    for (int i = 0; i < 4; ++i) {
+        const int TT = cand[i];
+        const size_t need = (size_t)M * (((size_t)TT * K * 3 * in_bytes + 15) / 16 * 16) +
+                            (size_t)5 * K * (TT + 1) * out_bytes;
+        if (need <= 56 * 1024) return TT;
+    }
+    return 0;
+}
+
 template <class Tin, class P>
 int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int V, int T, int K, int avg_median,
-                    int var_mode, double nan_repl, P* out, const EnsOut& eo, double* partials, int TT,
-                    cudaStream_t st) {
+                    int var_mode, double nan_repl, P* out, const EnsOut& eo, double* partials, cudaStream_t st) {
+    EKS_REQUIRE(M <= 32, "ensemble: at most 32 seeds supported, got %d", M);
+    const int TTs = staged_tile_frames(M, K, (int)sizeof(Tin), (int)sizeof(P));
+    const bool staged = TTs > 0;
+    const int TT = staged ? TTs : 64;
     const int ntiles = (T + TT - 1) / TT;
     dim3 grid(ntiles, V, S), block(256);
-    const size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
+    size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
+    if (staged) smem += (size_t)M * (((size_t)TT * K * 3 * sizeof(Tin) + 15) / 16 * 16);
     EKS_REQUIRE(smem <= 200 * 1024, "ensemble: K=%d too large for the shared-memory tile", K);
 #define EKS_ENS_LAUNCH(MAXM)                                                                                      \
     do {                                                                                                          \
-        auto kern = ensemble_kernel<Tin, P, MAXM>;                                                                \
-        if (smem > 48 * 1024)                                                                                     \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
-        kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl, out, \
-                                        eo, partials, TT);                                                        \
+        if (staged) {                                                                                             \
+            auto kern = ensemble_staged_kernel<Tin, P, MAXM>;                                                     \
+            if (smem > 48 * 1024)                                                                                 \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+            kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl,  \
+                                            out, eo, partials, TT);                                               \
+        } else {                                                                                                  \
+            auto kern = ensemble_kernel<Tin, P, MAXM>;                                                            \
+            if (smem > 48 * 1024)                                                                                 \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+            kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl,  \
+                                            out, eo, partials, TT);                                               \
+        }                                                                                                         \
     } while (0)
     if (M <= 4) EKS_ENS_LAUNCH(4);
     else if (M <= 8) EKS_ENS_LAUNCH(8);
     else if (M <= 16) EKS_ENS_LAUNCH(16);
-    else if (M <= 32) EKS_ENS_LAUNCH(32);
-    else EKS_REQUIRE(false, "ensemble: at most 32 seeds supported, got %d", M);
+    else EKS_ENS_LAUNCH(32);
 #undef EKS_ENS_LAUNCH
     return check_launch("ensemble_kernel");
 }
@@ -223,7 +353,10 @@ int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int
 
 using namespace eks;
 
-extern "C" int eks_ensemble_tile_frames(void) { return 64; }
+extern "C" int eks_ensemble_tile_frames(int M, int K, int raw_dtype, int out_dtype) {
+    const int TT = staged_tile_frames(M, K, raw_dtype == EKS_F32 ? 4 : 8, out_dtype == EKS_F32 ? 4 : 8);
+    return TT > 0 ? TT : 64;
+}
 
 extern "C" int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_sess_stride, int n_sessions, int M,
                                   int V, int T, int K, int avg_median, int var_mode, double nan_replacement,
@@ -237,26 +370,24 @@ extern "C" int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_
     eo.sess_stride = sess_stride; eo.cam_stride = cam_stride; eo.kp_stride = kp_stride;
     for (int i = 0; i < 5; ++i) eo.plane_off[i] = plane_off[i];
     cudaStream_t st = (cudaStream_t)stream;
-    const int TT = eks_ensemble_tile_frames();
     if (raw_dtype == EKS_F32 && out_dtype == EKS_F32)
         return launch_ensemble<float, float>((const float*)raw, raw_sess_stride, n_sessions, M, V, T, K, avg_median,
-                                             var_mode, nan_replacement, (float*)out, eo, moment_partials, TT, st);
+                                             var_mode, nan_replacement, (float*)out, eo, moment_partials, st);
     if (raw_dtype == EKS_F64 && out_dtype == EKS_F32)
         return launch_ensemble<double, float>((const double*)raw, raw_sess_stride, n_sessions, M, V, T, K,
                                               avg_median, var_mode, nan_replacement, (float*)out, eo,
-                                              moment_partials, TT, st);
+                                              moment_partials, st);
     if (raw_dtype == EKS_F64 && out_dtype == EKS_F64)
         return launch_ensemble<double, double>((const double*)raw, raw_sess_stride, n_sessions, M, V, T, K,
                                                avg_median, var_mode, nan_replacement, (double*)out, eo,
-                                               moment_partials, TT, st);
+                                               moment_partials, st);
     EKS_REQUIRE(false, "ensemble: unsupported dtype combination");
 }
 
-extern "C" int eks_center_moments(const double* moment_partials, int n_seq, int T, void* mean_out, void* var_out,
-                                  int dtype, void* stream) {
+extern "C" int eks_center_moments(const double* moment_partials, int n_seq, int n_tiles, int T, void* mean_out,
+                                  void* var_out, int dtype, void* stream) {
     EKS_REQUIRE(moment_partials && mean_out && var_out, "center_moments: null pointer");
-    const int TT = eks_ensemble_tile_frames();
-    const int ntiles = (T + TT - 1) / TT;
+    const int ntiles = n_tiles;
     const int threads = 128, warps_per_block = threads / 32;
     const int blocks = (n_seq + warps_per_block - 1) / warps_per_block;
     cudaStream_t st = (cudaStream_t)stream;

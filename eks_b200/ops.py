@@ -88,7 +88,7 @@ def ensemble_stats(raw: torch.Tensor, out: torch.Tensor, sess_stride: int, cam_s
     Returns the per-tile moment partials tensor (or None)."""
     assert raw.is_cuda and raw.is_contiguous() and raw.dim() == 6 and raw.shape[-1] == 3
     S, M, V, T, K, _ = raw.shape
-    TT = lib().eks_ensemble_tile_frames()
+    TT = lib().eks_ensemble_tile_frames(M, K, dt_code(raw.dtype), dt_code(out.dtype))
     ntiles = (T + TT - 1) // TT
     partials = torch.empty((S * V * K, ntiles, 4), dtype=torch.float64, device=raw.device) if moments else None
     po = i64_host(plane_off)
@@ -105,7 +105,8 @@ def center_moments(partials: torch.Tensor, T: int, dtype):
     n_seq = partials.shape[0]
     mean = torch.empty((n_seq, 2), dtype=dtype, device=partials.device)
     var = torch.empty((n_seq, 2), dtype=dtype, device=partials.device)
-    check(lib().eks_center_moments(ptr(partials), n_seq, T, ptr(mean), ptr(var), dt_code(dtype), stream_ptr()),
+    check(lib().eks_center_moments(ptr(partials), n_seq, partials.shape[1], T, ptr(mean), ptr(var), dt_code(dtype),
+                                   stream_ptr()),
           'eks_center_moments')
     _count(1)
     return mean, var

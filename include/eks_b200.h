@@ -42,10 +42,10 @@ int eks_version(void);
  * raw_dtype f32|f64 (values are cast to out_dtype before any arithmetic, as core.py:90-92 does).
  * Writes 5 planes [x_avg, y_avg, var_x, var_y, likelihood] per (session, camera, keypoint) at
  *   out[s*sess_stride + v*cam_stride + k*kp_stride + plane_off[f] + t].
- * moment_partials (nullable): [n_sessions*V*K][ceil(T/eks_ensemble_tile_frames())][4] doubles
+ * moment_partials (nullable): [n_sessions*V*K][ceil(T/eks_ensemble_tile_frames(M,K,raw_dtype,out_dtype))][4] doubles
  * receiving per-tile sums (x, y, x^2, y^2) of the averaged coordinates, consumed by eks_center_moments.
  * avg_median: 1 median | 0 mean.  var_mode: 1 confidence_weighted_var | 0 var. */
-int eks_ensemble_tile_frames(void);
+int eks_ensemble_tile_frames(int M, int K, int raw_dtype, int out_dtype);
 int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_sess_stride, int n_sessions, int M, int V,
                        int T, int K, int avg_median, int var_mode, double nan_replacement, void* out, int out_dtype,
                        long long sess_stride, long long cam_stride, long long kp_stride,
@@ -54,8 +54,8 @@ int eks_ensemble_stats(const void* raw, int raw_dtype, long long raw_sess_stride
 /* ---- centring moments: the all-frames case of center_predictions (eks/utils.py:293-365 with
  * quantile 100, eks/singlecam_smoother.py:155-157) and S0 = diag(nanvar) (singlecam_smoother.py:262-266).
  * mean_out/var_out: [n_seq][2] real. */
-int eks_center_moments(const double* moment_partials, int n_seq, int T, void* mean_out, void* var_out, int dtype,
-                       void* stream);
+int eks_center_moments(const double* moment_partials, int n_seq, int n_tiles, int T, void* mean_out, void* var_out,
+                       int dtype, void* stream);
 
 /* ---- initial guess: compute_initial_guesses + caller fallback (eks/core.py:104-133, :233-236) and
  * the float32 log seed (core.py:612-613, :622).  var view = raw ensemble variances (unclipped).

@@ -137,3 +137,83 @@ def test_ensemble_matches_oracle(M, avg_mode):
         e = eks_b200.ensemble(MarkerArray(data, data_fields=['x', 'y', 'likelihood']), avg_mode=avg_mode, var_mode=vm)
         ref = oracle.ensemble(data, avg_mode, vm, dtype=np.float32)
         np.testing.assert_allclose(e.array[0], ref, rtol=2e-6, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize('T', [7, 33, 2001, 8192, 8193, 20010])
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_ragged_lengths_and_alignment(T, dtype):
+    """frame counts that are tiny, not multiples of the vector width, exactly one tile, one past a tile:
+    exercises the transient-only path, the unaligned copy path and partial tiles of the scan kernels."""
+    from oracle import oracle
+    raw = synth_singlecam(M=3, K=2, T=T, seed=T)
+    ref = oracle.singlecam(raw, dtype=np.float64)
+    out, res = _run(raw if dtype == torch.float64 else raw.astype(np.float32), dtype)
+    rtol = RTOL64 if dtype == torch.float64 else RTOL32
+    if dtype == torch.float64:
+        assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
+        np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=rtol)
+        _check_out(out, ref['out'], rtol, f'T={T}')
+    else:
+        # fp32: compare the smoother at the oracle's s (the stop iteration is a knife edge in fp32)
+        out32, _ = _run(raw.astype(np.float32), dtype, smooth_param=list(ref['s_finals']))
+        _check_out(out32, ref['out'], rtol, f'T={T} fp32 fixed s')
+        d_it = np.abs(res.iters[0].cpu().numpy().astype(int) - ref['info']['iters'].astype(int))
+        assert d_it.max() <= 3, f'fp32 iteration counts drift: {res.iters[0].cpu().numpy()} vs {ref["info"]["iters"]}'
+
+
+def test_blocks_share_s_and_match_oracle():
+    """reference tests/test_core.py:194-211 (block members share one s) + parity of the shared-s loss."""
+    from oracle import oracle
+    raw = synth_singlecam(M=4, K=4, T=1500, seed=21)
+    blocks = [[0, 2], [1]]
+    ref = oracle.singlecam(raw, dtype=np.float64, blocks=[[0, 2], [1], [3]])
+    out, res = _run(raw, torch.float64, blocks=blocks)
+    s = res.s_finals[0].cpu().numpy()
+    assert s[0] == s[2]
+    np.testing.assert_allclose(s, ref['s_finals'], rtol=RTOL64)
+    out_g, res_g = _run(raw, torch.float64, blocks=blocks, force_generic=True)
+    np.testing.assert_allclose(res_g.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=RTOL64)
+    _check_out(out, ref['out'], RTOL64, 'blocks')
+
+
+def test_nll_grad_entry_point_matches_oracle():
+    """eks_nll_grad through the C ABI on a multicam-shaped linear model (D=3, O=4, full Q) and the pinhole EKF."""
+    from eks_b200 import ops
+    from eks_b200.ops import Model, PlaneView
+    from oracle import oracle
+    from test_oracle import fly_cams, random_linear
+    dev = torch.device('cuda')
+    for dt, tdt, rtol in ((np.float64, torch.float64, 1e-7), (np.float32, torch.float32, 2e-3)):
+        y, m0, S0, A, C, Q, Rt = random_linear(3, 4, 700, seed=9)
+        B = 3
+        ys = np.stack([y, y * 0.5, y + 1.0])
+        f = lambda a: torch.as_tensor(np.broadcast_to(a, (B, *a.shape)).copy(), dtype=tdt, device=dev)
+        model = Model(f(m0), f(S0), f(A), f(Q), f(C))
+        yp = torch.as_tensor(ys, dtype=tdt, device=dev).permute(0, 2, 1).contiguous()
+        T, O = 700, 4
+        yv = PlaneView(yp, O * T, [o * T for o in range(O)])
+        Rc = torch.as_tensor(np.broadcast_to(Rt[0], (B, O)).copy(), dtype=tdt, device=dev)
+        s = torch.tensor([0.1, 0.5, 2.0], dtype=tdt, device=dev)
+        nll, dn = ops.nll_grad(model, yv, T, Rc, s)
+        n_o, g_o = oracle.nll_grad(ys, np.tile(m0, (B, 1)), np.tile(S0, (B, 1, 1)), np.tile(A, (B, 1, 1)),
+                                   np.tile(C, (B, 1, 1)), np.tile(Q, (B, 1, 1)), np.tile(Rt[0], (B, 1)),
+                                   np.array([0.1, 0.5, 2.0]), dtype=np.float64)
+        np.testing.assert_allclose(nll.double().cpu().numpy(), n_o, rtol=rtol)
+        np.testing.assert_allclose(dn.double().cpu().numpy(), g_o, rtol=rtol * 20)
+    cams = fly_cams()
+    rng = np.random.default_rng(1)
+    T = 400
+    X = np.array([-1.75, -0.30, 3.5]) + np.cumsum(rng.standard_normal((T, 3)) * 1e-3, axis=0)
+    y = oracle.project(cams, X) + rng.standard_normal((T, 6)) * 0.5
+    m0, S0, A, Q = X[0] + 0.01, np.eye(3) * 1e-2, np.eye(3), np.diag([1e-6, 2e-6, 1.5e-6])
+    tdt = torch.float64
+    g = lambda a: torch.as_tensor(a[None].copy(), dtype=tdt, device=dev)
+    model = Model(g(m0), g(S0), g(A), g(Q), None, torch.as_tensor(cams, dtype=tdt, device=dev))
+    yp = torch.as_tensor(y[None], dtype=tdt, device=dev).permute(0, 2, 1).contiguous()
+    yv = PlaneView(yp, 6 * T, [o * T for o in range(6)])
+    Rc = torch.full((1, 6), 0.3, dtype=tdt, device=dev)
+    nll, dn = ops.nll_grad(model, yv, T, Rc, torch.tensor([1.3], dtype=tdt, device=dev))
+    n_o, g_o = oracle.nll_grad(y[None], m0[None], S0[None], A[None], None, Q[None], np.full((1, 6), 0.3), 1.3,
+                               cams=cams)
+    np.testing.assert_allclose(nll.cpu().numpy(), n_o, rtol=1e-8)
+    np.testing.assert_allclose(dn.cpu().numpy(), g_o, rtol=1e-6)

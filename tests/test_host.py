@@ -121,7 +121,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f'{name} declared in include/eks_b200.h but not exported'
     assert L.eks_version() >= 100
-    assert L.eks_ensemble_tile_frames() > 0
+    assert L.eks_ensemble_tile_frames(10, 20, 0, 0) > 0
 
 
 def test_no_cpu_fallback_without_gpu():
