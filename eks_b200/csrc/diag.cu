@@ -152,6 +152,20 @@ __device__ inline void opt_issue_tile(unsigned char* stage, const P* __restrict_
     }
 }
 
+// Fast path of opt_issue_tile for a tile that lies completely inside [e_min, n) and is 16-byte aligned:
+// granule i of this thread sits at constant offsets from two per-thread bases (no masks, no index math).
+template <class P>
+__device__ inline void opt_issue_tile_fast(unsigned char* stage_thread, const P* __restrict__ tile_thread) {
+    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
+    constexpr int GPC = OPT_CHUNK_BYTES / 16;
+    constexpr int CPI = DIAG_NT / GPC;  // chunks covered by one round of DIAG_NT granules
+#pragma unroll
+    for (int i = 0; i < GPC; ++i) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(stage_thread + i * CPI * OPT_PAD_BYTES);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(tile_thread + i * CPI * L) : "memory");
+    }
+}
+
 // ---- transient: sequential scalar filter with s-sensitivities until the variance recursion has reached
 // its floating-point fixed point (or the sequence ends).  One thread per (sequence, channel).
 template <class P>
@@ -358,9 +372,22 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_const
     const P b_lane = lane == 0 ? P(0) : nl * pow_(alpha, nl - P(1)) * sh.ch.dalpha;
     double E2 = 0, G = 0;
     const int nt = tile_hi - first_tile;
+    // per-thread bases of the fast copy path: granule (threadIdx.x) of round 0
+    constexpr int GPC = OPT_CHUNK_BYTES / 16;
+    constexpr int EPG = 16 / (int)sizeof(P);
+    const int g_chunk = threadIdx.x / GPC, g_q = threadIdx.x % GPC;
+    const int fast_goff = g_chunk * L + g_q * EPG;                    // elements from the tile start
+    const int fast_soff = g_chunk * OPT_PAD_BYTES + g_q * 16;         // bytes from the stage start
+    auto issue = [&](int stage, int tile) {
+        const int t0i = t_c + tile * TILE;
+        if (vec && t0i >= e_min && t0i + TILE <= a.n)
+            opt_issue_tile_fast<P>(ring + stage * OPT_STAGE_BYTES + fast_soff, yc + t0i + fast_goff);
+        else
+            opt_issue_tile<P>(ring + stage * OPT_STAGE_BYTES, yc, t0i, e_min, a.n, vec);
+    };
 #pragma unroll
     for (int st = 0; st < OPT_STAGES - 1; ++st) {
-        if (st < nt) opt_issue_tile<P>(ring + st * OPT_STAGE_BYTES, yc, t_c + (first_tile + st) * TILE, e_min, a.n, vec);
+        if (st < nt) issue(st, first_tile + st);
         cp_async_commit();
     }
     int buf = 0;
@@ -368,22 +395,32 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_const
         cp_async_wait<OPT_STAGES - 2>();
         __syncthreads();  // tile `it` has landed for everyone; the stage read in iteration it-1 is free again
         const int nx = it + OPT_STAGES - 1;
-        if (nx < nt)
-            opt_issue_tile<P>(ring + (nx % OPT_STAGES) * OPT_STAGE_BYTES, yc, t_c + (first_tile + nx) * TILE, e_min, a.n, vec);
+        if (nx < nt) issue(nx % OPT_STAGES, first_tile + nx);
         cp_async_commit();
         const unsigned char* mine = ring + (it % OPT_STAGES) * OPT_STAGE_BYTES + threadIdx.x * OPT_PAD_BYTES;
         const int t0 = t_c + (first_tile + it) * TILE;
         const int cstart = t0 + (int)threadIdx.x * L;
         // centred observations; masked (warm-up prefix / beyond the end) frames stay exactly zero
         P y[L];
+        const bool inner = (t0 >= e_min) && (t0 + TILE <= a.n);  // uniform: no masked frames in this tile
+        if (inner) {
 #pragma unroll
-        for (int i = 0; i < L / VW; ++i) {
-            const V v = *reinterpret_cast<const V*>(mine + i * 16);
-            const P* e = reinterpret_cast<const P*>(&v);
+            for (int i = 0; i < L / VW; ++i) {
+                const V v = *reinterpret_cast<const V*>(mine + i * 16);
+                const P* e = reinterpret_cast<const P*>(&v);
 #pragma unroll
-            for (int q = 0; q < VW; ++q) {
-                const int fr = cstart + i * VW + q;
-                y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
+                for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < L / VW; ++i) {
+                const V v = *reinterpret_cast<const V*>(mine + i * 16);
+                const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+                for (int q = 0; q < VW; ++q) {
+                    const int fr = cstart + i * VW + q;
+                    y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
+                }
             }
         }
         const bool acc = (first_tile + it) >= tile_lo;

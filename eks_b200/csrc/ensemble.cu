@@ -12,6 +12,7 @@
 // input with keypoint fastest (fully coalesced), results are transposed through shared memory and
 // written with frame fastest (fully coalesced).  HBM-bound: 12*M bytes in, 20 bytes out per cell.
 #include "common.cuh"
+#include "sort_networks.cuh"
 #include "../../include/eks_b200.h"
 
 namespace eks {
@@ -50,9 +51,17 @@ __device__ inline void sort_network(P (&v)[N]) {
     }
 }
 
-// statistics of one coordinate over the M seeds (NaN-aware), reference core.py:64-79
-template <class P, int MAXM>
-__device__ inline void coord_stats(const P (&x)[MAXM], int M, bool avg_median, P& avg, P& var) {
+template <class P, int N>
+__device__ __forceinline__ void sort_values(P (&v)[N]) {
+    if constexpr (N <= 16) SortNet<N>::run(v);
+    else sort_network<P, N>(v);
+}
+
+// statistics of one coordinate over the M seeds (NaN-aware), reference core.py:64-79.
+// EXACT: the array length MAXM is the seed count (all `m < M` predicates fold away).
+template <class P, int MAXM, bool EXACT = false>
+__device__ inline void coord_stats(const P (&x)[MAXM], int M_rt, bool avg_median, P& avg, P& var) {
+    const int M = EXACT ? MAXM : M_rt;
     int n = 0;
     P sum = P(0);
 #pragma unroll
@@ -76,17 +85,22 @@ __device__ inline void coord_stats(const P (&x)[MAXM], int M, bool avg_median, P
     P s[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) s[m] = (m < M && !isnan(x[m])) ? x[m] : pos_inf<P>();
-    sort_network<P, MAXM>(s);
+    sort_values<P, MAXM>(s);
     // nanmedian: middle element, or mean of the two middle elements, of the n valid values
-    const int hi = n >> 1, lo = (n & 1) ? hi : hi - 1;
-    P a = P(0), b = P(0);
+    P a, b;
+    if (EXACT && n == MAXM) {  // no NaN among the seeds (the common case): fixed positions
+        a = s[(MAXM - 1) / 2];
+        b = s[MAXM / 2];
+    } else {
+        const int hi = n >> 1, lo = (n & 1) ? hi : hi - 1;
+        a = P(0); b = P(0);
 #pragma unroll
-    for (int m = 0; m < MAXM; ++m) {
-        if (m == lo) a = s[m];
-        if (m == hi) b = s[m];
+        for (int m = 0; m < MAXM; ++m) {
+            if (m == lo) a = s[m];
+            if (m == hi) b = s[m];
+        }
     }
-    avg = a * P(0.5) + b * P(0.5);
-    if (n & 1) avg = b;
+    avg = (a == b) ? a : a * P(0.5) + b * P(0.5);
 }
 
 template <class Tin, class P, int MAXM>
@@ -181,12 +195,13 @@ __device__ inline void ens_cp_async_small(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(gmem), "n"(BYTES) : "memory");
 }
 
-template <class Tin, class P, int MAXM>
+template <class Tin, class P, int MAXM, bool EXACT>
 __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restrict__ raw, long long raw_sess_stride,
-                                                              int M, int V, int T, int K, int avg_median,
+                                                              int M_rt, int V, int T, int K, int avg_median,
                                                               int var_mode, P nan_repl, P* __restrict__ out, EnsOut eo,
                                                               double* __restrict__ partials, int TT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = EXACT ? MAXM : M_rt;
     const int tile_idx = blockIdx.x, v = blockIdx.y, sess = blockIdx.z;
     const int t0 = tile_idx * TT;
     const int nt = min(TT, T - t0);
@@ -235,7 +250,7 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         conf = __shfl_sync(0xffffffffu, conf, threadIdx.x & 30);  // even lane of the pair owns the sum
         const P mean_conf = conf / P(M);
         P avg, var;
-        coord_stats<P, MAXM>(xs, M, avg_median != 0, avg, var);
+        coord_stats<P, MAXM, EXACT>(xs, M, avg_median != 0, avg, var);
         if (M == 1) var = P(1) / fmax(mean_conf, P(1e-5));
         else if (var_mode == 1) var = var / mean_conf;
         // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
@@ -325,27 +340,42 @@ int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int
     size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
     if (staged) smem += (size_t)M * (((size_t)TT * K * 3 * sizeof(Tin) + 15) / 16 * 16);
     EKS_REQUIRE(smem <= 200 * 1024, "ensemble: K=%d too large for the shared-memory tile", K);
-#define EKS_ENS_LAUNCH(MAXM)                                                                                      \
-    do {                                                                                                          \
-        if (staged) {                                                                                             \
-            auto kern = ensemble_staged_kernel<Tin, P, MAXM>;                                                     \
-            if (smem > 48 * 1024)                                                                                 \
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-            kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl,  \
-                                            out, eo, partials, TT);                                               \
-        } else {                                                                                                  \
-            auto kern = ensemble_kernel<Tin, P, MAXM>;                                                            \
-            if (smem > 48 * 1024)                                                                                 \
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-            kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl,  \
-                                            out, eo, partials, TT);                                               \
-        }                                                                                                         \
+#define EKS_ENS_STAGED(MAXM, EXACT)                                                                           \
+    do {                                                                                                      \
+        auto kern = ensemble_staged_kernel<Tin, P, MAXM, EXACT>;                                              \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl, out, \
+                                        eo, partials, TT);                                                    \
     } while (0)
-    if (M <= 4) EKS_ENS_LAUNCH(4);
-    else if (M <= 8) EKS_ENS_LAUNCH(8);
-    else if (M <= 16) EKS_ENS_LAUNCH(16);
-    else EKS_ENS_LAUNCH(32);
-#undef EKS_ENS_LAUNCH
+#define EKS_ENS_DIRECT(MAXM)                                                                                  \
+    do {                                                                                                      \
+        auto kern = ensemble_kernel<Tin, P, MAXM>;                                                            \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl, out, \
+                                        eo, partials, TT);                                                    \
+    } while (0)
+    if (staged) {
+        switch (M) {  // exact-size networks for the usual ensemble sizes
+            case 1: EKS_ENS_STAGED(1, true); break;
+            case 2: EKS_ENS_STAGED(2, true); break;
+            case 3: EKS_ENS_STAGED(3, true); break;
+            case 4: EKS_ENS_STAGED(4, true); break;
+            case 5: EKS_ENS_STAGED(5, true); break;
+            case 6: EKS_ENS_STAGED(6, true); break;
+            case 7: EKS_ENS_STAGED(7, true); break;
+            case 8: EKS_ENS_STAGED(8, true); break;
+            case 9: EKS_ENS_STAGED(9, true); break;
+            case 10: EKS_ENS_STAGED(10, true); break;
+            default:
+                if (M <= 16) EKS_ENS_STAGED(16, false);
+                else EKS_ENS_STAGED(32, false);
+        }
+    } else {
+        if (M <= 16) EKS_ENS_DIRECT(16);
+        else EKS_ENS_DIRECT(32);
+    }
+#undef EKS_ENS_STAGED
+#undef EKS_ENS_DIRECT
     return check_launch("ensemble_kernel");
 }
 
