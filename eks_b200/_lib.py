@@ -18,7 +18,7 @@ F32, F64 = 0, 1
 MAX_CHAN, MAX_STATE, CAM_STRIDE = 16, 6, 29
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libeks_b200.so')
+LIB_PATH = os.environ.get('EKS_B200_LIB') or os.path.join(_HERE, 'lib', 'libeks_b200.so')
 _lib = None
 
 
@@ -54,8 +54,10 @@ _SIGS = {
                                   c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
 }
-# entry points of the specialised (decoupled / time-parallel) path; bound if the library exports them
 _OPTIONAL_SIGS = {
+    'eks_reproject': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_longlong, c_longlong,
+                              c_void_p, c_void_p]),
     'eks_diag_smooth_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'eks_diag_smooth': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,

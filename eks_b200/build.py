@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libeks_b200.so')
-SOURCES = ['generic.cu', 'ensemble.cu', 'prestage.cu', 'diag.cu']
+SOURCES = ['generic.cu', 'ensemble.cu', 'prestage.cu', 'diag.cu', 'epilogue.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if not force and not _obj_stale(src_path, obj):
             continue
-        cmd = [_nvcc(), *NVCC_FLAGS, '-c', src_path, '-o', obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get('EKS_NVCC_DEFS', '').split(), '-c', src_path, '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

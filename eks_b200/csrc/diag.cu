@@ -47,13 +47,23 @@ struct ChanConst {
     P alpha, beta, a, cc, dalpha, dbeta, iS, diS, logS, dlogS;
     P aL[5], bL[5];  // Phi^(L 2^k) = [[aL,0],[bL,aL]]
     P aW, bW;        // Phi^(32 L)
+    P aH, bH;        // Phi^(L/2)
 };
 
 // shared-memory tile ring: every thread's chunk is CHUNK_BYTES of frames, padded to PAD_BYTES so that the
 // per-thread 16-byte reads are bank-conflict free (stride 144 B = 9 x 16 B)
 constexpr int OPT_CHUNK_BYTES = 128;
 constexpr int OPT_PAD_BYTES = 144;
-constexpr int OPT_STAGES = 3;
+#ifndef EKS_OPT_STAGES
+#define EKS_OPT_STAGES 2
+#endif
+#ifndef EKS_OPT_MINBLOCKS
+#define EKS_OPT_MINBLOCKS 3
+#endif
+#ifndef EKS_OPT_RELOAD
+#define EKS_OPT_RELOAD 0
+#endif
+constexpr int OPT_STAGES = EKS_OPT_STAGES;
 constexpr int OPT_STAGE_BYTES = DIAG_NT * OPT_PAD_BYTES;
 
 // ---- device-resident optimiser state -----------------------------------------------------------------
@@ -68,6 +78,7 @@ template <class P>
 struct ChanState {           // one per (sequence, channel): produced by diag_adam_kernel for the current s
     ChanConst<P> k;
     P z0[2];                 // (m, dm) at frame t_c
+    P a_lane[32], b_lane[32];// Phi^(L lane) = [[a_lane,0],[b_lane,a_lane]] for folding a warp carry
     double tsum[5];          // transient sums: logS, dlogS, e2 iS, e2 diS, cc e dm iS
     int t_c;                 // first steady-state frame (multiple of 4)
     int warm;                // frames after which a zero carry-in is forgotten below rounding
@@ -232,8 +243,10 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     k.logS = log_(S);
     k.dlogS = dS * iS;
     constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    P aL = pow_(k.alpha, P(L));
-    P bL = P(L) * pow_(k.alpha, P(L - 1)) * k.dalpha;
+    k.aH = pow_(k.alpha, P(L / 2));
+    k.bH = P(L / 2) * pow_(k.alpha, P(L / 2 - 1)) * k.dalpha;
+    P aL = k.aH * k.aH;                 // Phi^L = (Phi^(L/2))^2: keeps the half/full powers consistent
+    P bL = P(2) * k.aH * k.bH;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         k.aL[i] = aL; k.bL[i] = bL;
@@ -241,6 +254,12 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
         aL = aL * aL;
     }
     k.aW = aL; k.bW = bL;
+    out.a_lane[0] = P(1);
+    out.b_lane[0] = P(0);
+    for (int l = 1; l < 32; ++l) {  // Phi^(L l) = Phi^L Phi^(L (l-1))
+        out.a_lane[l] = k.aL[0] * out.a_lane[l - 1];
+        out.b_lane[l] = k.aL[0] * out.b_lane[l - 1] + k.bL[0] * out.a_lane[l - 1];
+    }
     out.z0[0] = m;
     out.z0[1] = dm;
     out.tsum[0] = sl; out.tsum[1] = sdl; out.tsum[2] = se; out.tsum[3] = sde; out.tsum[4] = sg;
@@ -254,23 +273,47 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     out.warm = (int)w;
 }
 
+template <class V> __device__ inline V lds_volatile(const unsigned char* p);
+template <> __device__ inline float4 lds_volatile<float4>(const unsigned char* p) {
+    float4 v;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa));
+    return v;
+}
+template <> __device__ inline double2 lds_volatile<double2>(const unsigned char* p) {
+    double2 v;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(sa));
+    return v;
+}
+
 // One tile of DIAG_NT * L frames of one channel; y[] is the thread's register-resident chunk (already
 // centred).  E2/G are this thread's fp64 accumulators.  ACC = false: warm-up tile (carry only).
+// The chunk is processed as two independent half-chunks (two dependency chains in flight per thread):
+// the zero-state responses of the halves are combined with Phi^(L/2), and the second half of phase 3
+// starts from the exact mid-chunk state Phi^(L/2) z_in + z_a.
 template <class P, int L, bool FULL, bool ACC>
-__device__ inline void diag_tile(const P (&y)[L], int nvalid, int buf, OptShared<P>& sh, P a_lane, P b_lane,
-                                 double& E2, double& G) {
+__device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& sh, P a_lane, P b_lane,
+                                 double& E2, double& G, const unsigned char* mine = nullptr, P mean = P(0)) {
+    constexpr int H = L / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ChanConst<P>& k = sh.ch;
     const P alpha = k.alpha;
-    // phase 1: zero-state response of the chunk.  U = sum alpha^(L-1-i) y_i, W = dU/dalpha
-    P U = P(0), W = P(0);
+    // phase 1: zero-state responses.  U = sum alpha^(H-1-i) y_i, W = dU/dalpha, per half
+    P Ua = P(0), Wa = P(0), Ub = P(0), Wb = P(0);
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        W = fma(alpha, W, U);
-        U = fma(alpha, U, y[i]);
+    for (int i = 0; i < H; ++i) {
+        Wa = fma(alpha, Wa, Ua);
+        Wb = fma(alpha, Wb, Ub);
+        Ua = fma(alpha, Ua, y[i]);
+        Ub = fma(alpha, Ub, y[H + i]);
     }
-    P zm = k.beta * U;
-    P zd = k.dbeta * U + k.beta * k.dalpha * W;
+    const P bda = k.beta * k.dalpha;
+    const P zam = k.beta * Ua, zad = fma(k.dbeta, Ua, bda * Wa);   // first half, zero state
+    const P zbm = k.beta * Ub, zbd = fma(k.dbeta, Ub, bda * Wb);   // second half, zero state
+    const P aH = k.aH, bH = k.bH;                                  // Phi^(L/2)
+    P zm = fma(aH, zam, zbm);
+    P zd = fma(aH, zad, fma(bH, zam, zbd));
     // warp inclusive scan with the closed-form powers of Phi
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
@@ -299,23 +342,40 @@ __device__ inline void diag_tile(const P (&y)[L], int nvalid, int buf, OptShared
         sh.z_tile[buf ^ 1][1] = fma(aW, cd, fma(bW, cm, sh.agg[buf][warp][1]));
     }
     if (!ACC) return;
-    P m = fma(a_lane, cm, em);
-    P dm = fma(a_lane, cd, fma(b_lane, cm, ed));
-    // phase 3: innovations with the true carry-in; e = y - cc m, m' = a m + beta e, dm' = alpha dm + dbeta e
-    const P beta = k.beta, dbeta = k.dbeta, av = k.a, cc = k.cc;
-    P e2 = P(0), g = P(0);
+    // exact states at the start of the two half-chunks
+    P m0 = fma(a_lane, cm, em);
+    P d0 = fma(a_lane, cd, fma(b_lane, cm, ed));
+    P m1 = fma(aH, m0, zam);
+    P d1 = fma(aH, d0, fma(bH, m0, zad));
+#if EKS_OPT_RELOAD
+    if (FULL) {  // re-read the chunk from the ring stage so that y[] need not live across the scan
+        using V = typename DiagTraits<P>::vec_t;
+        constexpr int VW = DiagTraits<P>::VW;
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        const P e = fma(-cc, m, y[i]);
-        if (FULL || i < nvalid) {
-            e2 = fma(e, e, e2);
-            g = fma(e, dm, g);
+        for (int i = 0; i < L / VW; ++i) {
+            const V v = lds_volatile<V>(mine + i * 16);
+            const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+            for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
         }
-        dm = fma(alpha, dm, dbeta * e);
-        m = fma(beta, e, av * m);
     }
-    E2 += (double)e2;
-    G += (double)g;
+#endif
+    // phase 3: m' = alpha m + beta y (one dependent FMA per frame), e = y - c m, dm' = alpha dm + dbeta e
+    const P beta = k.beta, dbeta = k.dbeta, cc = k.cc;
+    P e2a = P(0), ga = P(0), e2b = P(0), gb = P(0);
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const P ea = fma(-cc, m0, y[i]);
+        const P eb = fma(-cc, m1, y[H + i]);
+        m0 = fma(alpha, m0, beta * y[i]);
+        m1 = fma(alpha, m1, beta * y[H + i]);
+        if (FULL || i < nvalid) { e2a = fma(ea, ea, e2a); ga = fma(ea, d0, ga); }
+        if (FULL || H + i < nvalid) { e2b = fma(eb, eb, e2b); gb = fma(eb, d1, gb); }
+        d0 = fma(alpha, d0, dbeta * ea);
+        d1 = fma(alpha, d1, dbeta * eb);
+    }
+    E2 += (double)(e2a + e2b);
+    G += (double)(ga + gb);
 }
 
 // ---- kernel A: one NLL(+d/ds) evaluation.  grid = (nseg, 2 * B): CTA (k, 2b+c) handles segment k of
@@ -323,7 +383,7 @@ __device__ inline void diag_tile(const P (&y)[L], int nvalid, int buf, OptShared
 // or slow forgetting) or from a zero state `warm` frames earlier, which is exact to rounding because the
 // steady-state filter forgets its initial state geometrically (alpha^warm < 1e-14 / 1e-28).
 template <class P>
-__global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
+__global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
     __shared__ OptShared<P> sh;
     extern __shared__ __align__(16) unsigned char ring[];
     constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
@@ -366,10 +426,7 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_const
     const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
     const bool vec = (reinterpret_cast<uintptr_t>(yc + t_c) & 15) == 0;
     // per-thread powers Phi^(L lane) for folding the warp carry into the exclusive prefix
-    const P alpha = sh.ch.alpha;
-    const P nl = P(L * lane);
-    const P a_lane = lane == 0 ? P(1) : pow_(alpha, nl);
-    const P b_lane = lane == 0 ? P(0) : nl * pow_(alpha, nl - P(1)) * sh.ch.dalpha;
+    const P a_lane = cs.a_lane[lane], b_lane = cs.b_lane[lane];
     double E2 = 0, G = 0;
     const int nt = tile_hi - first_tile;
     // per-thread bases of the fast copy path: granule (threadIdx.x) of round 0
@@ -425,7 +482,7 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_nll_kernel(const __grid_const
         }
         const bool acc = (first_tile + it) >= tile_lo;
         if (!acc) diag_tile<P, L, true, false>(y, L, buf, sh, a_lane, b_lane, E2, G);
-        else if (t0 + TILE <= a.n) diag_tile<P, L, true, true>(y, L, buf, sh, a_lane, b_lane, E2, G);
+        else if (t0 + TILE <= a.n && inner) diag_tile<P, L, true, true>(y, L, buf, sh, a_lane, b_lane, E2, G, mine, mean);
         else diag_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), buf, sh, a_lane, b_lane, E2, G);
     }
     cp_async_wait<0>();
@@ -539,7 +596,7 @@ size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     const int nseg = diag_nseg(dtype, T);
     size_t bytes = 256;
     bytes += (size_t)n_blocks * 128;                   // BlockState
-    bytes += (size_t)B * 2 * 512;                      // ChanState (generous bound)
+    bytes += (size_t)B * 2 * 1024;                     // ChanState (generous bound)
     bytes += (size_t)B * 2 * nseg * 2 * sizeof(double);
     bytes += (size_t)B * sizeof(int) + 256;
     return bytes;
@@ -548,14 +605,14 @@ size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
 template <class P>
 static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspace_bytes, int dtype, int T,
                              cudaStream_t st) {
-    static_assert(sizeof(BlockState<P>) <= 128 && sizeof(ChanState<P>) <= 512, "workspace bound");
+    static_assert(sizeof(BlockState<P>) <= 128 && sizeof(ChanState<P>) <= 1024, "workspace bound");
     a.nseg = diag_nseg(dtype, a.n);
     EKS_REQUIRE(workspace && workspace_bytes >= diag_optimize_workspace_bytes(dtype, a.n_blocks, a.B, T),
                 "optimize_s: workspace too small");
     unsigned char* w = (unsigned char*)workspace;
     a.n_active = (int*)w; w += 256;
     a.bstate = (BlockState<P>*)w; w += (size_t)a.n_blocks * 128;
-    a.cstate = (ChanState<P>*)w; w += (size_t)a.B * 2 * 512;
+    a.cstate = (ChanState<P>*)w; w += (size_t)a.B * 2 * 1024;
     a.partials = (double*)w; w += (size_t)a.B * 2 * a.nseg * 2 * sizeof(double);
     int* seq_block = (int*)w;
     a.seq_block = seq_block;

@@ -199,7 +199,8 @@ template <class Tin, class P, int MAXM, bool EXACT>
 __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restrict__ raw, long long raw_sess_stride,
                                                               int M_rt, int V, int T, int K, int avg_median,
                                                               int var_mode, P nan_repl, P* __restrict__ out, EnsOut eo,
-                                                              double* __restrict__ partials, int TT) {
+                                                              double* __restrict__ partials, int TT, int log2TT,
+                                                              unsigned invK) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int M = EXACT ? MAXM : M_rt;
     const int tile_idx = blockIdx.x, v = blockIdx.y, sess = blockIdx.z;
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         const int idx = rnd * blockDim.x + threadIdx.x;
         const bool valid = idx < nitems;
         const int e = valid ? idx >> 1 : 0, c = idx & 1;
-        const int tl = e / K, k = e - tl * K;
+        const int tl = (K == 1) ? e : (int)__umulhi((unsigned)e, invK);  // e / K without a divide
+        const int k = e - tl * K;
         P xs[MAXM];
         P conf = P(0);
 #pragma unroll
@@ -262,12 +264,16 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         }
     }
     __syncthreads();
-    // coalesced plane writes: frame fastest
+    // coalesced plane writes: frame fastest (TT is a power of two: no integer division)
     P* obase = out + (long long)sess * eo.sess_stride + (long long)v * eo.cam_stride;
-    for (int idx = threadIdx.x; idx < 5 * K * nt; idx += blockDim.x) {
-        const int tl = idx % nt, fk = idx / nt;
-        const int f = fk / K, k = fk - f * K;
-        obase[(long long)k * eo.kp_stride + eo.plane_off[f] + t0 + tl] = tile[(f * K + k) * ld + tl];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        P* of = obase + eo.plane_off[f] + t0;
+        const P* tf = tile + (size_t)f * K * ld;
+        for (int idx = threadIdx.x; idx < (K << log2TT); idx += blockDim.x) {
+            const int k = idx >> log2TT, tl = idx & (TT - 1);
+            if (tl < nt) of[(long long)k * eo.kp_stride + tl] = tf[k * ld + tl];
+        }
     }
     if (partials != nullptr) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -340,12 +346,16 @@ int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int
     size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
     if (staged) smem += (size_t)M * (((size_t)TT * K * 3 * sizeof(Tin) + 15) / 16 * 16);
     EKS_REQUIRE(smem <= 200 * 1024, "ensemble: K=%d too large for the shared-memory tile", K);
+    int log2TT = 0;
+    while ((1 << log2TT) < TT) ++log2TT;
+    // e / K == umulhi(e, ceil(2^32 / K)) for e * K < 2^32 (cells per tile are far below that)
+    const unsigned invK = (unsigned)((((unsigned long long)1 << 32) + (unsigned long long)K - 1) / (unsigned long long)K);
 #define EKS_ENS_STAGED(MAXM, EXACT)                                                                           \
     do {                                                                                                      \
         auto kern = ensemble_staged_kernel<Tin, P, MAXM, EXACT>;                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         kern<<<grid, block, smem, st>>>(raw, raw_sess_stride, M, V, T, K, avg_median, var_mode, (P)nan_repl, out, \
-                                        eo, partials, TT);                                                    \
+                                        eo, partials, TT, log2TT, invK);                                      \
     } while (0)
 #define EKS_ENS_DIRECT(MAXM)                                                                                  \
     do {                                                                                                      \

@@ -220,3 +220,18 @@ def diag_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Ten
                                 stream_ptr()), 'eks_diag_smooth')
     _count(2)
     return ws
+
+
+def reproject(ms: torch.Tensor, Vs: torch.Tensor, V: int, out: torch.Tensor, out_seq_stride: int,
+              out_cam_stride: int, plane_off, C=None, ymean=None, cams=None, var: PlaneView | None = None,
+              pinhole_var_quirk: bool = False):
+    """Smoothed latent moments -> per-camera planes (x, y, posterior var x, posterior var y)."""
+    B, T, D = ms.shape
+    po = i64_host(plane_off)
+    vo = i64_host(var.chan_off) if var is not None else None
+    check(lib().eks_reproject(dt_code(ms.dtype), B, T, D, V, ptr(ms), ptr(Vs), ptr(C), ptr(ymean),
+                              0 if cams is None else cams.shape[0], ptr(cams),
+                              ptr(var.base) if var is not None else None, var.seq_stride if var is not None else 0,
+                              ptr(vo), int(pinhole_var_quirk), ptr(out), out_seq_stride, out_cam_stride, ptr(po),
+                              stream_ptr()), 'eks_reproject')
+    _count(1)

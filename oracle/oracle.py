@@ -333,3 +333,69 @@ def singlecam(raw, smooth_param=None, s_frames=None, blocks=None, avg_mode='medi
     info['means'] = means
     info['S0s'] = S0s
     return dict(out=out, s_finals=s_finals, info=info, ms=ms, Vs=Vs)
+
+
+def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_param=None, s_frames=None,
+             avg_mode='median', var_mode='confidence_weighted_var', dtype=np.float32, trace_cap=0):
+    """ensemble_kalman_smoother_multicam restated (eks/multicam_smoother.py:279-551), inflate_vars=False.
+
+    raw: (M,V,T,K,3).  The one-off host pre-stage (centring, sklearn PCA, triangulation + geometric init)
+    is shared with the product's host utilities -- it is not on the hot path; the
+    hot path (ensemble, s-optimisation, filter/smoother, reprojection) is the oracle's own.
+    Returns dict(cam_out (V,T,K,9), out3d (T,K,2*D), s_finals, info)."""
+    from eks_b200.marker_array import MarkerArray, mA_to_stacked_array
+    from eks_b200.multicam_smoother import (initialize_kalman_filter_geometric, initialize_kalman_filter_pca,
+                                            make_projection_from_camgroup, triangulate_3d_models)
+    from eks_b200.stats import compute_pca
+    from eks_b200.utils import center_predictions
+    raw = np.asarray(raw)
+    M, V, T, K, _ = raw.shape
+    ens = ensemble(raw, avg_mode, var_mode, dtype=dtype)                    # (V,T,K,5)
+    ema = MarkerArray(ens[None], data_fields=['x', 'y', 'var_x', 'var_y', 'likelihood'])
+    unsm, evars = ema.slice_fields('x', 'y'), ema.slice_fields('var_x', 'var_y')
+    mask, cen, good, means = center_predictions(ema, quantile_keep_pca)
+    cams = None
+    if camgroup is not None:
+        tri = triangulate_3d_models(MarkerArray(raw, data_fields=['x', 'y', 'likelihood']), camgroup)
+        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_geometric(tri.mean(axis=0))
+        cams = make_projection_from_camgroup(camgroup)[0].cams
+        ys = np.stack([mA_to_stacked_array(unsm, k) for k in range(K)])
+        D = 3
+    else:
+        pcas, good_pcs = compute_pca(mask, cen, good, n_components=n_latent)
+        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_pca(good_pcs, pcas, n_latent)
+        ys = np.stack([mA_to_stacked_array(cen, k) for k in range(K)])
+        D = n_latent
+    ev = np.stack([mA_to_stacked_array(evars, k) for k in range(K)])         # (K,T,2V)
+    s_finals, ms, Vs, info = run_kalman_smoother(ys, m0s, S0s, As, Cs, Qs, np.swapaxes(ev, 0, 1),
+                                                 s_frames=s_frames, smooth_param=smooth_param, cams=cams,
+                                                 dtype=dtype, trace_cap=trace_cap)
+    ms64, Vs64 = ms.astype(np.float64), Vs.astype(np.float64)
+    cam_out = np.empty((V, T, K, 9))
+    for k in range(K):
+        if cams is not None:
+            uv, J = project(cams, ms64[k], jac=True)                          # (T,2V), (T,2V,3)
+            cov = np.einsum('tij,tjk,tlk->til', J, Vs64[k], J)
+        else:
+            Ck = np.asarray(Cs[k], dtype=np.float64)
+            uv = ms64[k] @ Ck.T + means.array[0, :, 0, k, :].reshape(-1)[None, :]
+            cov = np.einsum('ij,tjk,lk->til', Ck, Vs64[k], Ck)
+        for c in range(V):
+            cam_out[c, :, k, 0] = uv[:, 2 * c]
+            cam_out[c, :, k, 1] = uv[:, 2 * c + 1]
+            cam_out[c, :, k, 2] = ens[c, :, k, 4]
+            cam_out[c, :, k, 3:5] = ens[c, :, k, 0:2]
+            cam_out[c, :, k, 5:7] = ens[c, :, k, 2:4]
+            if cams is not None:  # :943-944 -- always variance columns 0 / 1
+                cam_out[c, :, k, 7] = cov[:, 2 * c, 2 * c] + ev[k][:, 0]
+                cam_out[c, :, k, 8] = cov[:, 2 * c + 1, 2 * c + 1] + ev[k][:, 1]
+            else:
+                cam_out[c, :, k, 7] = cov[:, 2 * c, 2 * c] + ev[k][:, 2 * c]
+                cam_out[c, :, k, 8] = cov[:, 2 * c + 1, 2 * c + 1] + ev[k][:, 2 * c + 1]
+    out3d = np.empty((T, K, 6))
+    for k in range(K):
+        out3d[:, k, 0:3] = ms64[k][:, 0:3]
+        out3d[:, k, 3] = Vs64[k][:, 0, 0]
+        out3d[:, k, 4] = Vs64[k][:, 1, 1]
+        out3d[:, k, 5] = Vs64[k][:, 2, 2]
+    return dict(cam_out=cam_out, out3d=out3d, s_finals=s_finals, info=info, ms=ms, Vs=Vs)

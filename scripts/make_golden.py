@@ -56,6 +56,42 @@ def singlecam_case(name, files, keypoints=None, raw_from=None, **kw):
           res.get('iters_f64'), res.get('iters_f32'))
 
 
+def multicam_case(name, cam_files, camera_names, keypoints=None, calibration=None, **kw):
+    """cam_files: {camera: [csv per seed]}.  Stores raw (M,V,T,K,3) float32 + oracle outputs."""
+    from eks_b200.multicam_smoother import CameraGroup
+    raws = []
+    kps = keypoints
+    for cam in camera_names:
+        r, kps = load_csvs(cam_files[cam], kps)
+        raws.append(r)
+    raw = np.stack(raws, axis=1).astype(np.float32).astype(np.float64)   # (M,V,T,K,3)
+    camgroup = CameraGroup.load(calibration) if calibration else None
+    res = {'raw': raw.astype(np.float32), 'keypoints': np.array(kps), 'cameras': np.array(camera_names)}
+    for tag, dt in (('f64', np.float64), ('f32', np.float32)):
+        r = oracle.multicam(raw, camgroup=camgroup, dtype=dt, **kw)
+        res[f'cam_out_{tag}'] = r['cam_out'].astype(np.float64 if tag == 'f64' else np.float32)
+        res[f'out3d_{tag}'] = r['out3d'].astype(np.float64 if tag == 'f64' else np.float32)
+        res[f's_{tag}'] = r['s_finals']
+        res[f'iters_{tag}'] = r['info']['iters']
+    np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **res)
+    print(name, raw.shape, res['s_f64'], res['iters_f64'], res['iters_f32'])
+
+
+def multicam_goldens():
+    # BASELINE config 3 family: multicam linear on data/mirror-mouse-separate (2 cams x 10? seeds, 501 frames)
+    d = f'{REF}/mirror-mouse-separate'
+    cams = ['top', 'bot']
+    files = {c: sorted(glob.glob(f'{d}/*.{c}.csv')) for c in cams}
+    multicam_case('multicam_mirror_mouse_separate', files, cams, quantile_keep_pca=95.0)
+    # BASELINE config 4 family: calibrated nonlinear EKF on data/fly, bodyparts L1A, L1B
+    # (reference tests/integration/test_multicam.py:31-41)
+    d = f'{REF}/fly'
+    cams = ['Cam-A', 'Cam-B', 'Cam-C']
+    files = {c: sorted(glob.glob(f'{d}/*{c}*.csv')) for c in cams}
+    multicam_case('multicam_fly_nonlinear', files, cams, keypoints=['L1A', 'L1B'],
+                  calibration=f'{d}/calibration.toml', quantile_keep_pca=95.0)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     # BASELINE config 1: `eks singlecam` on data/ibl-pupil (tests/integration/test_singlecam.py:4-10)
@@ -68,3 +104,4 @@ if __name__ == '__main__':
     # mirror-mouse (singlecam on 5 seeds, 501 frames, many keypoints): first 6 keypoints
     singlecam_case('singlecam_mirror_mouse', sorted(glob.glob(f'{REF}/mirror-mouse/*.csv')),
                    keypoints=None)
+    multicam_goldens()

@@ -1,0 +1,132 @@
+"""GPU parity tests for the multi-camera paths (linear PCA latent, calibrated pinhole EKF) through the
+drop-in API and the generic kernels, against oracle-generated golden vectors (scripts/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL64, RTOL32 = 1e-5, 1e-3
+
+
+def _ma(raw):
+    from eks_b200 import MarkerArray
+    return MarkerArray(np.ascontiguousarray(raw), data_fields=['x', 'y', 'likelihood'])
+
+
+def _cam_array(camera_dfs, K):
+    return np.stack([df.to_numpy().reshape(len(df), K, 9) for df in camera_dfs])  # (V,T,K,9)
+
+
+def _check(a, b, rtol, label):
+    for c in range(a.shape[-1]):
+        x, y = a[..., c], b[..., c]
+        scale = np.maximum(np.abs(y), 1e-6)
+        err = np.max(np.abs(x - y) / scale)
+        assert err <= rtol, f'{label}: column {c} rel err {err:.3e} > {rtol}'
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    import eks_b200
+    yield
+    eks_b200.set_precision('float32')
+
+
+def test_multicam_linear_fp64_matches_oracle():
+    import eks_b200
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    g = load_golden('multicam_mirror_mouse_separate')
+    eks_b200.set_precision('float64')
+    kps = [str(k) for k in g['keypoints']]
+    cams = [str(c) for c in g['cameras']]
+    dfs, s, df3 = ensemble_kalman_smoother_multicam(_ma(g['raw'].astype(np.float64)), kps, cams,
+                                                    quantile_keep_pca=95.0)
+    np.testing.assert_allclose(s, g['s_f64'], rtol=RTOL64)
+    _check(_cam_array(dfs, len(kps)), g['cam_out_f64'], RTOL64, 'multicam linear')
+    _check(df3.to_numpy().reshape(-1, len(kps), 6), g['out3d_f64'], RTOL64, 'multicam linear 3d')
+    assert list(dfs[0].columns.get_level_values('coords')[:9]) == [
+        'x', 'y', 'likelihood', 'x_ens_median', 'y_ens_median', 'x_ens_var', 'y_ens_var', 'x_posterior_var',
+        'y_posterior_var']
+
+
+def test_multicam_linear_fp32():
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    g = load_golden('multicam_mirror_mouse_separate')
+    kps = [str(k) for k in g['keypoints']]
+    cams = [str(c) for c in g['cameras']]
+    # at the oracle's s: isolates the smoother/reprojection from the fp32 knife-edge stop rule
+    dfs, s, df3 = ensemble_kalman_smoother_multicam(_ma(g['raw']), kps, cams, quantile_keep_pca=95.0,
+                                                    smooth_param=list(g['s_f64']))
+    assert np.allclose(s, g['s_f64'])
+    out = _cam_array(dfs, len(kps))
+    # fp32 PCA-projected coordinates: compare positions absolutely (pixels), variances relatively
+    np.testing.assert_allclose(out[..., 0:2], g['cam_out_f64'][..., 0:2], atol=2e-3)
+    np.testing.assert_allclose(out[..., 7:9], g['cam_out_f64'][..., 7:9], rtol=5e-3)
+    dfs2, s2, _ = ensemble_kalman_smoother_multicam(_ma(g['raw']), kps, cams, quantile_keep_pca=95.0)
+    np.testing.assert_allclose(s2, g['s_f32'], rtol=0.1)
+
+
+def test_multicam_nonlinear_fp64_matches_oracle():
+    import eks_b200
+    from eks_b200.multicam_smoother import CameraGroup, ensemble_kalman_smoother_multicam
+    g = load_golden('multicam_fly_nonlinear')
+    eks_b200.set_precision('float64')
+    kps = [str(k) for k in g['keypoints']]
+    cams = [str(c) for c in g['cameras']]
+    camgroup = CameraGroup.load(os.path.join(GOLDEN, 'fly_calibration.toml'))
+    dfs, s, df3 = ensemble_kalman_smoother_multicam(_ma(g['raw'].astype(np.float64)), kps, cams,
+                                                    quantile_keep_pca=95.0, camgroup=camgroup)
+    np.testing.assert_allclose(s, g['s_f64'], rtol=1e-4)
+    _check(_cam_array(dfs, len(kps)), g['cam_out_f64'], 1e-4, 'multicam nonlinear')
+    _check(df3.to_numpy().reshape(-1, len(kps), 6), g['out3d_f64'], 1e-4, 'multicam nonlinear 3d')
+
+
+def test_fixed_smooth_param_and_latent_dims():
+    """reference tests/test_multicam_smoother.py:196-228: n_latent in {3,4,5} with 4 cameras, s echoed."""
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    rng = np.random.default_rng(0)
+    M, V, T, K = 3, 4, 120, 2
+    lat = np.cumsum(rng.standard_normal((T, K, 3)), axis=0)
+    W = rng.standard_normal((2 * V, 3))
+    obs = np.einsum('tkd,od->tko', lat, W).reshape(T, K, V, 2).transpose(2, 0, 1, 3)      # (V,T,K,2)
+    raw = np.zeros((M, V, T, K, 3))
+    raw[..., 0:2] = obs[None] + rng.standard_normal((M, V, T, K, 2)) * 0.3 + 100.0
+    raw[..., 2] = rng.uniform(0.8, 1.0, (M, V, T, K))
+    for n_latent in (3, 4, 5):
+        dfs, s, df3 = ensemble_kalman_smoother_multicam(_ma(raw), ['a', 'b'], ['c0', 'c1', 'c2', 'c3'],
+                                                        smooth_param=10.0, n_latent=n_latent)
+        assert len(dfs) == V and dfs[0].shape == (T, K * 9) and np.all(s == 10.0)
+        assert np.all(np.isfinite(dfs[0].to_numpy()))
+    with pytest.raises(ValueError):
+        ensemble_kalman_smoother_multicam(_ma(raw), ['a', 'b'], [])
+
+
+def test_run_kalman_smoother_rejects_python_callable():
+    import eks_b200
+    K, T = 1, 20
+    with pytest.raises(TypeError):
+        eks_b200.run_kalman_smoother(np.zeros((K, T, 6)), np.zeros((K, 3)), np.tile(np.eye(3), (K, 1, 1)),
+                                     np.tile(np.eye(3), (K, 1, 1)), None, np.tile(np.eye(3), (K, 1, 1)),
+                                     np.ones((T, K, 6)), h_fn=lambda x: x)
+
+
+def test_core_api_shapes_and_blocks():
+    """reference tests/test_core.py:155-232 (slow path fills s_finals; members share s; s_frames)."""
+    import eks_b200
+    rng = np.random.default_rng(0)
+    K, T = 3, 30
+    ys = rng.standard_normal((K, T, 2))
+    eye = np.tile(np.eye(2), (K, 1, 1))
+    Rs = np.tile(np.eye(2), (K, T, 1, 1))
+    for s_frames in (None, [(0, 15)]):
+        s_finals = np.empty(K)
+        eks_b200.optimize_smooth_param(ys=ys, m0s=np.zeros((K, 2)), S0s=eye, As=eye, Cs=eye, Qs=eye, Rs=Rs,
+                                       blocks=[[0, 1], [2]], s_finals=s_finals, s_frames=s_frames,
+                                       s_guess_per_k=np.ones(K), safety_cap=5)
+        assert np.all(np.isfinite(s_finals)) and np.all(s_finals > 0) and s_finals[0] == s_finals[1]
+    s, ms, Vs = eks_b200.run_kalman_smoother(ys, np.zeros((K, 2)), eye, eye, eye, eye, np.ones((T, K, 2)),
+                                             smooth_param=[1.0, 2.0, 3.0])
+    assert ms.shape == (K, T, 2) and Vs.shape == (K, T, 2, 2) and list(s) == [1.0, 2.0, 3.0]
