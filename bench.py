@@ -84,7 +84,7 @@ def cpu_leg(M, K, T_sample, steps, warmup):
     from oracle import oracle
     raw = synth_session_host(M, K, T_sample, seed=0)
     cores = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    os.environ['OMP_NUM_THREADS'] = str(cores)   # torchrun exports OMP_NUM_THREADS=1: use every host core
     times, iters = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -309,15 +309,26 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, 'fallback 6.65 TB/s (of fallback)'
     opt_ms = stage_ms.get('optimize_s')
-    # algorithmic bytes of one launch: every NLL evaluation reads the obs planes once (SURVEY 8d:
-    # w * obs bytes per keypoint-frame per evaluation); one launch performs sum_b iters_b evaluations
-    alg_bytes = float(iters.sum().item()) * T * 2 * w
+    # dominant kernel: diag_nll_kernel, launched once per Adam evaluation.  Algorithmic bytes of one launch:
+    # every evaluation reads the observation planes of each still-active sequence once (SURVEY 8d:
+    # w * obs bytes per keypoint-frame per evaluation).  Launch duration = CUDA-event time of the optimiser
+    # stage / number of launches that had work (the interleaved one-warp Adam kernels, ~2% of the stage per
+    # the ncu launch list, are included => the fraction is slightly pessimistic).
+    n_launch = max(1, n_eval_max)
+    alg_bytes = float(iters.sum().item()) * T * 2 * w / n_launch
     roofline = None
     if opt_ms:
-        achieved = alg_bytes / (opt_ms * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'diag_optimize_kernel', 'achieved': achieved, 'peak': peak,
-                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': opt_ms,
+        launch_ms = opt_ms / n_launch
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):   # dram bytes per algorithmic byte from the committed ncu --set full capture
+            tj = json.load(open(tpath)).get('diag_nll_kernel')
+            if tj:
+                traffic = alg_bytes * tj['dram_bytes'] / tj['algorithmic_bytes']
+        roofline = {'bound': 'hbm', 'kernel': 'diag_nll_kernel', 'achieved': achieved, 'peak': peak,
+                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': alg_bytes, 'launches': n_launch, 'launch_ms': launch_ms,
                     'share_of_step': opt_ms / ms_step}
     b_alg = w * (3 * M + 9)
     pipeline_frac = (kf_step * b_alg / (ms_step * 1e-3) / 1e9) / peak

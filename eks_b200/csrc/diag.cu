@@ -45,6 +45,7 @@ template <> struct DiagTraits<double> {
 template <class P>
 struct ChanConst {
     P alpha, beta, a, cc, dalpha, dbeta, iS, diS, logS, dlogS;
+    P gamma;         // -c beta: coupling of the scaled recursion (see diag_tile)
     P aL[5], bL[5];  // Phi^(L 2^k) = [[aL,0],[bL,aL]]
     P aW, bW;        // Phi^(32 L)
     P aH, bH;        // Phi^(L/2)
@@ -243,8 +244,13 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     k.logS = log_(S);
     k.dlogS = dS * iS;
     constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    k.aH = pow_(k.alpha, P(L / 2));
-    k.bH = P(L / 2) * pow_(k.alpha, P(L / 2 - 1)) * k.dalpha;
+    k.gamma = -cc * k.beta;
+    // Phi^(L/2) of the scaled recursion by repeated squaring of Phi = [[alpha,0],[gamma,alpha]]
+    {
+        P pa = k.alpha, pb = k.gamma;
+        for (int h = 1; h < L / 2; h <<= 1) { pb = P(2) * pa * pb; pa = pa * pa; }
+        k.aH = pa; k.bH = pb;
+    }
     P aL = k.aH * k.aH;                 // Phi^L = (Phi^(L/2))^2: keeps the half/full powers consistent
     P bL = P(2) * k.aH * k.bH;
 #pragma unroll
@@ -260,8 +266,9 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
         out.a_lane[l] = k.aL[0] * out.a_lane[l - 1];
         out.b_lane[l] = k.aL[0] * out.b_lane[l - 1] + k.bL[0] * out.a_lane[l - 1];
     }
-    out.z0[0] = m;
-    out.z0[1] = dm;
+    // scaled state: mt = m / beta, dt = dm / dbeta  (dm' = alpha dm + dbeta e  =>  dt' = alpha dt + e)
+    out.z0[0] = m / k.beta;
+    out.z0[1] = (k.dbeta != P(0)) ? dm / k.dbeta : P(0);
     out.tsum[0] = sl; out.tsum[1] = sdl; out.tsum[2] = se; out.tsum[3] = sde; out.tsum[4] = sg;
     out.t_c = t;
     // frames after which the response to the state at their start has decayed below rounding:
@@ -289,6 +296,11 @@ template <> __device__ inline double2 lds_volatile<double2>(const unsigned char*
 
 // One tile of DIAG_NT * L frames of one channel; y[] is the thread's register-resident chunk (already
 // centred).  E2/G are this thread's fp64 accumulators.  ACC = false: warm-up tile (carry only).
+//
+// The recursion runs in SCALED variables mt = m / beta, dt = (dm/ds) / dbeta, which removes every
+// multiply that is not fused:   mt' = alpha mt + y,   e = y + gamma mt  (gamma = -c beta),   dt' = alpha dt + e,
+// i.e. z' = Phi z + (y, y) with Phi = [[alpha, 0], [gamma, alpha]]  (5 FMA per frame in phase 3).
+// sum e^2 is unchanged and sum e dm = dbeta * sum e dt (applied once, in diag_adam_kernel).
 // The chunk is processed as two independent half-chunks (two dependency chains in flight per thread):
 // the zero-state responses of the halves are combined with Phi^(L/2), and the second half of phase 3
 // starts from the exact mid-chunk state Phi^(L/2) z_in + z_a.
@@ -298,8 +310,8 @@ __device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& s
     constexpr int H = L / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ChanConst<P>& k = sh.ch;
-    const P alpha = k.alpha;
-    // phase 1: zero-state responses.  U = sum alpha^(H-1-i) y_i, W = dU/dalpha, per half
+    const P alpha = k.alpha, gamma = k.gamma;
+    // phase 1: zero-state responses.  U = sum alpha^(H-1-i) y_i (= mt),  W = sum alpha^(H-1-i) U_i
     P Ua = P(0), Wa = P(0), Ub = P(0), Wb = P(0);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
@@ -308,10 +320,9 @@ __device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& s
         Ua = fma(alpha, Ua, y[i]);
         Ub = fma(alpha, Ub, y[H + i]);
     }
-    const P bda = k.beta * k.dalpha;
-    const P zam = k.beta * Ua, zad = fma(k.dbeta, Ua, bda * Wa);   // first half, zero state
-    const P zbm = k.beta * Ub, zbd = fma(k.dbeta, Ub, bda * Wb);   // second half, zero state
-    const P aH = k.aH, bH = k.bH;                                  // Phi^(L/2)
+    const P zam = Ua, zad = fma(gamma, Wa, Ua);   // first half from a zero state: (mt, dt)
+    const P zbm = Ub, zbd = fma(gamma, Wb, Ub);   // second half from a zero state
+    const P aH = k.aH, bH = k.bH;                 // Phi^(L/2)
     P zm = fma(aH, zam, zbm);
     P zd = fma(aH, zad, fma(bH, zam, zbd));
     // warp inclusive scan with the closed-form powers of Phi
@@ -360,19 +371,18 @@ __device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& s
         }
     }
 #endif
-    // phase 3: m' = alpha m + beta y (one dependent FMA per frame), e = y - c m, dm' = alpha dm + dbeta e
-    const P beta = k.beta, dbeta = k.dbeta, cc = k.cc;
+    // phase 3 (5 FMA per frame)
     P e2a = P(0), ga = P(0), e2b = P(0), gb = P(0);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
-        const P ea = fma(-cc, m0, y[i]);
-        const P eb = fma(-cc, m1, y[H + i]);
-        m0 = fma(alpha, m0, beta * y[i]);
-        m1 = fma(alpha, m1, beta * y[H + i]);
+        const P ea = fma(gamma, m0, y[i]);
+        const P eb = fma(gamma, m1, y[H + i]);
+        m0 = fma(alpha, m0, y[i]);
+        m1 = fma(alpha, m1, y[H + i]);
         if (FULL || i < nvalid) { e2a = fma(ea, ea, e2a); ga = fma(ea, d0, ga); }
         if (FULL || H + i < nvalid) { e2b = fma(eb, eb, e2b); gb = fma(eb, d1, gb); }
-        d0 = fma(alpha, d0, dbeta * ea);
-        d1 = fma(alpha, d1, dbeta * eb);
+        d0 = fma(alpha, d0, ea);
+        d1 = fma(alpha, d1, eb);
     }
     E2 += (double)(e2a + e2b);
     G += (double)(ga + gb);
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ D
                     nll += (double)a.n * HALF_LOG2PI + 0.5 * cs.tsum[0] + 0.5 * cs.tsum[2] + 0.5 * nB * (double)k.logS +
                            0.5 * (double)k.iS * te;
                     dnll += 0.5 * cs.tsum[1] + 0.5 * cs.tsum[3] - cs.tsum[4] + 0.5 * nB * (double)k.dlogS +
-                            0.5 * (double)k.diS * te - (double)k.cc * (double)k.iS * tg;
+                            0.5 * (double)k.diS * te - (double)k.cc * (double)k.iS * (double)k.dbeta * tg;
                 }
                 P v = (P)nll, g = (P)dnll;
                 if (!isfinite(nll) || !isfinite((double)v)) { v = P(1e12); g = P(0); }  // core.py:650
@@ -581,10 +591,14 @@ __global__ void diag_seq_block_kernel(int n_blocks, const int* __restrict__ bloc
     for (int mi = block_off[j]; mi < block_off[j + 1]; ++mi) seq_block[members[mi]] = j;
 }
 
-static int diag_nseg(int dtype, int n) {
+static int diag_nseg(int dtype, int n, int B) {
     const int L = OPT_CHUNK_BYTES / (dtype == EKS_F32 ? 4 : 8);
     const int ntile = (n + DIAG_NT * L - 1) / (DIAG_NT * L);
-    int nseg = ntile / 12;  // >= 12 tiles per segment keeps the one-tile warm-up below ~3% of the traffic
+    // >= 12 tiles per segment keeps the warm-up below ~3% of the work ...
+    int nseg = ntile / 12;
+    // ... but a small batch needs more, shorter segments to put ~2 waves of CTAs on the 148 SMs
+    const int want = (600 + 2 * B - 1) / (2 * B);
+    if (nseg < want) nseg = want < ntile / 2 ? want : ntile / 2;
     if (nseg < 1) nseg = 1;
     if (nseg > 16) nseg = 16;
     return nseg;
@@ -593,7 +607,7 @@ static int diag_nseg(int dtype, int n) {
 size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     const size_t real = dtype == EKS_F32 ? 4 : 8;
     (void)real;
-    const int nseg = diag_nseg(dtype, T);
+    const int nseg = 16;  // upper bound of diag_nseg
     size_t bytes = 256;
     bytes += (size_t)n_blocks * 128;                   // BlockState
     bytes += (size_t)B * 2 * 1024;                     // ChanState (generous bound)
@@ -606,7 +620,7 @@ template <class P>
 static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspace_bytes, int dtype, int T,
                              cudaStream_t st) {
     static_assert(sizeof(BlockState<P>) <= 128 && sizeof(ChanState<P>) <= 1024, "workspace bound");
-    a.nseg = diag_nseg(dtype, a.n);
+    a.nseg = diag_nseg(dtype, a.n, a.B);
     EKS_REQUIRE(workspace && workspace_bytes >= diag_optimize_workspace_bytes(dtype, a.n_blocks, a.B, T),
                 "optimize_s: workspace too small");
     unsigned char* w = (unsigned char*)workspace;

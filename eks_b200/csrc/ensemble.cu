@@ -276,48 +276,66 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         }
     }
     if (partials != nullptr) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+        // per-tile moments of the averaged coordinates: row = (coordinate, keypoint), LPR lanes per row with
+        // 4 frames each, fixed xor tree inside the lane group (deterministic)
+        const int LPR = TT >> 2;                       // TT in {8,16,32,64} -> 2..16 lanes per row
+        const int rows_per_pass = blockDim.x / LPR;
+        const int q = threadIdx.x & (LPR - 1);
         const int ntiles = gridDim.x;
-        for (int k = warp; k < K; k += nwarp) {
-            double sx = 0, sy = 0, sxx = 0, syy = 0;
-            for (int tl = lane; tl < nt; tl += 32) {
-                const double x = (double)tile[(0 * K + k) * ld + tl];
-                const double y = (double)tile[(1 * K + k) * ld + tl];
-                sx += x; sy += y; sxx += x * x; syy += y * y;
+        const int npass = (2 * K + rows_per_pass - 1) / rows_per_pass;
+        for (int ps = 0; ps < npass; ++ps) {
+            const int row = ps * rows_per_pass + threadIdx.x / LPR;
+            const bool rv = row < 2 * K;
+            const int c = rv ? row / K : 0, k = rv ? row - c * K : 0;
+            double sm = 0, sq = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int tl = q * 4 + jj;
+                if (rv && tl < nt) {
+                    const double x = (double)tile[(c * K + k) * ld + tl];
+                    sm += x;
+                    sq += x * x;
+                }
             }
-            sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); syy = warp_sum(syy);
-            if (lane == 0) {
+            for (int off = LPR >> 1; off > 0; off >>= 1) {
+                sm += __shfl_xor_sync(0xffffffffu, sm, off);
+                sq += __shfl_xor_sync(0xffffffffu, sq, off);
+            }
+            if (rv && q == 0) {
                 double* pp = partials + ((((long long)sess * V + v) * K + k) * ntiles + tile_idx) * 4;
-                pp[0] = sx; pp[1] = sy; pp[2] = sxx; pp[3] = syy;
+                pp[c] = sm;
+                pp[2 + c] = sq;
             }
         }
     }
 }
 
-// reduce the per-tile partials in a fixed order: one warp per (session, camera, keypoint)
+// reduce the per-tile partials in a fixed order: one CTA per (session, camera, keypoint)
 template <class P>
-__global__ void moments_finalize_kernel(const double* __restrict__ partials, int nseq, int ntiles, long long T,
-                                        P* __restrict__ mean_out, P* __restrict__ var_out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nseq) return;
-    const double* pp = partials + (long long)warp * ntiles * 4;
+__global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __restrict__ partials, int nseq,
+                                                               int ntiles, long long T, P* __restrict__ mean_out,
+                                                               P* __restrict__ var_out) {
+    __shared__ double scratch[32];
+    const int seq = blockIdx.x;
+    const double* pp = partials + (long long)seq * ntiles * 4;
     double a[4] = {0, 0, 0, 0};
-    for (int i = lane; i < ntiles; i += 32) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] += pp[(long long)i * 4 + q];
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) {
+        const double2 lo = *reinterpret_cast<const double2*>(pp + (long long)i * 4);
+        const double2 hi = *reinterpret_cast<const double2*>(pp + (long long)i * 4 + 2);
+        a[0] += lo.x; a[1] += lo.y; a[2] += hi.x; a[3] += hi.y;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = warp_sum(a[q]);
-    if (lane == 0) {
+    for (int q = 0; q < 4; ++q) a[q] = block_sum(a[q], scratch);
+    if (threadIdx.x == 0) {
         const double n = (double)T;
         const double mx = a[0] / n, my = a[1] / n;
         // the centred data are formed in precision P (x - P(mean)); its variance about its own mean
         // equals the variance of x, so S0 = E[x^2] - mean^2 in fp64 (utils.py:350-351,
         // singlecam_smoother.py:262-266)
-        mean_out[warp * 2 + 0] = P(mx);
-        mean_out[warp * 2 + 1] = P(my);
-        var_out[warp * 2 + 0] = P(fmax(a[2] / n - mx * mx, 0.0));
-        var_out[warp * 2 + 1] = P(fmax(a[3] / n - my * my, 0.0));
+        mean_out[seq * 2 + 0] = P(mx);
+        mean_out[seq * 2 + 1] = P(my);
+        var_out[seq * 2 + 0] = P(fmax(a[2] / n - mx * mx, 0.0));
+        var_out[seq * 2 + 1] = P(fmax(a[3] / n - my * my, 0.0));
     }
 }
 
@@ -428,14 +446,12 @@ extern "C" int eks_center_moments(const double* moment_partials, int n_seq, int 
                                   void* var_out, int dtype, void* stream) {
     EKS_REQUIRE(moment_partials && mean_out && var_out, "center_moments: null pointer");
     const int ntiles = n_tiles;
-    const int threads = 128, warps_per_block = threads / 32;
-    const int blocks = (n_seq + warps_per_block - 1) / warps_per_block;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == EKS_F32)
-        moments_finalize_kernel<float><<<blocks, threads, 0, st>>>(moment_partials, n_seq, ntiles, T,
-                                                                   (float*)mean_out, (float*)var_out);
+        moments_finalize_kernel<float><<<n_seq, 256, 0, st>>>(moment_partials, n_seq, ntiles, T, (float*)mean_out,
+                                                              (float*)var_out);
     else
-        moments_finalize_kernel<double><<<blocks, threads, 0, st>>>(moment_partials, n_seq, ntiles, T,
-                                                                    (double*)mean_out, (double*)var_out);
+        moments_finalize_kernel<double><<<n_seq, 256, 0, st>>>(moment_partials, n_seq, ntiles, T, (double*)mean_out,
+                                                               (double*)var_out);
     return check_launch("moments_finalize_kernel");
 }
