@@ -280,36 +280,23 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     out.warm = (int)w;
 }
 
-template <class V> __device__ inline V lds_volatile(const unsigned char* p);
-template <> __device__ inline float4 lds_volatile<float4>(const unsigned char* p) {
-    float4 v;
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa));
-    return v;
-}
-template <> __device__ inline double2 lds_volatile<double2>(const unsigned char* p) {
-    double2 v;
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(sa));
-    return v;
-}
-
-// One tile of DIAG_NT * L frames of one channel; y[] is the thread's register-resident chunk (already
-// centred).  E2/G are this thread's fp64 accumulators.  ACC = false: warm-up tile (carry only).
+// One WARP-tile: 32 lanes x L frames of one channel, y[] = the lane's register-resident chunk (already
+// centred).  Every warp owns a contiguous run of warp-tiles, so the whole evaluation needs no block-wide
+// barrier: the only cross-lane traffic is the 5-step shuffle scan below.
 //
 // The recursion runs in SCALED variables mt = m / beta, dt = (dm/ds) / dbeta, which removes every
 // multiply that is not fused:   mt' = alpha mt + y,   e = y + gamma mt  (gamma = -c beta),   dt' = alpha dt + e,
 // i.e. z' = Phi z + (y, y) with Phi = [[alpha, 0], [gamma, alpha]]  (5 FMA per frame in phase 3).
 // sum e^2 is unchanged and sum e dm = dbeta * sum e dt (applied once, in diag_adam_kernel).
-// The chunk is processed as two independent half-chunks (two dependency chains in flight per thread):
+// The chunk is processed as two independent half-chunks (two dependency chains in flight per lane):
 // the zero-state responses of the halves are combined with Phi^(L/2), and the second half of phase 3
 // starts from the exact mid-chunk state Phi^(L/2) z_in + z_a.
+// (cm, cd) is the warp's carry: state at the first frame of this warp-tile on entry, of the next on exit.
 template <class P, int L, bool FULL, bool ACC>
-__device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& sh, P a_lane, P b_lane,
-                                 double& E2, double& G, const unsigned char* mine = nullptr, P mean = P(0)) {
+__device__ inline void diag_warp_tile(const P (&y)[L], int nvalid, const ChanConst<P>& k, P a_lane, P b_lane,
+                                      P& cm, P& cd, double& E2, double& G) {
     constexpr int H = L / 2;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const ChanConst<P>& k = sh.ch;
+    const int lane = threadIdx.x & 31;
     const P alpha = k.alpha, gamma = k.gamma;
     // phase 1: zero-state responses.  U = sum alpha^(H-1-i) y_i (= mt),  W = sum alpha^(H-1-i) U_i
     P Ua = P(0), Wa = P(0), Ub = P(0), Wb = P(0);
@@ -336,41 +323,18 @@ __device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& s
             zm = fma(k.aL[q], pm, zm);
         }
     }
-    if (lane == 31) { sh.agg[buf][warp][0] = zm; sh.agg[buf][warp][1] = zd; }
     P em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
     if (lane == 0) { em = P(0); ed = P(0); }
-    __syncthreads();
-    // carry at the start of this warp: tile carry pushed through the preceding warps' aggregates
-    P cm = sh.z_tile[buf][0], cd = sh.z_tile[buf][1];
-    const P aW = k.aW, bW = k.bW;
-    for (int w = 0; w < warp; ++w) {
-        const P nm = fma(aW, cm, sh.agg[buf][w][0]);
-        cd = fma(aW, cd, fma(bW, cm, sh.agg[buf][w][1]));
-        cm = nm;
-    }
-    if (warp == DIAG_NW - 1 && lane == 0) {  // carry for the next tile (other buffer)
-        sh.z_tile[buf ^ 1][0] = fma(aW, cm, sh.agg[buf][warp][0]);
-        sh.z_tile[buf ^ 1][1] = fma(aW, cd, fma(bW, cm, sh.agg[buf][warp][1]));
-    }
+    const P tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);  // warp aggregate
+    const P cm0 = cm, cd0 = cd;
+    cm = fma(k.aW, cm0, tm);                       // carry for the next warp-tile: Phi^(32 L) c + aggregate
+    cd = fma(k.aW, cd0, fma(k.bW, cm0, td));
     if (!ACC) return;
     // exact states at the start of the two half-chunks
-    P m0 = fma(a_lane, cm, em);
-    P d0 = fma(a_lane, cd, fma(b_lane, cm, ed));
+    P m0 = fma(a_lane, cm0, em);
+    P d0 = fma(a_lane, cd0, fma(b_lane, cm0, ed));
     P m1 = fma(aH, m0, zam);
     P d1 = fma(aH, d0, fma(bH, m0, zad));
-#if EKS_OPT_RELOAD
-    if (FULL) {  // re-read the chunk from the ring stage so that y[] need not live across the scan
-        using V = typename DiagTraits<P>::vec_t;
-        constexpr int VW = DiagTraits<P>::VW;
-#pragma unroll
-        for (int i = 0; i < L / VW; ++i) {
-            const V v = lds_volatile<V>(mine + i * 16);
-            const P* e = reinterpret_cast<const P*>(&v);
-#pragma unroll
-            for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
-        }
-    }
-#endif
     // phase 3 (5 FMA per frame)
     P e2a = P(0), ga = P(0), e2b = P(0), gb = P(0);
 #pragma unroll
@@ -388,16 +352,65 @@ __device__ inline void diag_tile(P (&y)[L], int nvalid, int buf, OptShared<P>& s
     G += (double)(ga + gb);
 }
 
+// per-warp ring stage: 32 padded chunks
+constexpr int WRP_STAGE_BYTES = 32 * OPT_PAD_BYTES;
+
+// Asynchronous copy of one warp-tile (32 x L frames starting at frame t0) into a warp's ring stage; frames
+// outside [e_min, n) are zero-filled without touching memory.  Lane l fetches granules l, l+32, ...:
+// every instruction is one fully coalesced 512-byte request.
+template <class P>
+__device__ inline void warp_issue_tile(unsigned char* stage, const P* __restrict__ plane, int t0, int e_min, int n,
+                                       bool vec, bool inner) {
+    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
+    constexpr int EPG = 16 / (int)sizeof(P);
+    constexpr int GPC = OPT_CHUNK_BYTES / 16;
+    const int lane = threadIdx.x & 31;
+    if (vec && inner) {
+        const int j0 = lane / GPC, q = lane % GPC;
+        const P* src = plane + t0 + j0 * L + q * EPG;
+        unsigned char* dst = stage + j0 * OPT_PAD_BYTES + q * 16;
+        constexpr int CPI = 32 / GPC;  // chunks covered per instruction
+#pragma unroll
+        for (int i = 0; i < GPC; ++i) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * CPI * OPT_PAD_BYTES);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i * CPI * L) : "memory");
+        }
+    } else if (vec) {
+#pragma unroll
+        for (int i = 0; i < GPC; ++i) {
+            const int v = i * 32 + lane;
+            const int j = v / GPC, q = v - j * GPC;
+            const int e = t0 + j * L + q * EPG;
+            int valid = max(0, min(EPG, n - e)) * (int)sizeof(P);
+            if (e < e_min) valid = 0;  // e_min is chunk aligned: whole granules
+            cp_async_16(stage + j * OPT_PAD_BYTES + q * 16, plane + (valid > 0 ? e : 0), valid);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < L; ++i) {
+            const int v = i * 32 + lane;
+            const int j = v / L, q = v - j * L;
+            const int e = t0 + j * L + q;
+            const int valid = (e < n && e >= e_min) ? (int)sizeof(P) : 0;
+            if (sizeof(P) == 4) cp_async_4(stage + j * OPT_PAD_BYTES + q * 4, plane + (valid > 0 ? e : 0), valid);
+            else cp_async_8(stage + j * OPT_PAD_BYTES + q * 8, plane + (valid > 0 ? e : 0), valid);
+        }
+    }
+}
+
 // ---- kernel A: one NLL(+d/ds) evaluation.  grid = (nseg, 2 * B): CTA (k, 2b+c) handles segment k of
-// channel c of sequence b.  A segment is a run of tiles; it starts from the exact state at t_c (segment 0
-// or slow forgetting) or from a zero state `warm` frames earlier, which is exact to rounding because the
-// steady-state filter forgets its initial state geometrically (alpha^warm < 1e-14 / 1e-28).
+// channel c of sequence b, and each of its 8 warps an independent contiguous run of warp-tiles (32 lanes x
+// L frames) inside it.  A run starts from the exact state at t_c (first run, or slow forgetting) or from a
+// zero state `warm` frames earlier, which is exact to rounding because the steady-state filter forgets its
+// initial state geometrically (alpha^warm < 1e-14 / 1e-28).  Warps never synchronise with each other until
+// the final reduction; each streams its own 2-stage cp.async ring.
 template <class P>
 __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
-    __shared__ OptShared<P> sh;
+    __shared__ ChanConst<P> shk;
+    __shared__ double red[DIAG_NW][2];
     extern __shared__ __align__(16) unsigned char ring[];
     constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    constexpr int TILE = DIAG_NT * L;
+    constexpr int WT = 32 * L;  // frames per warp-tile
     using V = typename DiagTraits<P>::vec_t;
     constexpr int VW = DiagTraits<P>::VW;
     const int seg = blockIdx.x, b = blockIdx.y >> 1, c = blockIdx.y & 1;
@@ -407,102 +420,91 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
     const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
     double* part = a.partials + (((long long)b * 2 + c) * a.nseg + seg) * 2;
     const int t_c = cs.t_c;
-    const int ntile = (a.n - t_c + TILE - 1) / TILE;
-    const int tps = (ntile + a.nseg - 1) / a.nseg;
-    const int tile_lo = seg * tps, tile_hi = min(ntile, tile_lo + tps);
-    if (tile_lo >= tile_hi) {
-        if (threadIdx.x == 0) { part[0] = 0.0; part[1] = 0.0; }
-        return;
-    }
-    // warm-up: whole chunks, starting `warm` frames before the segment
-    const int warm_chunks = (cs.warm + L - 1) / L;
-    long long e_min_ll = (long long)t_c + (long long)tile_lo * TILE - (long long)warm_chunks * L;
-    int first_tile, e_min;
-    bool exact_start;
-    if (tile_lo == 0 || e_min_ll <= (long long)t_c) {
-        first_tile = 0; e_min = 0; exact_start = true;
-    } else {
-        e_min = (int)e_min_ll;
-        first_tile = (e_min - t_c) / TILE;
-        exact_start = false;
-    }
-    if (threadIdx.x == 0) {
-        sh.ch = cs.k;
-        sh.z_tile[0][0] = exact_start ? cs.z0[0] : P(0);
-        sh.z_tile[0][1] = exact_start ? cs.z0[1] : P(0);
-    }
+    if (threadIdx.x == 0) shk = cs.k;
     __syncthreads();
-    const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
-    const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
-    const bool vec = (reinterpret_cast<uintptr_t>(yc + t_c) & 15) == 0;
-    // per-thread powers Phi^(L lane) for folding the warp carry into the exclusive prefix
-    const P a_lane = cs.a_lane[lane], b_lane = cs.b_lane[lane];
+    // this warp's run of warp-tiles
+    const int nwt = (a.n - t_c + WT - 1) / WT;
+    const int nrun = a.nseg * DIAG_NW;
+    const int wpr = (nwt + nrun - 1) / nrun;
+    const int run = seg * DIAG_NW + warp;
+    const int wt_lo = min(nwt, run * wpr), wt_hi = min(nwt, wt_lo + wpr);
     double E2 = 0, G = 0;
-    const int nt = tile_hi - first_tile;
-    // per-thread bases of the fast copy path: granule (threadIdx.x) of round 0
-    constexpr int GPC = OPT_CHUNK_BYTES / 16;
-    constexpr int EPG = 16 / (int)sizeof(P);
-    const int g_chunk = threadIdx.x / GPC, g_q = threadIdx.x % GPC;
-    const int fast_goff = g_chunk * L + g_q * EPG;                    // elements from the tile start
-    const int fast_soff = g_chunk * OPT_PAD_BYTES + g_q * 16;         // bytes from the stage start
-    auto issue = [&](int stage, int tile) {
-        const int t0i = t_c + tile * TILE;
-        if (vec && t0i >= e_min && t0i + TILE <= a.n)
-            opt_issue_tile_fast<P>(ring + stage * OPT_STAGE_BYTES + fast_soff, yc + t0i + fast_goff);
-        else
-            opt_issue_tile<P>(ring + stage * OPT_STAGE_BYTES, yc, t0i, e_min, a.n, vec);
-    };
-#pragma unroll
-    for (int st = 0; st < OPT_STAGES - 1; ++st) {
-        if (st < nt) issue(st, first_tile + st);
-        cp_async_commit();
-    }
-    int buf = 0;
-    for (int it = 0; it < nt; ++it, buf ^= 1) {
-        cp_async_wait<OPT_STAGES - 2>();
-        __syncthreads();  // tile `it` has landed for everyone; the stage read in iteration it-1 is free again
-        const int nx = it + OPT_STAGES - 1;
-        if (nx < nt) issue(nx % OPT_STAGES, first_tile + nx);
-        cp_async_commit();
-        const unsigned char* mine = ring + (it % OPT_STAGES) * OPT_STAGE_BYTES + threadIdx.x * OPT_PAD_BYTES;
-        const int t0 = t_c + (first_tile + it) * TILE;
-        const int cstart = t0 + (int)threadIdx.x * L;
-        // centred observations; masked (warm-up prefix / beyond the end) frames stay exactly zero
-        P y[L];
-        const bool inner = (t0 >= e_min) && (t0 + TILE <= a.n);  // uniform: no masked frames in this tile
-        if (inner) {
-#pragma unroll
-            for (int i = 0; i < L / VW; ++i) {
-                const V v = *reinterpret_cast<const V*>(mine + i * 16);
-                const P* e = reinterpret_cast<const P*>(&v);
-#pragma unroll
-                for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
-            }
+    if (wt_lo < wt_hi) {
+        // warm-up: whole chunks, starting `warm` frames before the run
+        const int warm_chunks = (cs.warm + L - 1) / L;
+        const long long e_min_ll = (long long)t_c + (long long)wt_lo * WT - (long long)warm_chunks * L;
+        int first_wt, e_min;
+        P cm, cd;
+        if (wt_lo == 0 || e_min_ll <= (long long)t_c) {
+            first_wt = 0; e_min = 0; cm = cs.z0[0]; cd = cs.z0[1];
         } else {
+            e_min = (int)e_min_ll;
+            first_wt = (e_min - t_c) / WT;
+            cm = P(0); cd = P(0);
+        }
+        const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
+        const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
+        const bool vec = (reinterpret_cast<uintptr_t>(yc + t_c) & 15) == 0;
+        const P a_lane = cs.a_lane[lane], b_lane = cs.b_lane[lane];
+        unsigned char* wring = ring + warp * (OPT_STAGES * WRP_STAGE_BYTES);
+        const int nt = wt_hi - first_wt;
+        auto issue = [&](int stage, int wt) {
+            const int t0i = t_c + wt * WT;
+            warp_issue_tile<P>(wring + stage * WRP_STAGE_BYTES, yc, t0i, e_min, a.n, vec,
+                               t0i >= e_min && t0i + WT <= a.n);
+        };
 #pragma unroll
-            for (int i = 0; i < L / VW; ++i) {
-                const V v = *reinterpret_cast<const V*>(mine + i * 16);
-                const P* e = reinterpret_cast<const P*>(&v);
+        for (int st = 0; st < OPT_STAGES - 1; ++st) {
+            if (st < nt) issue(st, first_wt + st);
+            cp_async_commit();
+        }
+        for (int it = 0; it < nt; ++it) {
+            const int nx = it + OPT_STAGES - 1;
+            // the stage about to be refilled was read in iteration it-1; make sure every lane is done with it
+            __syncwarp();
+            if (nx < nt) issue(nx % OPT_STAGES, first_wt + nx);
+            cp_async_commit();
+            cp_async_wait<OPT_STAGES - 1>();
+            __syncwarp();  // tile `it` has landed for every lane of this warp
+            const unsigned char* mine = wring + (it % OPT_STAGES) * WRP_STAGE_BYTES + lane * OPT_PAD_BYTES;
+            const int t0 = t_c + (first_wt + it) * WT;
+            const int cstart = t0 + lane * L;
+            P y[L];
+            const bool inner = (t0 >= e_min) && (t0 + WT <= a.n);  // warp-uniform: no masked frames
+            if (inner) {
 #pragma unroll
-                for (int q = 0; q < VW; ++q) {
-                    const int fr = cstart + i * VW + q;
-                    y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
+                for (int i = 0; i < L / VW; ++i) {
+                    const V v = *reinterpret_cast<const V*>(mine + i * 16);
+                    const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < L / VW; ++i) {
+                    const V v = *reinterpret_cast<const V*>(mine + i * 16);
+                    const P* e = reinterpret_cast<const P*>(&v);
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) {
+                        const int fr = cstart + i * VW + q;
+                        y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
+                    }
                 }
             }
+            const bool acc = (first_wt + it) >= wt_lo;
+            if (!acc) diag_warp_tile<P, L, true, false>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
+            else if (inner) diag_warp_tile<P, L, true, true>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
+            else diag_warp_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), shk, a_lane, b_lane, cm, cd, E2, G);
         }
-        const bool acc = (first_tile + it) >= tile_lo;
-        if (!acc) diag_tile<P, L, true, false>(y, L, buf, sh, a_lane, b_lane, E2, G);
-        else if (t0 + TILE <= a.n && inner) diag_tile<P, L, true, true>(y, L, buf, sh, a_lane, b_lane, E2, G, mine, mean);
-        else diag_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), buf, sh, a_lane, b_lane, E2, G);
+        cp_async_wait<0>();
     }
-    cp_async_wait<0>();
     E2 = warp_sum(E2);
     G = warp_sum(G);
-    if (lane == 0) { sh.red[warp][0] = E2; sh.red[warp][1] = G; }
+    if (lane == 0) { red[warp][0] = E2; red[warp][1] = G; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double te = 0, tg = 0;
-        for (int w = 0; w < DIAG_NW; ++w) { te += sh.red[w][0]; tg += sh.red[w][1]; }
+        for (int w = 0; w < DIAG_NW; ++w) { te += red[w][0]; tg += red[w][1]; }
         part[0] = te;
         part[1] = tg;
     }
@@ -592,13 +594,15 @@ __global__ void diag_seq_block_kernel(int n_blocks, const int* __restrict__ bloc
 }
 
 static int diag_nseg(int dtype, int n, int B) {
+    // Work unit = one warp's run of warp-tiles (32 lanes x L frames); a CTA holds 8 runs.  Each run pays a
+    // warm-up of >= 1 warp-tile, so runs should be >= ~24 warp-tiles long (<= 4% overhead), while the grid
+    // should hold a few waves of CTAs (148 SMs x 3 CTAs).
     const int L = OPT_CHUNK_BYTES / (dtype == EKS_F32 ? 4 : 8);
-    const int ntile = (n + DIAG_NT * L - 1) / (DIAG_NT * L);
-    // >= 12 tiles per segment keeps the warm-up below ~3% of the work ...
-    int nseg = ntile / 12;
-    // ... but a small batch needs more, shorter segments to put ~2 waves of CTAs on the 148 SMs
-    const int want = (600 + 2 * B - 1) / (2 * B);
-    if (nseg < want) nseg = want < ntile / 2 ? want : ntile / 2;
+    const int nwt = (n + 32 * L - 1) / (32 * L);
+    int nseg = nwt / (DIAG_NW * 24);
+    const int want = (900 + 2 * B - 1) / (2 * B);          // ~2 waves of CTAs for small batches
+    const int cap = nwt / (DIAG_NW * 2) > 0 ? nwt / (DIAG_NW * 2) : 1;
+    if (nseg < want) nseg = want < cap ? want : cap;
     if (nseg < 1) nseg = 1;
     if (nseg > 16) nseg = 16;
     return nseg;
@@ -630,7 +634,7 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     a.partials = (double*)w; w += (size_t)a.B * 2 * a.nseg * 2 * sizeof(double);
     int* seq_block = (int*)w;
     a.seq_block = seq_block;
-    const int smem = OPT_STAGES * OPT_STAGE_BYTES;
+    const int smem = DIAG_NW * OPT_STAGES * WRP_STAGE_BYTES;
     cudaError_t e = cudaFuncSetAttribute(diag_nll_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         set_error("diag_nll_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));

@@ -195,6 +195,27 @@ __device__ inline void ens_cp_async_small(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(sa), "l"(gmem), "n"(BYTES) : "memory");
 }
 
+// NaN-free statistics of one coordinate (all M seeds valid): mean, ddof-0 variance in seed order, median
+// from the fixed middle positions of the exact-size sorting network.
+template <class P, int M>
+__device__ __forceinline__ void coord_stats_clean(const P (&x)[M], bool avg_median, P& avg, P& var) {
+    P sum = P(0);
+#pragma unroll
+    for (int m = 0; m < M; ++m) sum += x[m];
+    const P mean = sum / P(M);
+    P ss = P(0);
+#pragma unroll
+    for (int m = 0; m < M; ++m) { const P d = x[m] - mean; ss += d * d; }
+    var = ss / P(M);
+    if (!avg_median) { avg = mean; return; }
+    P s[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) s[m] = x[m];
+    sort_values<P, M>(s);
+    const P a = s[(M - 1) / 2], b = s[M / 2];
+    avg = (M & 1) ? b : a * P(0.5) + b * P(0.5);
+}
+
 template <class Tin, class P, int MAXM, bool EXACT>
 __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restrict__ raw, long long raw_sess_stride,
                                                               int M_rt, int V, int T, int K, int avg_median,
@@ -209,7 +230,6 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
     const int ld = TT + 1;
     const int chunk = TT * K * 3;                     // elements per seed in a full tile
     const int chunk_pad = (chunk * (int)sizeof(Tin) + 15) / 16 * 16;  // bytes, keeps every seed 16-B aligned
-    Tin* stage = reinterpret_cast<Tin*>(smem_raw);
     P* tile = reinterpret_cast<P*>(smem_raw + (size_t)M * chunk_pad);  // [5][K][TT+1]
     const Tin* base = raw + (long long)sess * raw_sess_stride;
     const long long m_stride = (long long)V * T * K * 3;
@@ -218,50 +238,65 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
     constexpr int EPG = 16 / (int)sizeof(Tin);
     const bool vec = ((reinterpret_cast<uintptr_t>(base + off0) & 15) == 0) && ((m_stride * (int)sizeof(Tin)) % 16 == 0);
     const int ngran = vec ? nel / EPG : 0;
-    for (int m = 0; m < M; ++m) {
-        const Tin* src = base + (long long)m * m_stride + off0;
-        unsigned char* dst = smem_raw + (size_t)m * chunk_pad;
-        for (int g = threadIdx.x; g < ngran; g += blockDim.x) ens_cp_async_16(dst + g * 16, src + g * EPG);
-        for (int e = ngran * EPG + threadIdx.x; e < nel; e += blockDim.x)
-            ens_cp_async_small<(int)sizeof(Tin)>(dst + e * sizeof(Tin), src + e);
+    {   // stage the M contiguous seed chunks: coalesced 16-byte cp.async, pointers advanced by constant strides
+        const Tin* src = base + off0;
+        unsigned char* dst = smem_raw;
+        for (int m = 0; m < M; ++m, src += m_stride, dst += chunk_pad) {
+            for (int g = threadIdx.x; g < ngran; g += blockDim.x) ens_cp_async_16(dst + g * 16, src + g * EPG);
+            for (int e = ngran * EPG + threadIdx.x; e < nel; e += blockDim.x)
+                ens_cp_async_small<(int)sizeof(Tin)>(dst + e * sizeof(Tin), src + e);
+        }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
-    // work item = (cell e, coordinate c); neighbouring lanes share a cell
-    const int nitems = nt * K * 2;
-    const int nround = (nitems + blockDim.x - 1) / blockDim.x;
-    for (int rnd = 0; rnd < nround; ++rnd) {
-        const int idx = rnd * blockDim.x + threadIdx.x;
-        const bool valid = idx < nitems;
-        const int e = valid ? idx >> 1 : 0, c = idx & 1;
+    // one thread per cell (frame, keypoint): 3*M shared-memory reads at a constant stride
+    const int ncell = nt * K;
+    for (int e = threadIdx.x; e < ncell; e += blockDim.x) {
         const int tl = (K == 1) ? e : (int)__umulhi((unsigned)e, invK);  // e / K without a divide
         const int k = e - tl * K;
-        P xs[MAXM];
+        P xs[MAXM], ys[MAXM];
         P conf = P(0);
+        bool any_nan = false;
+        const unsigned char* sp = smem_raw + (size_t)e * 3 * sizeof(Tin);
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
             if (m < M) {
-                const Tin* sp = reinterpret_cast<const Tin*>(smem_raw + (size_t)m * chunk_pad) + e * 3;
-                xs[m] = P(sp[c]);                    // cast to the compute precision first (core.py:90-92)
-                if (c == 0) conf += P(sp[2]);        // likelihood sum is NOT NaN-aware (core.py:67-68)
+                const Tin* q = reinterpret_cast<const Tin*>(sp + (size_t)m * chunk_pad);
+                xs[m] = P(q[0]);                     // cast to the compute precision first (core.py:90-92)
+                ys[m] = P(q[1]);
+                conf += P(q[2]);                     // likelihood sum is NOT NaN-aware (core.py:67-68)
+                any_nan = any_nan || isnan(xs[m]) || isnan(ys[m]);
             } else {
                 xs[m] = P(0);
+                ys[m] = P(0);
             }
         }
-        conf = __shfl_sync(0xffffffffu, conf, threadIdx.x & 30);  // even lane of the pair owns the sum
         const P mean_conf = conf / P(M);
-        P avg, var;
-        coord_stats<P, MAXM, EXACT>(xs, M, avg_median != 0, avg, var);
-        if (M == 1) var = P(1) / fmax(mean_conf, P(1e-5));
-        else if (var_mode == 1) var = var / mean_conf;
-        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
-        if (isnan(var)) var = nan_repl; else if (isinf(var)) var = var > 0 ? real_max<P>() : -real_max<P>();
-        if (valid) {
-            tile[(c * K + k) * ld + tl] = avg;
-            tile[((2 + c) * K + k) * ld + tl] = var;
-            if (c == 0) tile[(4 * K + k) * ld + tl] = mean_conf;
+        P ax, vx, ay, vy;
+        if (EXACT && !any_nan) {
+            coord_stats_clean<P, MAXM>(xs, avg_median != 0, ax, vx);
+            coord_stats_clean<P, MAXM>(ys, avg_median != 0, ay, vy);
+        } else {
+            coord_stats<P, MAXM, EXACT>(xs, M, avg_median != 0, ax, vx);
+            coord_stats<P, MAXM, EXACT>(ys, M, avg_median != 0, ay, vy);
         }
+        if (M == 1) {
+            vx = vy = P(1) / fmax(mean_conf, P(1e-5));
+        } else if (var_mode == 1) {
+            vx = vx / mean_conf;
+            vy = vy / mean_conf;
+        }
+        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
+        if (isnan(vx)) vx = nan_repl; else if (isinf(vx)) vx = vx > 0 ? real_max<P>() : -real_max<P>();
+        if (isnan(vy)) vy = nan_repl; else if (isinf(vy)) vy = vy > 0 ? real_max<P>() : -real_max<P>();
+        P* tp = tile + k * ld + tl;
+        const int fs = K * ld;
+        tp[0] = ax;
+        tp[fs] = ay;
+        tp[2 * fs] = vx;
+        tp[3 * fs] = vy;
+        tp[4 * fs] = mean_conf;
     }
     __syncthreads();
     // coalesced plane writes: frame fastest (TT is a power of two: no integer division)
