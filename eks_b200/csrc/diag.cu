@@ -693,6 +693,10 @@ int diag_optimize(int dtype, int B, int T, const void* m0, const void* S0, const
 //   backward: m_s[t] = G_t m_s[t+1] + (1 - G_t a) m_f[t],  P_s[t] = G_t^2 P_s[t+1] + (P_f[t] - G_t^2 S_p)
 //             are affine recurrences with known coefficients -> one scan in reversed thread order.
 // =====================================================================================================
+#ifndef EKS_SMOOTH_MINBLOCKS
+#define EKS_SMOOTH_MINBLOCKS 2
+#endif
+
 template <class P>
 struct DiagSmoothArgs {
     int B, T;
@@ -793,7 +797,7 @@ struct FwdShared {
 };
 
 template <class P>
-__global__ void __launch_bounds__(DIAG_NT, 2) diag_filter_kernel(const __grid_constant__ DiagSmoothArgs<P> a) {
+__global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_filter_kernel(const __grid_constant__ DiagSmoothArgs<P> a) {
     __shared__ FwdShared<P> sh;
     constexpr int L = DiagTraits<P>::L;
     constexpr int TILE = DIAG_NT * L;
@@ -814,12 +818,25 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_filter_kernel(const __grid_co
     }
     const P a2 = av * av, c2 = cc * cc, qc2 = q * c2;
     int buf = 0;
+    // software prefetch: the next tile's observations are requested before the current tile is processed
+    P y_n[L], r_n[L];
+    {
+        const int start0 = threadIdx.x * L;
+        const int nv0 = max(0, min(L, a.T - start0));
+        load_chunk<P, L>(yp + start0, vec, nv0, mean, y_n);
+        load_chunk<P, L>(vp + start0, vec, nv0, P(0), r_n);
+    }
     for (int t0 = 0; t0 < a.T; t0 += TILE, buf ^= 1) {
         const int start = t0 + threadIdx.x * L;
         const int nvalid = max(0, min(L, a.T - start));
         P y[L], r[L], Pf[L];
-        load_chunk<P, L>(yp + start, vec, nvalid, mean, y);
-        load_chunk<P, L>(vp + start, vec, nvalid, P(0), r);
+#pragma unroll
+        for (int i = 0; i < L; ++i) { y[i] = y_n[i]; r[i] = r_n[i]; }
+        if (t0 + TILE < a.T) {
+            const int nvn = max(0, min(L, a.T - (start + TILE)));
+            load_chunk<P, L>(yp + start + TILE, vec, nvn, mean, y_n);
+            load_chunk<P, L>(vp + start + TILE, vec, nvn, P(0), r_n);
+        }
 #pragma unroll
         for (int i = 0; i < L; ++i) {
             if (i >= nvalid) r[i] = P(1);
@@ -906,7 +923,7 @@ struct BwdShared {
 };
 
 template <class P>
-__global__ void __launch_bounds__(DIAG_NT, 2) diag_rts_kernel(const __grid_constant__ DiagSmoothArgs<P> a) {
+__global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_rts_kernel(const __grid_constant__ DiagSmoothArgs<P> a) {
     __shared__ BwdShared<P> sh;
     constexpr int L = DiagTraits<P>::L;
     constexpr int TILE = DIAG_NT * L;
@@ -925,13 +942,25 @@ __global__ void __launch_bounds__(DIAG_NT, 2) diag_rts_kernel(const __grid_const
     const P a2 = av * av, c2 = cc * cc;
     const int ntiles = (a.T + TILE - 1) / TILE;
     int buf = 0;
+    // software prefetch of the next (earlier) tile's filtered moments
+    P mf_n[L], Pf_n[L];
+    {
+        const int start0 = (ntiles - 1) * TILE + (DIAG_NT - 1 - threadIdx.x) * L;
+        const int nv0 = max(0, min(L, a.T - start0));
+        load_chunk<P, L>(mfp + start0, vec, nv0, P(0), mf_n);
+        load_chunk<P, L>(Pfp + start0, vec, nv0, P(0), Pf_n);
+    }
     for (int tile = ntiles - 1; tile >= 0; --tile, buf ^= 1) {
         // thread index increases BACKWARD in time so that an ordinary inclusive scan runs in reverse time
         const int start = tile * TILE + (DIAG_NT - 1 - threadIdx.x) * L;
         const int nvalid = max(0, min(L, a.T - start));
         P mf[L], Pf[L], G[L];
-        load_chunk<P, L>(mfp + start, vec, nvalid, P(0), mf);
-        load_chunk<P, L>(Pfp + start, vec, nvalid, P(0), Pf);
+#pragma unroll
+        for (int i = 0; i < L; ++i) { mf[i] = mf_n[i]; Pf[i] = Pf_n[i]; }
+        if (tile > 0) {
+            load_chunk<P, L>(mfp + start - TILE, vec, L, P(0), mf_n);   // earlier tiles are always full
+            load_chunk<P, L>(Pfp + start - TILE, vec, L, P(0), Pf_n);
+        }
         // ---- phase 1: compose the chunk's affine maps, last frame first
         P Ag = P(1), bm = P(0), bP = P(0);
 #pragma unroll
