@@ -61,7 +61,7 @@ _OPTIONAL_SIGS = {
     'eks_diag_smooth_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'eks_diag_smooth': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,
-                                c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
 }
 
 

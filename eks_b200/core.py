@@ -215,8 +215,18 @@ def run_kalman_smoother(
 
     t0 = time.perf_counter()
     s_dev = torch.as_tensor(s_finals, device=dev).to(dtype)
-    ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev)
-    ms_np, Vs_np = ms.cpu().numpy(), Vs.cpu().numpy()
+    if structure == ops.STRUCT_DIAG:
+        # decoupled model: time-parallel filter + RTS kernels, latent moments as planes [K][4][T]
+        lat = torch.empty((K, 4, T), dtype=dtype, device=dev)
+        ops.diag_smooth(model, yv, vv, T, s_dev, None, lat, 4 * T, [0, T, 2 * T, 3 * T], latent_out=True)
+        lat_np = lat.cpu().numpy()
+        ms_np = np.ascontiguousarray(np.transpose(lat_np[:, 0:2, :], (0, 2, 1)))
+        Vs_np = np.zeros((K, T, 2, 2), dtype=lat_np.dtype)
+        Vs_np[:, :, 0, 0] = lat_np[:, 2, :]
+        Vs_np[:, :, 1, 1] = lat_np[:, 3, :]
+    else:
+        ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev)
+        ms_np, Vs_np = ms.cpu().numpy(), Vs.cpu().numpy()
     logger.debug(f'[profile]   final smoother pass ({K} keypoints): {time.perf_counter() - t0:.3f}s')
     return s_finals, ms_np, Vs_np
 

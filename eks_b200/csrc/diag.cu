@@ -595,17 +595,27 @@ __global__ void diag_seq_block_kernel(int n_blocks, const int* __restrict__ bloc
 
 static int diag_nseg(int dtype, int n, int B) {
     // Work unit = one warp's run of warp-tiles (32 lanes x L frames); a CTA holds 8 runs.  Each run pays a
-    // warm-up of >= 1 warp-tile, so runs should be >= ~24 warp-tiles long (<= 4% overhead), while the grid
-    // should hold a few waves of CTAs (148 SMs x 3 CTAs).
+    // warm-up of ~1 warp-tile, and the grid (nseg x 2B CTAs) is executed in waves of (SMs x 3) resident CTAs.
+    // Pick the segment count that maximises  wave efficiency x useful fraction of a run.
+    static int slots = 0;
+    if (slots == 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = sms * EKS_OPT_MINBLOCKS;
+    }
     const int L = OPT_CHUNK_BYTES / (dtype == EKS_F32 ? 4 : 8);
     const int nwt = (n + 32 * L - 1) / (32 * L);
-    int nseg = nwt / (DIAG_NW * 24);
-    const int want = (900 + 2 * B - 1) / (2 * B);          // ~2 waves of CTAs for small batches
-    const int cap = nwt / (DIAG_NW * 2) > 0 ? nwt / (DIAG_NW * 2) : 1;
-    if (nseg < want) nseg = want < cap ? want : cap;
-    if (nseg < 1) nseg = 1;
-    if (nseg > 16) nseg = 16;
-    return nseg;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int nseg = 1; nseg <= 16; ++nseg) {
+        const int run = (nwt + nseg * DIAG_NW - 1) / (nseg * DIAG_NW);  // warp-tiles per run
+        if (run < 1 || (nseg > 1 && run < 2)) break;
+        const double waves = (double)nseg * 2.0 * B / slots;
+        const double wave_eff = waves / ceil(waves);
+        const double eff = wave_eff * run / (run + 1.0);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = nseg; }
+    }
+    return best;
 }
 
 size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
@@ -694,7 +704,9 @@ int diag_optimize(int dtype, int B, int T, const void* m0, const void* S0, const
 //             are affine recurrences with known coefficients -> one scan in reversed thread order.
 // =====================================================================================================
 #ifndef EKS_SMOOTH_MINBLOCKS
-#define EKS_SMOOTH_MINBLOCKS 2
+// 3 CTAs per SM (<= 85 registers): 148 x 3 = 444 resident CTAs, so that the 2 x (sessions x keypoints)
+// persistent CTAs of a typical batch fit in ONE wave (a second, nearly empty wave would double the time)
+#define EKS_SMOOTH_MINBLOCKS 3
 #endif
 
 template <class P>
@@ -709,6 +721,7 @@ struct DiagSmoothArgs {
     P* out;
     long long out_seq_stride;
     long long out_off[4];  // x plane ch0, ch1 ; posterior-variance plane ch0, ch1
+    int latent_out;        // 1: write the latent smoothed moments (m_s, P_s) instead of C m + mean, C V C^T
 };
 
 template <class P> __device__ inline P pow2_scale(P sum);
@@ -818,25 +831,12 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_filter_ker
     }
     const P a2 = av * av, c2 = cc * cc, qc2 = q * c2;
     int buf = 0;
-    // software prefetch: the next tile's observations are requested before the current tile is processed
-    P y_n[L], r_n[L];
-    {
-        const int start0 = threadIdx.x * L;
-        const int nv0 = max(0, min(L, a.T - start0));
-        load_chunk<P, L>(yp + start0, vec, nv0, mean, y_n);
-        load_chunk<P, L>(vp + start0, vec, nv0, P(0), r_n);
-    }
     for (int t0 = 0; t0 < a.T; t0 += TILE, buf ^= 1) {
         const int start = t0 + threadIdx.x * L;
         const int nvalid = max(0, min(L, a.T - start));
         P y[L], r[L], Pf[L];
-#pragma unroll
-        for (int i = 0; i < L; ++i) { y[i] = y_n[i]; r[i] = r_n[i]; }
-        if (t0 + TILE < a.T) {
-            const int nvn = max(0, min(L, a.T - (start + TILE)));
-            load_chunk<P, L>(yp + start + TILE, vec, nvn, mean, y_n);
-            load_chunk<P, L>(vp + start + TILE, vec, nvn, P(0), r_n);
-        }
+        load_chunk<P, L>(yp + start, vec, nvalid, mean, y);
+        load_chunk<P, L>(vp + start, vec, nvalid, P(0), r);
 #pragma unroll
         for (int i = 0; i < L; ++i) {
             if (i >= nvalid) r[i] = P(1);
@@ -942,25 +942,13 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_rts_kernel
     const P a2 = av * av, c2 = cc * cc;
     const int ntiles = (a.T + TILE - 1) / TILE;
     int buf = 0;
-    // software prefetch of the next (earlier) tile's filtered moments
-    P mf_n[L], Pf_n[L];
-    {
-        const int start0 = (ntiles - 1) * TILE + (DIAG_NT - 1 - threadIdx.x) * L;
-        const int nv0 = max(0, min(L, a.T - start0));
-        load_chunk<P, L>(mfp + start0, vec, nv0, P(0), mf_n);
-        load_chunk<P, L>(Pfp + start0, vec, nv0, P(0), Pf_n);
-    }
     for (int tile = ntiles - 1; tile >= 0; --tile, buf ^= 1) {
         // thread index increases BACKWARD in time so that an ordinary inclusive scan runs in reverse time
         const int start = tile * TILE + (DIAG_NT - 1 - threadIdx.x) * L;
         const int nvalid = max(0, min(L, a.T - start));
         P mf[L], Pf[L], G[L];
-#pragma unroll
-        for (int i = 0; i < L; ++i) { mf[i] = mf_n[i]; Pf[i] = Pf_n[i]; }
-        if (tile > 0) {
-            load_chunk<P, L>(mfp + start - TILE, vec, L, P(0), mf_n);   // earlier tiles are always full
-            load_chunk<P, L>(Pfp + start - TILE, vec, L, P(0), Pf_n);
-        }
+        load_chunk<P, L>(mfp + start, vec, nvalid, P(0), mf);
+        load_chunk<P, L>(Pfp + start, vec, nvalid, P(0), Pf);
         // ---- phase 1: compose the chunk's affine maps, last frame first
         P Ag = P(1), bm = P(0), bP = P(0);
 #pragma unroll
@@ -1016,8 +1004,8 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_rts_kernel
             const P g = G[i];
             ms = fma(g, ms, mf[i]);
             Ps = fma(g * g, Ps, Pf[i]);
-            mf[i] = fma(cc, ms, mean);  // x = C m + mean   (singlecam_smoother.py:190-197)
-            Pf[i] = c2 * Ps;            // diag(C V C^T)    (singlecam_smoother.py:191, 210-211)
+            mf[i] = a.latent_out ? ms : fma(cc, ms, mean);  // x = C m + mean   (singlecam_smoother.py:190-197)
+            Pf[i] = a.latent_out ? Ps : c2 * Ps;            // diag(C V C^T)    (singlecam_smoother.py:191, 210-211)
         }
         store_chunk<P, L>(xo + start, vec, nvalid, mf);
         store_chunk<P, L>(vo + start, vec, nvalid, Pf);
@@ -1032,7 +1020,7 @@ template <class P>
 static int diag_smooth_launch(int B, int T, const void* m0, const void* S0, const void* A, const void* Q,
                               const void* C, const PlaneView& y, const PlaneView& var, const void* ymean,
                               const void* s, void* out, long long out_seq_stride, const long long* out_off,
-                              void* workspace, cudaStream_t st) {
+                              int latent_out, void* workspace, cudaStream_t st) {
     DiagSmoothArgs<P> a;
     a.B = B; a.T = T;
     a.m0 = (const P*)m0; a.S0 = (const P*)S0; a.A = (const P*)A; a.Q = (const P*)Q; a.C = (const P*)C;
@@ -1042,6 +1030,7 @@ static int diag_smooth_launch(int B, int T, const void* m0, const void* S0, cons
     a.Pf = a.mf + (size_t)B * 2 * T;
     a.out = (P*)out; a.out_seq_stride = out_seq_stride;
     for (int i = 0; i < 4; ++i) a.out_off[i] = out_off[i];
+    a.latent_out = latent_out;
     diag_filter_kernel<P><<<B * 2, DIAG_NT, 0, st>>>(a);
     int rc = check_launch("diag_filter_kernel");
     if (rc) return rc;
@@ -1059,7 +1048,8 @@ extern "C" int eks_diag_smooth(int dtype, int B, int T, const void* m0, const vo
                                const void* C, const void* y_base, long long y_seq_stride, const long long* y_off,
                                const void* ymean, const void* var_base, long long var_seq_stride,
                                const long long* var_off, const void* s, void* out, long long out_seq_stride,
-                               const long long* out_off, void* workspace, size_t workspace_bytes, void* stream) {
+                               const long long* out_off, int latent_out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
     EKS_REQUIRE(m0 && S0 && A && Q && C && y_base && y_off && var_base && var_off && s && out && out_off,
                 "diag_smooth: null pointer");
     EKS_REQUIRE(B >= 1 && T >= 1, "diag_smooth: bad dims");
@@ -1072,7 +1062,7 @@ extern "C" int eks_diag_smooth(int dtype, int B, int T, const void* m0, const vo
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == EKS_F32)
         return diag_smooth_launch<float>(B, T, m0, S0, A, Q, C, y, var, ymean, s, out, out_seq_stride, out_off,
-                                         workspace, st);
+                                         latent_out, workspace, st);
     return diag_smooth_launch<double>(B, T, m0, S0, A, Q, C, y, var, ymean, s, out, out_seq_stride, out_off,
-                                      workspace, st);
+                                      latent_out, workspace, st);
 }

@@ -122,13 +122,15 @@ int eks_filter_smooth(int dtype, int B, int D, int O, int T, const void* m0, con
 /* Decoupled (single-camera) final pass: EKS_STRUCT_DIAG form of eks_filter_smooth fused with the
  * reprojection epilogue of eks/singlecam_smoother.py:189-217 (x = C m + mean, posterior variance =
  * diag(C V C^T)).  Time-parallel (Moebius / affine block scans).  Writes, per sequence b, the planes
- * out[b*out_seq_stride + out_off[j] + t], j = 0..3: smoothed x, smoothed y, posterior var x, posterior var y. */
+ * out[b*out_seq_stride + out_off[j] + t], j = 0..3: smoothed x, smoothed y, posterior var x, posterior var y.
+ * latent_out = 1 writes the latent smoothed means / variances themselves (the ms, diag Vs of eks_filter_smooth). */
 size_t eks_diag_smooth_workspace_bytes(int dtype, int B, int T);
 int eks_diag_smooth(int dtype, int B, int T, const void* m0, const void* S0, const void* A, const void* Q,
                     const void* C, const void* y_base, long long y_seq_stride, const long long* y_chan_off_host,
                     const void* ymean, const void* var_base, long long var_seq_stride,
                     const long long* var_chan_off_host, const void* s, void* out, long long out_seq_stride,
-                    const long long* out_off_host, void* workspace, size_t workspace_bytes, void* stream);
+                    const long long* out_off_host, int latent_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Reprojection epilogue for generic models: replaces the loops of eks/multicam_smoother.py:450-511 and
  * project_3d_covariance_to_2d (:914-946).  ms [B][T][D], Vs [B][T][D][D].  For camera c of sequence b writes

@@ -217,3 +217,29 @@ def test_nll_grad_entry_point_matches_oracle():
                                cams=cams)
     np.testing.assert_allclose(nll.cpu().numpy(), n_o, rtol=1e-8)
     np.testing.assert_allclose(dn.cpu().numpy(), g_o, rtol=1e-6)
+
+
+def test_run_kalman_smoother_dropin_matches_oracle():
+    """eks_b200.run_kalman_smoother with the singlecam model (decoupled -> time-parallel kernels) and with a
+    non-diagonal Q (generic kernels) against oracle.run_kalman_smoother on the same arrays."""
+    import eks_b200
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    K, T = 3, 2500
+    lat = np.cumsum(rng.normal(0, 0.3, (K, T, 2)), axis=1)
+    ev = rng.uniform(0.05, 0.6, (T, K, 2))
+    ys = lat + rng.standard_normal((K, T, 2)) * np.sqrt(np.swapaxes(ev, 0, 1))
+    ys -= ys.mean(axis=1, keepdims=True)
+    eye = np.tile(np.eye(2), (K, 1, 1))
+    S0s = np.stack([np.diag(ys[k].var(axis=0)) for k in range(K)])
+    eks_b200.set_precision('float64')
+    try:
+        for Qs in (eye, np.tile(np.array([[1.0, 0.3], [0.3, 0.8]]), (K, 1, 1))):
+            s, ms, Vs = eks_b200.run_kalman_smoother(ys, np.zeros((K, 2)), S0s, eye, eye, Qs, ev)
+            s_o, ms_o, Vs_o, info = oracle.run_kalman_smoother(ys, np.zeros((K, 2)), S0s, eye, eye, Qs, ev,
+                                                               dtype=np.float64)
+            np.testing.assert_allclose(s, s_o, rtol=RTOL64)
+            np.testing.assert_allclose(ms, ms_o, rtol=RTOL64, atol=1e-7)
+            np.testing.assert_allclose(Vs, Vs_o, rtol=RTOL64, atol=1e-9)
+    finally:
+        eks_b200.set_precision('float32')
