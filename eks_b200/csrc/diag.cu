@@ -113,6 +113,7 @@ struct DiagOptArgs {
     ChanState<P>* cstate;        // [B][2]
     double* partials;            // [B][2][nseg][2]  (sum e^2, sum e dm) per segment
     int* n_active;
+    int* block_counter;          // [n_blocks] CTAs of the current evaluation that have finished
 };
 
 __device__ inline void cp_async_16(void* smem, const void* gmem, int src_bytes) {
@@ -279,6 +280,8 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     w = fmin(w + 64.0, 2.0e9);
     out.warm = (int)w;
 }
+
+template <class P> __device__ void diag_adam_body(const DiagOptArgs<P>& a, int j, bool first);
 
 // One WARP-tile: 32 lanes x L frames of one channel, y[] = the lane's register-resident chunk (already
 // centred).  Every warp owns a contiguous run of warp-tiles, so the whole evaluation needs no block-wide
@@ -502,22 +505,36 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
     G = warp_sum(G);
     if (lane == 0) { red[warp][0] = E2; red[warp][1] = G; }
     __syncthreads();
+    __shared__ int is_last;
     if (threadIdx.x == 0) {
         double te = 0, tg = 0;
         for (int w = 0; w < DIAG_NW; ++w) { te += red[w][0]; tg += red[w][1]; }
         part[0] = te;
         part[1] = tg;
+        // the CTA that completes its block's evaluation takes the Adam step and prepares the next evaluation
+        // while other blocks are still streaming (no separate launch, no idle gap between evaluations)
+        __threadfence();
+        const int expected = a.nseg * 2 * (a.block_off[blk + 1] - a.block_off[blk]);
+        const int prev = atomicAdd(&a.block_counter[blk], 1);
+        is_last = (prev + 1 == expected);
+        if (is_last) a.block_counter[blk] = 0;
+    }
+    __syncthreads();
+    if (is_last && warp == 0) {
+        __threadfence();
+        diag_adam_body<P>(a, blk, false);
     }
 }
 
-// ---- kernel B: one warp per block.  Consumes the partial sums of the previous evaluation (Adam step,
-// stop rule of eks/core.py:654-681), then prepares the next one (new s; per-channel transient + constants).
+// ---- Adam step for one block, executed by ONE WARP.  Consumes the partial sums of the evaluation that just
+// finished (stop rule of eks/core.py:654-681), then prepares the next one (new s; per-channel transient and
+// steady-state constants).  first = true: initialise instead of consuming.
 template <class P>
-__global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ DiagOptArgs<P> a, int iter) {
-    const int j = blockIdx.x, lane = threadIdx.x;
+__device__ void diag_adam_body(const DiagOptArgs<P>& a, int j, bool first) {
+    const int lane = threadIdx.x & 31;
     BlockState<P>& bs = a.bstate[j];
     const int m_lo = a.block_off[j], m_hi = a.block_off[j + 1];
-    if (iter == 0) {
+    if (first) {
         if (lane == 0) {
             adam_init(bs.adam, a.s_log0[j]);
             bs.done = (a.cap <= 0);
@@ -538,7 +555,8 @@ __global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ D
                     const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
                     const double* part = a.partials + ((long long)b * 2 + c) * a.nseg * 2;
                     double te = 0, tg = 0;
-                    for (int q = 0; q < a.nseg; ++q) { te += part[2 * q]; tg += part[2 * q + 1]; }
+                    // written by other CTAs of this launch: read through L2 (bypass this SM's L1)
+                    for (int q = 0; q < a.nseg; ++q) { te += __ldcg(part + 2 * q); tg += __ldcg(part + 2 * q + 1); }
                     const double nB = (double)(a.n - cs.t_c);
                     const ChanConst<P>& k = cs.k;
                     nll += (double)a.n * HALF_LOG2PI + 0.5 * cs.tsum[0] + 0.5 * cs.tsum[2] + 0.5 * nB * (double)k.logS +
@@ -584,6 +602,12 @@ __global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ D
     }
 }
 
+// ---- kernel B: initialisation (one warp per block): Adam state + the first transient
+template <class P>
+__global__ void __launch_bounds__(32) diag_adam_kernel(const __grid_constant__ DiagOptArgs<P> a) {
+    diag_adam_body<P>(a, blockIdx.x, true);
+}
+
 // sequence -> block index table + active-block counter
 __global__ void diag_seq_block_kernel(int n_blocks, const int* __restrict__ block_off, const int* __restrict__ members,
                                       int* __restrict__ seq_block, int* __restrict__ n_active) {
@@ -627,6 +651,7 @@ size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     bytes += (size_t)B * 2 * 1024;                     // ChanState (generous bound)
     bytes += (size_t)B * 2 * nseg * 2 * sizeof(double);
     bytes += (size_t)B * sizeof(int) + 256;
+    bytes += (size_t)n_blocks * sizeof(int) + 256;
     return bytes;
 }
 
@@ -642,8 +667,10 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     a.bstate = (BlockState<P>*)w; w += (size_t)a.n_blocks * 128;
     a.cstate = (ChanState<P>*)w; w += (size_t)a.B * 2 * 1024;
     a.partials = (double*)w; w += (size_t)a.B * 2 * a.nseg * 2 * sizeof(double);
-    int* seq_block = (int*)w;
+    int* seq_block = (int*)w; w += ((size_t)a.B * sizeof(int) + 255) / 256 * 256;
     a.seq_block = seq_block;
+    a.block_counter = (int*)w;
+    cudaMemsetAsync(a.block_counter, 0, (size_t)a.n_blocks * sizeof(int), st);
     const int smem = DIAG_NW * OPT_STAGES * WRP_STAGE_BYTES;
     cudaError_t e = cudaFuncSetAttribute(diag_nll_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -653,13 +680,12 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);  // -1: sequence belongs to no block
     diag_seq_block_kernel<<<(a.n_blocks + 127) / 128, 128, 0, st>>>(a.n_blocks, a.block_off, a.members, seq_block,
                                                                     a.n_active);
-    // Every evaluation is one (tiny) Adam/transient launch + one streaming launch.  The loop is unrolled
-    // on the stream without host synchronisation: finished blocks make their CTAs exit immediately.
+    // One initialisation launch, then ONE streaming launch per evaluation; the Adam step between evaluations
+    // runs inside the streaming kernel (last CTA of each block).  The loop is unrolled on the stream without
+    // host synchronisation: finished blocks make their CTAs exit immediately.
     const dim3 grid(a.nseg, 2 * a.B);
-    for (int it = 0; it <= a.cap; ++it) {
-        diag_adam_kernel<P><<<a.n_blocks, 32, 0, st>>>(a, it);
-        if (it < a.cap) diag_nll_kernel<P><<<grid, DIAG_NT, smem, st>>>(a);
-    }
+    diag_adam_kernel<P><<<a.n_blocks, 32, 0, st>>>(a);
+    for (int it = 0; it < a.cap; ++it) diag_nll_kernel<P><<<grid, DIAG_NT, smem, st>>>(a);
     return check_launch("diag optimise kernels");
 }
 

@@ -182,7 +182,10 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                ptr(s_log0), float(lr), float(s_bounds_log[0]), float(s_bounds_log[1]), float(tol),
                                int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
                                int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
-    _count(1)
+    # decoupled path: block-table + Adam-init kernels, then one NLL launch per allowed evaluation (launches of
+    # already converged blocks exit immediately); generic path: one persistent kernel
+    diag = structure == STRUCT_DIAG and D == 2 and O == 2 and model.ncam == 0 and n <= 1
+    _count(2 + int(safety_cap) if diag else 1)
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
 
