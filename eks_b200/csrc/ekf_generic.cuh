@@ -355,37 +355,14 @@ EKS_HD void chol_solve_vec(const P* L, int D, const P* b, P* x) {
     }
 }
 
-// EKF filter + RTS smoother for one sequence; mf/Pf are scratch of size T*D, T*D*D (row-major per
-// frame); ms/Vs are the outputs in the reference layout (T,D), (T,D,D).
-template <class P, int DC, int OC, bool FIXED, bool NL>
-EKS_HD void seq_smooth(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const SeqObs<P>& ob, int T, P s,
-                       P* mf, P* Pf, P* ms, P* Vs) {
-    const int D = dm.D(), O = dm.O();
-    P m[DC], Pm[DC * DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) if (i < D) m[i] = mdl.m0[i];
-#pragma unroll
-    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = mdl.S0[i];
-    P nll = P(0);
-    for (int t = 0; t < T; ++t) {
-        P yv[OC], rv[OC];
-        load_obs<P, OC>(ob, O, t, yv, rv);
-        ekf_step<P, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, s, m, Pm, nll, mf + (long long)t * D,
-                                          Pf + (long long)t * D * D);
-    }
-    // backward pass (SURVEY 7.4): G = psd_solve(A P_f A^T + sQ, A P_f)^T, boost 1e-9
-    P msn[DC], Vsn[DC * DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) if (i < D) { msn[i] = mf[(long long)(T - 1) * D + i]; ms[(long long)(T - 1) * D + i] = msn[i]; }
-#pragma unroll
-    for (int i = 0; i < DC * DC; ++i)
-        if (i < D * D) { Vsn[i] = Pf[(long long)(T - 1) * D * D + i]; Vs[(long long)(T - 1) * D * D + i] = Vsn[i]; }
-    for (int t = T - 2; t >= 0; --t) {
-        P mft[DC], Pft[DC * DC], mp[DC], AP[DC * DC], Sp[DC * DC], L[DC * DC], G[DC * DC];
-#pragma unroll
-        for (int i = 0; i < DC; ++i) if (i < D) mft[i] = mf[(long long)t * D + i];
-#pragma unroll
-        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pft[i] = Pf[(long long)t * D * D + i];
+// One RTS step: given the filtered moments (mft, Pft) of frame t and the smoothed moments
+// (msn, Vsn) of frame t+1, overwrite (msn, Vsn) with the smoothed moments of frame t.
+// G = psd_solve(A P_f A^T + sQ, A P_f)^T with the 1e-9 boost.
+template <class P, int DC, int OC, bool FIXED>
+EKS_HD void rts_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, P s, const P* mft, const P* Pft, P* msn,
+                     P* Vsn) {
+    const int D = dm.D();
+        P mp[DC], AP[DC * DC], Sp[DC * DC], L[DC * DC], G[DC * DC];
 #pragma unroll
         for (int i = 0; i < DC; ++i) {
             if (i < D) {
@@ -472,9 +449,47 @@ EKS_HD void seq_smooth(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, co
                     }
             }
 #pragma unroll
-        for (int i = 0; i < DC; ++i) if (i < D) { ms[(long long)t * D + i] = mst[i]; msn[i] = mst[i]; }
+        for (int i = 0; i < DC; ++i) if (i < D) msn[i] = mst[i];
 #pragma unroll
-        for (int i = 0; i < DC * DC; ++i) if (i < D * D) { Vs[(long long)t * D * D + i] = Vst[i]; Vsn[i] = Vst[i]; }
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Vsn[i] = Vst[i];
+}
+
+// EKF filter + RTS smoother for one sequence; mf/Pf are scratch of size T*D, T*D*D (row-major per
+// frame); ms/Vs are the outputs in the reference layout (T,D), (T,D,D).
+template <class P, int DC, int OC, bool FIXED, bool NL>
+EKS_HD void seq_smooth(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const SeqObs<P>& ob, int T, P s,
+                       P* mf, P* Pf, P* ms, P* Vs) {
+    const int D = dm.D(), O = dm.O();
+    P m[DC], Pm[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) if (i < D) m[i] = mdl.m0[i];
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = mdl.S0[i];
+    P nll = P(0);
+    for (int t = 0; t < T; ++t) {
+        P yv[OC], rv[OC];
+        load_obs<P, OC>(ob, O, t, yv, rv);
+        ekf_step<P, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, s, m, Pm, nll, mf + (long long)t * D,
+                                          Pf + (long long)t * D * D);
+    }
+    // backward pass (SURVEY 7.4): G = psd_solve(A P_f A^T + sQ, A P_f)^T, boost 1e-9
+    P msn[DC], Vsn[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) if (i < D) { msn[i] = mf[(long long)(T - 1) * D + i]; ms[(long long)(T - 1) * D + i] = msn[i]; }
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i)
+        if (i < D * D) { Vsn[i] = Pf[(long long)(T - 1) * D * D + i]; Vs[(long long)(T - 1) * D * D + i] = Vsn[i]; }
+    for (int t = T - 2; t >= 0; --t) {
+        P mft[DC], Pft[DC * DC];
+#pragma unroll
+        for (int i = 0; i < DC; ++i) if (i < D) mft[i] = mf[(long long)t * D + i];
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pft[i] = Pf[(long long)t * D * D + i];
+        rts_step<P, DC, OC, FIXED>(dm, mdl, s, mft, Pft, msn, Vsn);
+#pragma unroll
+        for (int i = 0; i < DC; ++i) if (i < D) ms[(long long)t * D + i] = msn[i];
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Vs[(long long)t * D * D + i] = Vsn[i];
     }
 }
 

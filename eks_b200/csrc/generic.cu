@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include "common.cuh"
 #include "ekf_generic.cuh"
+#include "generic.cuh"
 #include "diag.cuh"
 #include "../../include/eks_b200.h"
 
@@ -23,70 +24,6 @@ int check_launch(const char* what) {
         return (int)e;
     }
     return 0;
-}
-
-constexpr int G_MAX_SPANS = 16;
-struct GSpans {
-    int n, total;
-    int start[G_MAX_SPANS];
-    int cum[G_MAX_SPANS + 1];
-};
-struct FrameMap {
-    GSpans sp;
-    __device__ long long operator()(int i) const {
-        if (sp.n == 1) return sp.start[0] + i;
-        int j = 0;
-        while (j + 1 < sp.n && i >= sp.cum[j + 1]) ++j;
-        return sp.start[j] + (i - sp.cum[j]);
-    }
-};
-
-template <class P>
-struct GArgs {
-    int B, D, O, T, ncam;
-    const P *m0, *S0, *A, *Q, *C, *cams;
-    PlaneView y, var;
-    const P *ymean, *Rconst;
-    GSpans sp;
-    // optimise
-    int n_blocks;
-    const int *block_off, *members;
-    const P* s_log0;
-    P lr, lo, hi, tol;
-    int cap;
-    P *s_log_out, *last_loss_out;
-    int* iters_out;
-    P* trace;
-    int trace_cap;
-    // nll_grad / smooth
-    const P* s;
-    P *nll_out, *dnll_out;
-    P *mf, *Pf, *ms, *Vs;
-};
-
-template <class P>
-__device__ inline void make_seq(const GArgs<P>& a, int b, SeqModel<P>& mdl, SeqObs<P>& ob, bool use_var) {
-    const int D = a.D, O = a.O;
-    mdl.D = D; mdl.O = O; mdl.ncam = a.ncam;
-    mdl.m0 = a.m0 + (long long)b * D;
-    mdl.S0 = a.S0 + (long long)b * D * D;
-    mdl.A = a.A + (long long)b * D * D;
-    mdl.Q = a.Q + (long long)b * D * D;
-    mdl.C = a.C ? a.C + (long long)b * O * D : nullptr;
-    mdl.cams = a.cams;
-    ob.y_base = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride;
-    ob.y_off = a.y.chan_off;
-    ob.ymean = a.ymean ? a.ymean + (long long)b * O : nullptr;
-    if (use_var) {
-        ob.var_base = reinterpret_cast<const P*>(a.var.base) + (long long)b * a.var.seq_stride;
-        ob.var_off = a.var.chan_off;
-        ob.Rconst = nullptr;
-    } else {
-        ob.var_base = nullptr;
-        ob.var_off = nullptr;
-        ob.Rconst = a.Rconst + (long long)b * O;
-    }
-    ob.var_floor = P(1e-12);
 }
 
 template <class P, int DC, int OC, bool FIXED, bool NL>
@@ -238,7 +175,8 @@ int optimize_impl(int B, int D, int O, int T, const void* m0, const void* S0, co
                   const long long* y_off, const void* ymean, const void* Rconst, int n_spans, const int* s0,
                   const int* s1, int n_blocks, const int* block_off, const int* members, const void* s_log0,
                   double lr, double lo, double hi, double tol, int cap, void* s_log_out, void* last_loss_out,
-                  int* iters_out, void* trace, int trace_cap, cudaStream_t st) {
+                  int* iters_out, void* trace, int trace_cap, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
     GArgs<P> a;
     if (common_args<P>(a, B, D, O, T, m0, S0, A, Q, C, ncam, cams)) return -1;
     EKS_REQUIRE(y_base && y_off && Rconst && block_off && members && s_log0 && s_log_out && last_loss_out &&
@@ -251,6 +189,8 @@ int optimize_impl(int B, int D, int O, int T, const void* m0, const void* S0, co
     a.lr = (P)lr; a.lo = (P)lo; a.hi = (P)hi; a.tol = (P)tol; a.cap = cap;
     a.s_log_out = (P*)s_log_out; a.last_loss_out = (P*)last_loss_out; a.iters_out = iters_out;
     a.trace = (P*)trace; a.trace_cap = trace_cap;
+    // long sequences: verified run-parallel execution (generic_runs.cu); short ones: one thread per block
+    if (a.sp.total >= GEN_RUNS_MIN_FRAMES) return generic_runs_optimize<P>(a, workspace, workspace_bytes, st);
     return dispatch<P>(OP_OPT, a, st);
 }
 
@@ -263,7 +203,8 @@ int smooth_impl(int B, int D, int O, int T, const void* m0, const void* S0, cons
     GArgs<P> a;
     if (common_args<P>(a, B, D, O, T, m0, S0, A, Q, C, ncam, cams)) return -1;
     EKS_REQUIRE(y_base && y_off && var_base && var_off && s && ms_out && Vs_out, "filter_smooth: null pointer");
-    const size_t need = (size_t)B * T * (D + D * D) * sizeof(P);
+    const size_t need = (size_t)B * T * (D + D * D) * sizeof(P) +
+                        (T >= GEN_RUNS_MIN_FRAMES ? generic_runs_smooth_extra_bytes(sizeof(P) == 4 ? EKS_F32 : EKS_F64, B, D, T) : 0);
     EKS_REQUIRE(workspace && workspace_bytes >= need, "filter_smooth: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
     a.y = view_of(y_base, y_seq_stride, y_off, O);
@@ -274,6 +215,7 @@ int smooth_impl(int B, int D, int O, int T, const void* m0, const void* S0, cons
     a.mf = (P*)workspace;
     a.Pf = a.mf + (size_t)B * T * D;
     a.ms = (P*)ms_out; a.Vs = (P*)Vs_out;
+    if (T >= GEN_RUNS_MIN_FRAMES) return generic_runs_smooth<P>(a, st);
     return dispatch<P>(OP_SMOOTH, a, st);
 }
 
@@ -298,8 +240,10 @@ extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m
 }
 
 extern "C" size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T) {
-    (void)D; (void)O;
-    return diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
+    (void)O;
+    const size_t a1 = diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
+    const size_t a2 = T >= GEN_RUNS_MIN_FRAMES ? generic_runs_optimize_workspace_bytes(dtype, n_blocks, B, D, T) : 0;
+    return a1 > a2 ? a1 : a2;
 }
 
 extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
@@ -328,14 +272,16 @@ extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void*
     if (dtype == EKS_F32)
         return optimize_impl<float>(B, D, O, T, m0, S0, A, Q, C, ncam, cams, y_base, y_seq_stride, y_off, ymean,
                                     Rconst, n_spans, s0, s1, n_blocks, block_off, members, s_log0, lr, lo, hi, tol,
-                                    cap, s_log_out, last_loss_out, iters_out, trace, trace_cap, st);
+                                    cap, s_log_out, last_loss_out, iters_out, trace, trace_cap, workspace,
+                                    workspace_bytes, st);
     return optimize_impl<double>(B, D, O, T, m0, S0, A, Q, C, ncam, cams, y_base, y_seq_stride, y_off, ymean, Rconst,
                                  n_spans, s0, s1, n_blocks, block_off, members, s_log0, lr, lo, hi, tol, cap,
-                                 s_log_out, last_loss_out, iters_out, trace, trace_cap, st);
+                                 s_log_out, last_loss_out, iters_out, trace, trace_cap, workspace, workspace_bytes, st);
 }
 
 extern "C" size_t eks_filter_smooth_workspace_bytes(int dtype, int B, int D, int T) {
-    return (size_t)B * T * (D + D * D) * (dtype == EKS_F32 ? 4 : 8);
+    return (size_t)B * T * (D + D * D) * (dtype == EKS_F32 ? 4 : 8) +
+           (T >= GEN_RUNS_MIN_FRAMES ? generic_runs_smooth_extra_bytes(dtype, B, D, T) : 0);
 }
 
 extern "C" int eks_filter_smooth(int dtype, int B, int D, int O, int T, const void* m0, const void* S0,

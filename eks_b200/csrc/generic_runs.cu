@@ -1,0 +1,482 @@
+// generic_runs.cu -- time-parallel execution of the GENERIC models (any linear model with D <= 6, obs <= 16,
+// and the calibrated pinhole EKF) for long sequences.
+//
+// The sequential kernels of generic.cu give one thread a whole sequence: at 10^6 frames that is ~10^9 dependent
+// cycles per pass.  Here a sequence is cut into runs of `run_len` frames, one thread per (sequence, run).  A run
+// that does not start at frame 0 starts `W` frames early from the sequence's prior (m0, S0): a stable Kalman
+// filter forgets its initial condition geometrically, so after the warm-up its state equals the sequential
+// filter's to rounding.  This is not assumed but VERIFIED: every run records its state at its first frame
+// (after warm-up) and at its end; adjacent records must agree to a tight relative tolerance.  By induction
+// from run 0 (exact start) agreement at every boundary proves the whole trajectory -- NLL, d NLL/ds, filtered
+// and smoothed moments -- equal to the sequential recursion up to that tolerance.  On disagreement the
+// sequence's warm-up length is quadrupled and the evaluation repeated (no Adam step is taken on an
+// unverified loss); with W >= n every run starts at frame 0, i.e. the scheme degrades to the exact one.
+//
+// Replaces the same reference code as generic.cu: eks/core.py:274-295 (final smoother), :403-559, :562-699
+// (s-optimisation) for non-decoupled models.
+#include "common.cuh"
+#include "ekf_generic.cuh"
+#include "generic.cuh"
+#include "../../include/eks_b200.h"
+
+namespace eks {
+
+constexpr int RUNS_W0 = 64;       // initial warm-up length (frames)
+constexpr int RUNS_EXTRA = 12;    // extra evaluation slots for warm-up escalations (64 * 4^10 > 10^7 frames)
+
+template <class P>
+struct RunBlockState {
+    AdamState<P> adam;
+    P s, dsdlog;
+    int done;
+    int redo;   // diagnostic: number of repeated evaluations
+};
+
+template <class P>
+struct RunArgs {
+    int run_len, nruns, ns;   // ns = 2 (D + D^2): values per boundary record (m, P, dm, dP)
+    int final_slot;           // evaluation slot index of this launch (for the forced finish)
+    int total_slots;
+    RunBlockState<P>* bstate; // [n_blocks]
+    int* warm;                // [B] per-sequence warm-up length
+    const int* seq_block;     // [B]
+    double* part;             // [B][nruns][3]: nll, d nll/ds, bad
+    P* bnd_start;             // [B][nruns][ns]
+    P* bnd_end;               // [B][nruns][ns]
+    int* flag;                // smoother: boundary mismatch flag
+};
+
+template <class P> __host__ __device__ inline P runs_tol() { return sizeof(P) == 4 ? P(2e-5) : P(1e-10); }
+// rounding floor: two different computation histories of the same quantity x differ by a few ulp of |x|
+template <class P> __host__ __device__ inline P runs_ulp() { return sizeof(P) == 4 ? P(64 * 1.2e-7) : P(64 * 2.3e-16); }
+
+// ---- one run of the filter NLL with s-sensitivities --------------------------------------------------------
+template <class P, int DC, int OC, bool FIXED, bool NL>
+__global__ void __launch_bounds__(32) gen_nll_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                          const __grid_constant__ RunArgs<P> g) {
+    using S = Dual<P>;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * g.nruns) return;
+    const int b = idx / g.nruns, r = idx - b * g.nruns;
+    const int blk = g.seq_block[b];
+    if (blk < 0 || g.bstate[blk].done) return;
+    const int n = a.sp.total;
+    const int t0 = r * g.run_len, t1 = min(n, t0 + g.run_len);
+    double* part = g.part + ((long long)b * g.nruns + r) * 3;
+    if (t0 >= n) { part[0] = 0; part[1] = 0; part[2] = 0; return; }
+    const int start = max(0, t0 - g.warm[b]);
+    Dims<DC, OC, FIXED> dm{a.D, a.O};
+    const int D = dm.D(), O = dm.O();
+    SeqModel<P> mdl;
+    SeqObs<P> ob;
+    make_seq(a, b, mdl, ob, false);
+    FrameMap fm{a.sp};
+    S m[DC], Pm[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) if (i < D) m[i] = S(mdl.m0[i]);
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = S(mdl.S0[i]);
+    const S sd(g.bstate[blk].s, P(1));
+    S nll = S(P(0));
+    bool ok = true;
+    P* bs = g.bnd_start + ((long long)b * g.nruns + r) * g.ns;
+    P* be = g.bnd_end + ((long long)b * g.nruns + r) * g.ns;
+    for (int i = start; i < t1; ++i) {
+        if (i == t0) {  // state after warm-up = predicted state of the run's first frame
+            for (int q = 0; q < D; ++q) { bs[q] = m[q].v; bs[D + D * D + q] = m[q].d; }
+            for (int q = 0; q < D * D; ++q) { bs[D + q] = Pm[q].v; bs[2 * D + D * D + q] = Pm[q].d; }
+            nll = S(P(0));
+            ok = true;
+        }
+        P yv[OC], rv[OC];
+        load_obs<P, OC>(ob, O, fm(i), yv, rv);
+        ok = ekf_step<S, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, sd, m, Pm, nll, (S*)nullptr, (S*)nullptr) && ok;
+    }
+    for (int q = 0; q < D; ++q) { be[q] = m[q].v; be[D + D * D + q] = m[q].d; }
+    for (int q = 0; q < D * D; ++q) { be[D + q] = Pm[q].v; be[2 * D + D * D + q] = Pm[q].d; }
+    part[0] = (double)nll.v;
+    part[1] = (double)nll.d;
+    part[2] = ok ? 0.0 : 1.0;
+}
+
+// boundary agreement: |a - b| <= tol * scale, scale from the covariance (means), the variances (covariance)
+// and the magnitude of the sensitivities themselves
+template <class P>
+__device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval) {
+    const P tol = runs_tol<P>();
+    bool ok = true;
+    for (int i = 0; i < D; ++i) {
+        const P sd = sqrt_(fabs(e[D + i * D + i]) + P(1e-30));
+        ok = ok && (fabs(e[i] - s[i]) <= tol * sd + runs_ulp<P>() * fabs(e[i]));
+        const P dsc = fabs(e[D + D * D + i]) + sd / sval;
+        ok = ok && (fabs(e[D + D * D + i] - s[D + D * D + i]) <= P(10) * tol * dsc);
+        for (int j = 0; j < D; ++j) {
+            const P pv = sqrt_(fabs(e[D + i * D + i] * e[D + j * D + j]) + P(1e-30));
+            ok = ok && (fabs(e[D + i * D + j] - s[D + i * D + j]) <= tol * pv);
+            const P dpv = fabs(e[2 * D + D * D + i * D + j]) + pv / sval;
+            ok = ok && (fabs(e[2 * D + D * D + i * D + j] - s[2 * D + D * D + i * D + j]) <= P(10) * tol * dpv);
+        }
+    }
+    return ok;
+}
+
+// ---- per block: verify the run boundaries, then Adam step (or escalate the warm-up and repeat) ---------------
+template <class P>
+__global__ void __launch_bounds__(32) gen_adam_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                           const __grid_constant__ RunArgs<P> g, int first) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_blocks) return;
+    RunBlockState<P>& bs = g.bstate[j];
+    const int n = a.sp.total;
+    if (first) {
+        adam_init(bs.adam, a.s_log0[j]);
+        bs.done = (a.cap <= 0);
+        bs.redo = 0;
+    } else {
+        if (bs.done) return;
+        bool verified = true;
+        for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
+            const int b = a.members[mi];
+            bool okb = true;
+            for (int r = 1; r < g.nruns && okb; ++r) {
+                const int t0 = r * g.run_len;
+                if (t0 >= n) break;
+                if (t0 - g.warm[b] <= 0) continue;  // this run started at frame 0: exact
+                okb = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
+                                          g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, bs.s);
+            }
+            if (!okb) {
+                verified = false;
+                g.warm[b] = (g.warm[b] >= n / 4) ? n : g.warm[b] * 4;
+            }
+        }
+        const bool last_slot = (g.final_slot == g.total_slots - 1);
+        if (!verified && !last_slot) {
+            bs.redo += 1;  // same s again with longer warm-ups; no Adam step on an unverified loss
+        } else {
+            P loss = P(0), grad = P(0);
+            for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
+                const int b = a.members[mi];
+                double v = 0, dv = 0, bad = 0;
+                for (int r = 0; r < g.nruns; ++r) {
+                    const double* p = g.part + ((long long)b * g.nruns + r) * 3;
+                    v += p[0]; dv += p[1]; bad += p[2];
+                }
+                P vv = (P)v, gg = (P)dv;
+                if (bad > 0 || !isfinite(v) || !isfinite((double)vv)) { vv = P(1e12); gg = P(0); }  // core.py:650
+                loss += vv;
+                grad += gg * bs.dsdlog;
+            }
+            if (a.trace && bs.adam.iters < a.trace_cap) {
+                P* tr = a.trace + ((long long)j * a.trace_cap + bs.adam.iters) * 3;
+                tr[0] = bs.adam.s_log; tr[1] = loss; tr[2] = grad * a.lr;
+            }
+            adam_step(bs.adam, loss, grad, a.lr, a.tol, a.cap);
+            if (last_slot) bs.adam.done = true;
+            if (bs.adam.done) {
+                bs.done = 1;
+                a.s_log_out[j] = bs.adam.s_log;
+                a.last_loss_out[j] = bs.adam.prev;
+                a.iters_out[j] = bs.adam.iters;
+                return;
+            }
+        }
+    }
+    if (bs.done) {
+        a.s_log_out[j] = bs.adam.s_log; a.last_loss_out[j] = bs.adam.prev; a.iters_out[j] = 0;
+        return;
+    }
+    P dsdlog;
+    bs.s = adam_current_s(bs.adam, a.lo, a.hi, &dsdlog);
+    bs.dsdlog = dsdlog;
+}
+
+__global__ void gen_runs_init_kernel(int B, int n_blocks, const int* __restrict__ block_off,
+                                     const int* __restrict__ members, int* __restrict__ seq_block,
+                                     int* __restrict__ warm, int w0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) warm[i] = w0;
+    if (i < n_blocks)
+        for (int mi = block_off[i]; mi < block_off[i + 1]; ++mi) seq_block[members[mi]] = i;
+}
+
+static int runs_geometry(int n, int B, int& run_len) {
+    // enough runs for ~16k threads, runs of at least 256 frames (warm-up of 64 stays below 25%)
+    int nruns = (16384 + B - 1) / B;
+    run_len = (n + nruns - 1) / nruns;
+    if (run_len < 256) run_len = 256;
+    run_len = (run_len + 31) / 32 * 32;
+    return (n + run_len - 1) / run_len;
+}
+
+size_t generic_runs_optimize_workspace_bytes(int dtype, int n_blocks, int B, int D, int T) {
+    const size_t w = dtype == EKS_F32 ? 4 : 8;
+    int run_len;
+    const int nruns = runs_geometry(T, B, run_len);
+    const size_t ns = 2 * (size_t)(D + D * D);
+    size_t bytes = 1024;
+    bytes += (size_t)n_blocks * 128;
+    bytes += 2 * ((size_t)B * sizeof(int) + 256);
+    bytes += (size_t)B * nruns * 3 * sizeof(double) + 256;
+    bytes += 2 * ((size_t)B * nruns * ns * w + 256);
+    return bytes;
+}
+
+template <class P, int DC, int OC, bool FIXED, bool NL>
+static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st) {
+    const int nthreads = a.B * g.nruns;
+    const int slots = a.cap + RUNS_EXTRA;
+    g.total_slots = slots;
+    g.final_slot = -1;
+    gen_adam_runs_kernel<P><<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a, g, 1);
+    for (int it = 0; it < slots; ++it) {
+        g.final_slot = it;
+        gen_nll_runs_kernel<P, DC, OC, FIXED, NL><<<(nthreads + 31) / 32, 32, 0, st>>>(a, g);
+        gen_adam_runs_kernel<P><<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a, g, 0);
+    }
+    return check_launch("generic run-parallel optimise kernels");
+}
+
+template <class P>
+int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    static_assert(sizeof(RunBlockState<P>) <= 128, "workspace bound");
+    RunArgs<P> g;
+    const int n = a.sp.total;
+    g.nruns = runs_geometry(n, a.B, g.run_len);
+    g.ns = 2 * (a.D + a.D * a.D);
+    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
+    EKS_REQUIRE(workspace && workspace_bytes >= generic_runs_optimize_workspace_bytes(dtype, a.n_blocks, a.B, a.D, a.T),
+                "optimize_s: workspace too small for the run-parallel generic path");
+    unsigned char* w = (unsigned char*)workspace;
+    auto take = [&](size_t bytes) { unsigned char* p = w; w += (bytes + 255) / 256 * 256; return p; };
+    g.bstate = (RunBlockState<P>*)take((size_t)a.n_blocks * 128);
+    g.warm = (int*)take((size_t)a.B * sizeof(int));
+    int* seq_block = (int*)take((size_t)a.B * sizeof(int));
+    g.seq_block = seq_block;
+    g.part = (double*)take((size_t)a.B * g.nruns * 3 * sizeof(double));
+    g.bnd_start = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
+    g.bnd_end = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
+    g.flag = nullptr;
+    cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);
+    const int nmax = a.B > a.n_blocks ? a.B : a.n_blocks;
+    gen_runs_init_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(a.B, a.n_blocks, a.block_off, a.members, seq_block,
+                                                             g.warm, RUNS_W0);
+    const int D = a.D, O = a.O;
+    if (a.ncam > 0) {
+        if (O == 4) return runs_optimize_launch<P, 3, 4, true, true>(a, g, st);
+        if (O == 6) return runs_optimize_launch<P, 3, 6, true, true>(a, g, st);
+        if (O == 8) return runs_optimize_launch<P, 3, 8, true, true>(a, g, st);
+        return runs_optimize_launch<P, 3, EKS_MAX_CHAN, false, true>(a, g, st);
+    }
+    if (D == 2 && O == 2) return runs_optimize_launch<P, 2, 2, true, false>(a, g, st);
+    if (D == 3 && O == 4) return runs_optimize_launch<P, 3, 4, true, false>(a, g, st);
+    if (D == 3 && O == 6) return runs_optimize_launch<P, 3, 6, true, false>(a, g, st);
+    if (D == 3 && O == 8) return runs_optimize_launch<P, 3, 8, true, false>(a, g, st);
+    return runs_optimize_launch<P, EKS_MAX_STATE, EKS_MAX_CHAN, false, false>(a, g, st);
+}
+template int generic_runs_optimize<float>(const GArgs<float>&, void*, size_t, cudaStream_t);
+template int generic_runs_optimize<double>(const GArgs<double>&, void*, size_t, cudaStream_t);
+
+// =====================================================================================================
+// final pass: forward filter runs, then RTS runs (right-to-left, warm-up on the right), both verified
+// =====================================================================================================
+template <class P>
+struct SmoothRunArgs {
+    int run_len, nruns, warm, nm;  // nm = D + D^2 values per boundary record
+    P* bnd_f_start;  // [B][nruns][nm] filter state after warm-up at the run's first frame
+    P* bnd_f_end;    // [B][nruns][nm] filter state after the run's last frame
+    P* bnd_b;        // [B][nruns][nm] this run's estimate of the smoothed moments at frame t1 (next run's first)
+    int* flag;       // [2]: forward / backward mismatch
+};
+
+template <class P, int DC, int OC, bool FIXED, bool NL>
+__global__ void __launch_bounds__(32) gen_filter_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                             const __grid_constant__ SmoothRunArgs<P> g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * g.nruns) return;
+    const int b = idx / g.nruns, r = idx - b * g.nruns;
+    const int T = a.T;
+    const int t0 = r * g.run_len, t1 = min(T, t0 + g.run_len);
+    if (t0 >= T) return;
+    const int start = max(0, t0 - g.warm);
+    Dims<DC, OC, FIXED> dm{a.D, a.O};
+    const int D = dm.D(), O = dm.O();
+    SeqModel<P> mdl;
+    SeqObs<P> ob;
+    make_seq(a, b, mdl, ob, true);
+    P m[DC], Pm[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) if (i < D) m[i] = mdl.m0[i];
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = mdl.S0[i];
+    const P s = a.s[b];
+    P nll = P(0);
+    P* bs = g.bnd_f_start + ((long long)b * g.nruns + r) * g.nm;
+    P* be = g.bnd_f_end + ((long long)b * g.nruns + r) * g.nm;
+    P* mfb = a.mf + (long long)b * T * D;
+    P* Pfb = a.Pf + (long long)b * T * D * D;
+    for (int t = start; t < t1; ++t) {
+        if (t == t0) {
+            for (int q = 0; q < D; ++q) bs[q] = m[q];
+            for (int q = 0; q < D * D; ++q) bs[D + q] = Pm[q];
+        }
+        P yv[OC], rv[OC];
+        load_obs<P, OC>(ob, O, t, yv, rv);
+        P mf[DC], Pf[DC * DC];
+        ekf_step<P, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, s, m, Pm, nll, mf, Pf);
+        if (t >= t0) {
+            for (int q = 0; q < D; ++q) mfb[(long long)t * D + q] = mf[q];
+            for (int q = 0; q < D * D; ++q) Pfb[(long long)t * D * D + q] = Pf[q];
+        }
+    }
+    for (int q = 0; q < D; ++q) be[q] = m[q];
+    for (int q = 0; q < D * D; ++q) be[D + q] = Pm[q];
+}
+
+template <class P, int DC, int OC, bool FIXED>
+__global__ void __launch_bounds__(32) gen_rts_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                          const __grid_constant__ SmoothRunArgs<P> g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * g.nruns) return;
+    const int b = idx / g.nruns, r = idx - b * g.nruns;
+    const int T = a.T;
+    const int t0 = r * g.run_len, t1 = min(T, t0 + g.run_len);
+    if (t0 >= T) return;
+    const int stop = min(T - 1, t1 - 1 + g.warm);  // first frame of the backward recursion (exact if T-1)
+    Dims<DC, OC, FIXED> dm{a.D, a.O};
+    const int D = dm.D();
+    SeqModel<P> mdl;
+    SeqObs<P> ob;
+    make_seq(a, b, mdl, ob, true);
+    const P s = a.s[b];
+    const P* mfb = a.mf + (long long)b * T * D;
+    const P* Pfb = a.Pf + (long long)b * T * D * D;
+    P* msb = a.ms + (long long)b * T * D;
+    P* Vsb = a.Vs + (long long)b * T * D * D;
+    P* bb = g.bnd_b + ((long long)b * g.nruns + r) * g.nm;
+    P msn[DC], Vsn[DC * DC];
+    for (int q = 0; q < D; ++q) msn[q] = mfb[(long long)stop * D + q];
+    for (int q = 0; q < D * D; ++q) Vsn[q] = Pfb[(long long)stop * D * D + q];
+    for (int t = stop; t >= t0; --t) {
+        if (t < stop) {
+            P mft[DC], Pft[DC * DC];
+            for (int q = 0; q < D; ++q) mft[q] = mfb[(long long)t * D + q];
+            for (int q = 0; q < D * D; ++q) Pft[q] = Pfb[(long long)t * D * D + q];
+            rts_step<P, DC, OC, FIXED>(dm, mdl, s, mft, Pft, msn, Vsn);
+        }
+        if (t == t1) {  // own estimate of the next run's first frame
+            for (int q = 0; q < D; ++q) bb[q] = msn[q];
+            for (int q = 0; q < D * D; ++q) bb[D + q] = Vsn[q];
+        }
+        if (t < t1) {
+            for (int q = 0; q < D; ++q) msb[(long long)t * D + q] = msn[q];
+            for (int q = 0; q < D * D; ++q) Vsb[(long long)t * D * D + q] = Vsn[q];
+        }
+    }
+}
+
+template <class P>
+__device__ inline bool moments_agree(const P* x, const P* y, int D) {
+    const P tol = runs_tol<P>();
+    bool ok = true;
+    for (int i = 0; i < D; ++i) {
+        const P sd = sqrt_(fabs(x[D + i * D + i]) + P(1e-30));
+        ok = ok && (fabs(x[i] - y[i]) <= tol * sd + runs_ulp<P>() * fabs(x[i]));
+        for (int j = 0; j < D; ++j) {
+            const P pv = sqrt_(fabs(x[D + i * D + i] * x[D + j * D + j]) + P(1e-30));
+            ok = ok && (fabs(x[D + i * D + j] - y[D + i * D + j]) <= tol * pv);
+        }
+    }
+    return ok;
+}
+
+// which = 0: filter boundaries (bnd_f_end[r-1] vs bnd_f_start[r]); which = 1: smoother boundaries
+// (bnd_b[r] vs the smoothed moments written by run r+1 at its first frame)
+template <class P>
+__global__ void gen_smooth_check_kernel(const __grid_constant__ GArgs<P> a, const __grid_constant__ SmoothRunArgs<P> g,
+                                        int which) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * g.nruns) return;
+    const int b = idx / g.nruns, r = idx - b * g.nruns;
+    const int T = a.T, D = a.D;
+    const int t0 = r * g.run_len, t1 = min(T, t0 + g.run_len);
+    if (t0 >= T) return;
+    bool ok = true;
+    if (which == 0) {
+        if (r > 0 && t0 - g.warm > 0)
+            ok = moments_agree<P>(g.bnd_f_end + ((long long)b * g.nruns + r - 1) * g.nm,
+                                  g.bnd_f_start + ((long long)b * g.nruns + r) * g.nm, D);
+    } else {
+        if (t1 < T && t1 - 1 + g.warm < T - 1) {
+            P y[EKS_MAX_STATE + EKS_MAX_STATE * EKS_MAX_STATE];
+            for (int q = 0; q < D; ++q) y[q] = a.ms[((long long)b * T + t1) * D + q];
+            for (int q = 0; q < D * D; ++q) y[D + q] = a.Vs[((long long)b * T + t1) * D * D + q];
+            ok = moments_agree<P>(y, g.bnd_b + ((long long)b * g.nruns + r) * g.nm, D);
+        }
+    }
+    if (!ok) atomicExch(g.flag + which, 1);
+}
+
+template <class P, int DC, int OC, bool FIXED, bool NL>
+static int runs_smooth_launch(const GArgs<P>& a, SmoothRunArgs<P> g, cudaStream_t st) {
+    const int nthreads = a.B * g.nruns;
+    const int blocks = (nthreads + 31) / 32;
+    int h_flag[2];
+    // NOTE: unlike the other entry points this driver synchronises the stream: the boundary verification
+    // decides on the host whether the pass has to be repeated with a longer warm-up.
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        cudaMemsetAsync(g.flag, 0, 2 * sizeof(int), st);
+        gen_filter_runs_kernel<P, DC, OC, FIXED, NL><<<blocks, 32, 0, st>>>(a, g);
+        gen_smooth_check_kernel<P><<<(nthreads + 127) / 128, 128, 0, st>>>(a, g, 0);
+        gen_rts_runs_kernel<P, DC, OC, FIXED><<<blocks, 32, 0, st>>>(a, g);
+        gen_smooth_check_kernel<P><<<(nthreads + 127) / 128, 128, 0, st>>>(a, g, 1);
+        cudaError_t e = cudaMemcpyAsync(h_flag, g.flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("generic run-parallel smoother: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        if (!h_flag[0] && !h_flag[1]) return 0;
+        if (g.warm >= a.T) break;  // already exact: nothing more to escalate
+        g.warm = (g.warm >= a.T / 4) ? a.T : g.warm * 4;
+    }
+    return check_launch("generic run-parallel smoother kernels");
+}
+
+template <class P>
+int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st) {
+    SmoothRunArgs<P> g;
+    g.nruns = runs_geometry(a.T, a.B, g.run_len);
+    g.warm = RUNS_W0;
+    g.nm = a.D + a.D * a.D;
+    // boundary records live behind the filtered moments in the caller's workspace (sized by
+    // eks_filter_smooth_workspace_bytes)
+    P* w = a.Pf + (size_t)a.B * a.T * a.D * a.D;
+    const size_t rec = (size_t)a.B * g.nruns * g.nm;
+    g.bnd_f_start = w;
+    g.bnd_f_end = w + rec;
+    g.bnd_b = w + 2 * rec;
+    g.flag = (int*)(w + 3 * rec);
+    const int D = a.D, O = a.O;
+    if (a.ncam > 0) {
+        if (O == 4) return runs_smooth_launch<P, 3, 4, true, true>(a, g, st);
+        if (O == 6) return runs_smooth_launch<P, 3, 6, true, true>(a, g, st);
+        if (O == 8) return runs_smooth_launch<P, 3, 8, true, true>(a, g, st);
+        return runs_smooth_launch<P, 3, EKS_MAX_CHAN, false, true>(a, g, st);
+    }
+    if (D == 2 && O == 2) return runs_smooth_launch<P, 2, 2, true, false>(a, g, st);
+    if (D == 3 && O == 4) return runs_smooth_launch<P, 3, 4, true, false>(a, g, st);
+    if (D == 3 && O == 6) return runs_smooth_launch<P, 3, 6, true, false>(a, g, st);
+    if (D == 3 && O == 8) return runs_smooth_launch<P, 3, 8, true, false>(a, g, st);
+    return runs_smooth_launch<P, EKS_MAX_STATE, EKS_MAX_CHAN, false, false>(a, g, st);
+}
+template int generic_runs_smooth<float>(const GArgs<float>&, cudaStream_t);
+template int generic_runs_smooth<double>(const GArgs<double>&, cudaStream_t);
+
+size_t generic_runs_smooth_extra_bytes(int dtype, int B, int D, int T) {
+    int run_len;
+    const int nruns = runs_geometry(T, B, run_len);
+    return 3 * (size_t)B * nruns * (D + D * D) * (dtype == EKS_F32 ? 4 : 8) + 256;
+}
+
+}  // namespace eks

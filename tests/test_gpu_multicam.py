@@ -130,3 +130,69 @@ def test_core_api_shapes_and_blocks():
     s, ms, Vs = eks_b200.run_kalman_smoother(ys, np.zeros((K, 2)), eye, eye, eye, eye, np.ones((T, K, 2)),
                                              smooth_param=[1.0, 2.0, 3.0])
     assert ms.shape == (K, T, 2) and Vs.shape == (K, T, 2, 2) and list(s) == [1.0, 2.0, 3.0]
+
+
+def _linear_case(K, T, seed, r_scale=1.0, q_scale=1.0):
+    rng = np.random.default_rng(seed)
+    V = 2
+    W = np.linalg.qr(rng.standard_normal((2 * V, 3)))[0]
+    lat = np.cumsum(rng.normal(0, 0.3 * np.sqrt(q_scale), (K, T, 3)), axis=1)
+    ev = rng.uniform(0.1, 0.6, (T, K, 2 * V)) * r_scale
+    ys = lat @ W.T + rng.standard_normal((K, T, 2 * V)) * np.sqrt(np.swapaxes(ev, 0, 1))
+    ys -= ys.mean(axis=1, keepdims=True)
+    Q = np.array([[1.0, 0.2, 0.05], [0.2, 0.7, 0.1], [0.05, 0.1, 0.5]])
+    return (ys, np.zeros((K, 3)), np.tile(np.diag([5.0, 4.0, 3.0]), (K, 1, 1)), np.tile(np.eye(3), (K, 1, 1)),
+            np.tile(W, (K, 1, 1)), np.tile(Q, (K, 1, 1)), ev)
+
+
+@pytest.mark.parametrize('T', [4096, 13001])
+def test_run_parallel_generic_linear_matches_oracle(T):
+    """T >= 4096 switches the generic path to verified run-parallel execution (generic_runs.cu): results must
+    equal the sequential oracle -- identical Adam iteration counts in fp64."""
+    import eks_b200
+    from oracle import oracle
+    args = _linear_case(3, T, seed=T)
+    eks_b200.set_precision('float64')
+    s, ms, Vs = eks_b200.run_kalman_smoother(*args)
+    s_o, ms_o, Vs_o, info = oracle.run_kalman_smoother(*args, dtype=np.float64)
+    np.testing.assert_allclose(s, s_o, rtol=RTOL64)
+    np.testing.assert_allclose(ms, ms_o, rtol=RTOL64, atol=1e-7 * np.abs(ms_o).max())
+    np.testing.assert_allclose(Vs, Vs_o, rtol=RTOL64, atol=1e-9 * np.abs(Vs_o).max())
+
+
+def test_run_parallel_generic_slow_forgetting_escalates():
+    """huge observation noise + small process noise: the filter forgets slowly, the 64-frame warm-up fails the
+    boundary verification and must be escalated; the result still equals the sequential oracle."""
+    import eks_b200
+    from oracle import oracle
+    args = _linear_case(2, 6000, seed=3, r_scale=2000.0, q_scale=1e-3)
+    eks_b200.set_precision('float64')
+    s, ms, Vs = eks_b200.run_kalman_smoother(*args, smooth_param=1e-3)
+    s_o, ms_o, Vs_o, _ = oracle.run_kalman_smoother(*args, smooth_param=1e-3, dtype=np.float64)
+    np.testing.assert_allclose(ms, ms_o, rtol=RTOL64, atol=1e-7 * np.abs(ms_o).max())
+    np.testing.assert_allclose(Vs, Vs_o, rtol=RTOL64, atol=1e-9 * np.abs(Vs_o).max())
+    s, ms, Vs = eks_b200.run_kalman_smoother(*args)
+    s_o, ms_o, Vs_o, _ = oracle.run_kalman_smoother(*args, dtype=np.float64)
+    np.testing.assert_allclose(s, s_o, rtol=RTOL64)
+    np.testing.assert_allclose(ms, ms_o, rtol=RTOL64, atol=1e-7 * np.abs(ms_o).max())
+
+
+def test_run_parallel_generic_pinhole_matches_oracle():
+    import eks_b200
+    from eks_b200.core import PinholeProjection
+    from oracle import oracle
+    from test_oracle import fly_cams
+    cams = fly_cams()
+    rng = np.random.default_rng(2)
+    K, T = 2, 5000
+    X = np.array([-1.75, -0.30, 3.5]) + np.cumsum(rng.standard_normal((K, T, 3)) * 1e-3, axis=1)
+    ys = np.stack([oracle.project(cams, X[k]) for k in range(K)]) + rng.standard_normal((K, T, 6)) * 0.5
+    ev = rng.uniform(0.1, 0.5, (T, K, 6))
+    args = (ys, X[:, 0, :] + 0.01, np.tile(np.eye(3) * 1e-2, (K, 1, 1)), np.tile(np.eye(3), (K, 1, 1)), None,
+            np.tile(np.eye(3) * 1e-6, (K, 1, 1)), ev)
+    eks_b200.set_precision('float64')
+    s, ms, Vs = eks_b200.run_kalman_smoother(*args, h_fn=PinholeProjection(cams))
+    s_o, ms_o, Vs_o, _ = oracle.run_kalman_smoother(*args, cams=cams, dtype=np.float64)
+    np.testing.assert_allclose(s, s_o, rtol=1e-4)
+    np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(Vs, Vs_o, rtol=1e-3, atol=1e-6 * np.abs(Vs_o).max())
