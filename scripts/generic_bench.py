@@ -15,6 +15,8 @@ from eks_b200.core import PinholeProjection  # noqa: E402
 from test_oracle import fly_cams  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+import logging
+logging.basicConfig(level=logging.DEBUG if os.environ.get('EKS_DEBUG') else logging.WARNING)
 rng = np.random.default_rng(0)
 
 
