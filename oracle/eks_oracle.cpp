@@ -187,7 +187,7 @@ struct FilterState {
 // Returns false when the innovation covariance is not positive definite / not finite.
 template <class S, class R>
 inline bool ekf_step(const Model<R>& mdl, const R* y, const R* Rdiag, S s, FilterState<S>& st, S& ll,
-                     S* mf_out, S* Pf_out) {
+                     S* mf_out, S* Pf_out, const S* A_s = nullptr, const S* Q_s = nullptr) {
     const int D = mdl.D, O = mdl.O;
     S yhat[OMAX], H[OMAX * DMAX], HP[OMAX * DMAX], Sm[OMAX * OMAX], L[OMAX * OMAX];
     emission<S, R>(mdl, st.m, yhat, H);
@@ -266,19 +266,19 @@ inline bool ekf_step(const Model<R>& mdl, const R* y, const R* Rdiag, S s, Filte
     S AP[DMAX * DMAX];
     for (int i = 0; i < D; ++i) {
         S acc = S(R(0));
-        for (int k = 0; k < D; ++k) acc += S(mdl.A[i * D + k]) * mf[k];
+        for (int k = 0; k < D; ++k) acc += (A_s ? A_s[i * D + k] : S(mdl.A[i * D + k])) * mf[k];
         st.m[i] = acc;
         for (int j = 0; j < D; ++j) {
             S a2 = S(R(0));
-            for (int k = 0; k < D; ++k) a2 += S(mdl.A[i * D + k]) * Pf[k * D + j];
+            for (int k = 0; k < D; ++k) a2 += (A_s ? A_s[i * D + k] : S(mdl.A[i * D + k])) * Pf[k * D + j];
             AP[i * D + j] = a2;
         }
     }
     for (int i = 0; i < D; ++i)
         for (int j = 0; j < D; ++j) {
             S acc = S(R(0));
-            for (int k = 0; k < D; ++k) acc += AP[i * D + k] * S(mdl.A[j * D + k]);
-            st.P[i * D + j] = acc + s * S(mdl.Q[i * D + j]);
+            for (int k = 0; k < D; ++k) acc += AP[i * D + k] * (A_s ? A_s[j * D + k] : S(mdl.A[j * D + k]));
+            st.P[i * D + j] = acc + (Q_s ? Q_s[i * D + j] : s * S(mdl.Q[i * D + j]));
         }
     return true;
 }
@@ -491,6 +491,86 @@ inline void ensemble(const R* raw, int M, int V, int T, int K, int avg_median, i
         }
 }
 
+
+// ---------------------------------------------------------------- IBL pupil model
+// Restates pupil_optimize_smooth / run_pupil_kalman_smoother (eks/ibl_pupil_smoother.py:363-607):
+// 3 states [diameter, com_x, com_y], AR(1) dynamics A = diag(s_d, s_c, s_c),
+// Q = diag(var_d (1 - s_d^2), var_x (1 - s_c^2), var_y (1 - s_c^2)), 8 observations through a fixed C,
+// time-varying diagonal R_t in the loss, two parameters u -> s = sigmoid(u) (1 - 2e-3) + 1e-3,
+// optax.adam(lr) on u with the relative-tolerance stop rule.
+inline float exp_(float x) { return std::exp(x); }
+inline double exp_(double x) { return std::exp(x); }
+template <class T> inline Dual<T> exp_(Dual<T> a) { auto e = exp_(a.v); return {e, a.d * e}; }
+
+template <class S, class R>
+inline void pupil_AQ(const S u[2], const R var3[3], S* A_s, S* Q_s) {
+    S sv[2];
+    for (int i = 0; i < 2; ++i) {
+        S sg = S(R(1)) / (S(R(1)) + exp_(-u[i]));                    // jax.nn.sigmoid
+        sv[i] = sg * S(R(1) - R(2) * R(1e-3)) + S(R(1e-3));          // _to_stable_s
+    }
+    const S sd[3] = {sv[0], sv[1], sv[1]};
+    for (int i = 0; i < 9; ++i) { A_s[i] = S(R(0)); Q_s[i] = S(R(0)); }
+    for (int i = 0; i < 3; ++i) {
+        A_s[i * 3 + i] = sd[i];
+        Q_s[i * 3 + i] = S(var3[i]) * (S(R(1)) - sd[i] * sd[i]);
+    }
+}
+
+template <class R>
+inline void pupil_nll_and_grad(const Model<R>& mdl, const R var3[3], const R* y, const R* Rdiag, int T,
+                               const R u[2], R* nll, R grad[2]) {
+    using S = Dual<R>;
+    for (int k = 0; k < 2; ++k) {   // one forward-mode pass per parameter
+        S ud[2] = {S(u[0], k == 0 ? R(1) : R(0)), S(u[1], k == 1 ? R(1) : R(0))};
+        S A_s[9], Q_s[9];
+        pupil_AQ<S, R>(ud, var3, A_s, Q_s);
+        FilterState<S> st;
+        for (int i = 0; i < 3; ++i) st.m[i] = S(mdl.m0[i]);
+        for (int i = 0; i < 9; ++i) st.P[i] = S(mdl.S0[i]);
+        S ll = S(R(0));
+        bool ok = true;
+        for (int t = 0; t < T && ok; ++t)
+            ok = ekf_step<S, R>(mdl, y + (size_t)t * mdl.O, Rdiag + (size_t)t * mdl.O, S(R(1)), st, ll, nullptr,
+                                nullptr, A_s, Q_s);
+        *nll = ok ? -ll.v : std::numeric_limits<R>::quiet_NaN();
+        grad[k] = ok ? -ll.d : std::numeric_limits<R>::quiet_NaN();
+    }
+}
+
+template <class R>
+inline void pupil_optimize(const Model<R>& mdl, const R var3[3], const R* y, const R* Rdiag, int T, R lr, R tol,
+                           int cap, R u_out[2], R* last_loss, int* iters_out, R* trace, int trace_cap) {
+    const R b1 = R(0.9), b2 = R(0.999), eps = R(1e-8);
+    const float s0[2] = {0.99f, 0.98f};
+    R u[2], mu[2] = {0, 0}, nu[2] = {0, 0};
+    for (int i = 0; i < 2; ++i) u[i] = R(std::log(s0[i] / (1.0f - s0[i])));  // float32 seed
+    R prev = std::numeric_limits<R>::infinity();
+    int iters = 0;
+    bool done = false;
+    while (!done && iters < cap) {
+        R loss, g[2];
+        pupil_nll_and_grad<R>(mdl, var3, y, Rdiag, T, u, &loss, g);
+        if (trace && iters < trace_cap) { trace[3 * iters] = u[0]; trace[3 * iters + 1] = u[1]; trace[3 * iters + 2] = loss; }
+        const int count = iters + 1;
+        for (int i = 0; i < 2; ++i) {
+            mu[i] = b1 * mu[i] + (R(1) - b1) * g[i];
+            nu[i] = b2 * nu[i] + (R(1) - b2) * g[i] * g[i];
+            const R mh = mu[i] / (R(1) - std::pow(b1, R(count)));
+            const R nh = nu[i] / (R(1) - std::pow(b2, R(count)));
+            u[i] = u[i] - lr * mh / (std::sqrt(nh) + eps);
+        }
+        const R rel_tol = tol * std::fabs(std::log(std::max(prev, R(1e-12))));
+        const bool stop = std::isfinite(prev) ? (std::fabs(loss - prev) < rel_tol + R(1e-6)) : false;
+        prev = loss;
+        iters += 1;
+        done = stop;
+    }
+    u_out[0] = u[0]; u_out[1] = u[1];
+    *last_loss = prev;
+    *iters_out = iters;
+}
+
 template <class R>
 Model<R> make_model(int D, int O, const R* m0, const R* S0, const R* A, const R* Q, const R* C, int ncam,
                     const R* cams) {
@@ -552,6 +632,17 @@ Model<R> make_model(int D, int O, const R* m0, const R* S0, const R* A, const R*
                         trace_cap);                                                                           \
         }                                                                                                     \
     }                                                                                                         \
+    extern "C" void eks_oracle_pupil_nll_grad_##P(const R* m0, const R* S0, const R* C, const R* var3, const R* y,  \
+                                                  const R* Rdiag, int T, const R* u, R* nll, R* grad) {           \
+        Model<R> mdl = make_model<R>(3, 8, m0, S0, nullptr, nullptr, C, 0, nullptr);                              \
+        pupil_nll_and_grad<R>(mdl, var3, y, Rdiag, T, u, nll, grad);                                              \
+    }                                                                                                             \
+    extern "C" void eks_oracle_pupil_optimize_##P(const R* m0, const R* S0, const R* C, const R* var3, const R* y,  \
+                                                  const R* Rdiag, int T, R lr, R tol, int cap, R* u_out,          \
+                                                  R* last_loss, int* iters, R* trace, int trace_cap) {            \
+        Model<R> mdl = make_model<R>(3, 8, m0, S0, nullptr, nullptr, C, 0, nullptr);                              \
+        pupil_optimize<R>(mdl, var3, y, Rdiag, T, lr, tol, cap, u_out, last_loss, iters, trace, trace_cap);       \
+    }                                                                                                             \
     extern "C" void eks_oracle_smooth_##P(int K, int D, int O, const R* m0, const R* S0, const R* A,          \
                                           const R* Q, const R* C, int ncam, const R* cams, const R* y,        \
                                           const R* Rdiag, int R_tv, int T, const R* s, R* ms, R* Vs, R* mfs,  \
