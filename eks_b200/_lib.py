@@ -55,6 +55,11 @@ _SIGS = {
                                   c_void_p]),
 }
 _OPTIONAL_SIGS = {
+    'eks_pupil_optimize_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'eks_pupil_optimize': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                   c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_void_p,
+                                   c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_size_t, c_void_p]),
     'eks_reproject': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_longlong, c_longlong,
                               c_void_p, c_void_p]),

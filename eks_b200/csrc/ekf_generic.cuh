@@ -95,7 +95,7 @@ struct Dims {
 // Returns false if an innovation variance is not positive/finite.
 template <class S, class P, int DC, int OC, bool FIXED, bool NL>
 EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const P* yv, const P* rv, S s, S* m,
-                     S* Pm, S& nll, S* mf_out, S* Pf_out) {
+                     S* Pm, S& nll, S* mf_out, S* Pf_out, const S* Adiag = nullptr, const S* Qdiag = nullptr) {
     const int D = dm.D(), O = dm.O();
     const P HALF_LOG2PI = P(0.91893853320467274178032973640562);
     S delta[DC];  // m_cur - m_pred
@@ -181,6 +181,18 @@ EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, cons
         for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pf_out[i] = Pm[i];
     }
     // predict: m = A m_f ; P = A P_f A^T + s Q
+    if (Adiag != nullptr) {  // parameter-dependent diagonal dynamics (IBL pupil AR(1) model): A = diag, Q~ = diag
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            if (i < D) {
+                m[i] = Adiag[i] * mf[i];
+#pragma unroll
+                for (int j = 0; j < DC; ++j)
+                    if (j < D) Pm[i * D + j] = Adiag[i] * Pm[i * D + j] * Adiag[j] + (i == j ? Qdiag[i] : S(P(0)));
+            }
+        }
+        return ok;
+    }
     S AP[DC * DC];
 #pragma unroll
     for (int i = 0; i < DC; ++i) {

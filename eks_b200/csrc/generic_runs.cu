@@ -473,6 +473,251 @@ int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st) {
 template int generic_runs_smooth<float>(const GArgs<float>&, cudaStream_t);
 template int generic_runs_smooth<double>(const GArgs<double>&, cudaStream_t);
 
+// =====================================================================================================
+// IBL pupil model (eks/ibl_pupil_smoother.py:363-607): 3 states [diameter, com_x, com_y], AR(1) dynamics
+// A = diag(s_d, s_c, s_c), Q = diag(var_i (1 - s_i^2)), 8 observations through a fixed C, time-varying diagonal
+// R_t in the loss, two parameters u -> s = sigmoid(u)(1 - 2e-3) + 1e-3, optax.adam(lr) on u, relative-tolerance
+// stop rule, cap 5000.  One thread per (session, run, parameter direction): forward-mode dual on u_k.
+// Same verified run-parallel scheme as above (nruns = 1 for short sequences = the exact sequential filter).
+// =====================================================================================================
+template <class P>
+struct PupilState {
+    P u[2], mu[2], nu[2], prev, s[2];
+    int iters, done, redo;
+};
+
+template <class P>
+struct PupilArgs {
+    int B, T, n;                    // n = cropped frames of the loss
+    GSpans sp;
+    const P *m0, *S0, *C, *var3;    // [B][3], [B][3][3], [B][8][3], [B][3]
+    PlaneView y, var;
+    const P* ymean;                 // [B][8] or null
+    P lr, tol;
+    int cap;
+    int run_len, nruns, slot, total_slots;
+    PupilState<P>* st;              // [B]
+    int* warm;                      // [B]
+    double* part;                   // [B][nruns][2 dirs][3]
+    P* bnd_start;                   // [B][nruns][2][24]
+    P* bnd_end;
+    P *u_out, *s_out, *last_loss_out;
+    int* iters_out;
+    P* trace;
+    int trace_cap;
+};
+
+template <class S, class P>
+__device__ inline void pupil_AQ(const S u[2], const P* var3, S* Ad, S* Qd) {
+    S sv[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const S ex(exp_(-u[i].v), -u[i].d * exp_(-u[i].v));
+        const S sg = S(P(1)) / (S(P(1)) + ex);                          // jax.nn.sigmoid
+        sv[i] = sg * S(P(1) - P(2) * P(1e-3)) + S(P(1e-3));             // _to_stable_s
+    }
+    const S sd[3] = {sv[0], sv[1], sv[1]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        Ad[i] = sd[i];
+        Qd[i] = S(var3[i]) * (S(P(1)) - sd[i] * sd[i]);
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(32) pupil_nll_runs_kernel(const __grid_constant__ PupilArgs<P> a) {
+    using S = Dual<P>;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * a.nruns * 2) return;
+    const int k = idx & 1, br = idx >> 1;
+    const int b = br / a.nruns, r = br - b * a.nruns;
+    if (a.st[b].done) return;
+    const int n = a.n;
+    const int t0 = r * a.run_len, t1 = min(n, t0 + a.run_len);
+    double* part = a.part + (((long long)b * a.nruns + r) * 2 + k) * 3;
+    if (t0 >= n) { part[0] = 0; part[1] = 0; part[2] = 0; return; }
+    const int start = max(0, t0 - a.warm[b]);
+    Dims<3, 8, true> dm{3, 8};
+    SeqModel<P> mdl{3, 8, 0, a.m0 + b * 3, a.S0 + b * 9, nullptr, nullptr, a.C + b * 24, nullptr};
+    SeqObs<P> ob;
+    ob.y_base = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride;
+    ob.y_off = a.y.chan_off;
+    ob.ymean = a.ymean ? a.ymean + b * 8 : nullptr;
+    ob.var_base = reinterpret_cast<const P*>(a.var.base) + (long long)b * a.var.seq_stride;
+    ob.var_off = a.var.chan_off;
+    ob.Rconst = nullptr;
+    ob.var_floor = P(1e-12);
+    FrameMap fm{a.sp};
+    const S u[2] = {S(a.st[b].u[0], k == 0 ? P(1) : P(0)), S(a.st[b].u[1], k == 1 ? P(1) : P(0))};
+    S Ad[3], Qd[3];
+    pupil_AQ<S, P>(u, a.var3 + b * 3, Ad, Qd);
+    S m[3], Pm[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m[i] = S(mdl.m0[i]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Pm[i] = S(mdl.S0[i]);
+    S nll = S(P(0));
+    bool ok = true;
+    P* bs = a.bnd_start + (((long long)b * a.nruns + r) * 2 + k) * 24;
+    P* be = a.bnd_end + (((long long)b * a.nruns + r) * 2 + k) * 24;
+    for (int i = start; i < t1; ++i) {
+        if (i == t0) {
+            for (int q = 0; q < 3; ++q) { bs[q] = m[q].v; bs[12 + q] = m[q].d; }
+            for (int q = 0; q < 9; ++q) { bs[3 + q] = Pm[q].v; bs[15 + q] = Pm[q].d; }
+            nll = S(P(0));
+            ok = true;
+        }
+        P yv[8], rv[8];
+        load_obs<P, 8>(ob, 8, fm(i), yv, rv);
+        ok = ekf_step<S, P, 3, 8, true, false>(dm, mdl, yv, rv, S(P(1)), m, Pm, nll, (S*)nullptr, (S*)nullptr, Ad, Qd) && ok;
+    }
+    for (int q = 0; q < 3; ++q) { be[q] = m[q].v; be[12 + q] = m[q].d; }
+    for (int q = 0; q < 9; ++q) { be[3 + q] = Pm[q].v; be[15 + q] = Pm[q].d; }
+    part[0] = (double)nll.v;
+    part[1] = (double)nll.d;
+    part[2] = ok ? 0.0 : 1.0;
+}
+
+// one warp per session: lanes stride over the runs (boundary check, fixed-order partial sums), lane 0 steps Adam
+template <class P>
+__global__ void __launch_bounds__(32) pupil_adam_kernel(const __grid_constant__ PupilArgs<P> a, int first) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    PupilState<P>& st = a.st[b];
+    if (first) {
+        if (lane == 0) {
+            const float s0[2] = {0.99f, 0.98f};
+            for (int i = 0; i < 2; ++i) { st.u[i] = P(logf(s0[i] / (1.0f - s0[i]))); st.mu[i] = P(0); st.nu[i] = P(0); }
+            st.prev = P(INFINITY);
+            st.iters = 0; st.redo = 0;
+            st.done = (a.cap <= 0);
+            a.warm[b] = RUNS_W0;
+        }
+        return;
+    }
+    if (st.done) return;
+    const int n = a.n, warm = a.warm[b];
+    bool verified = true;
+    for (int r = 1 + lane; r < a.nruns; r += 32) {
+        const int t0 = r * a.run_len;
+        if (t0 >= n || t0 - warm <= 0) continue;
+        for (int k = 0; k < 2; ++k)
+            verified = runs_boundary_ok<P>(a.bnd_end + (((long long)b * a.nruns + r - 1) * 2 + k) * 24,
+                                           a.bnd_start + (((long long)b * a.nruns + r) * 2 + k) * 24, 3, P(1)) && verified;
+    }
+    verified = __all_sync(0xffffffffu, verified);
+    const bool last_slot = (a.slot == a.total_slots - 1);
+    if (!verified && !last_slot) {
+        if (lane == 0) {
+            a.warm[b] = (warm >= n / 4) ? n : warm * 4;
+            st.redo += 1;
+        }
+        return;
+    }
+    double v = 0, g0 = 0, g1 = 0, bad = 0;
+    for (int r = lane; r < a.nruns; r += 32) {
+        const double* p = a.part + ((long long)b * a.nruns + r) * 6;
+        v += p[0]; g0 += p[1]; g1 += p[4]; bad += p[2] + p[5];
+    }
+    v = warp_sum(v); g0 = warp_sum(g0); g1 = warp_sum(g1); bad = warp_sum(bad);
+    if (lane != 0) return;
+    P loss = (P)v, gr[2] = {(P)g0, (P)g1};
+    if (bad > 0) { loss = P(NAN); gr[0] = gr[1] = P(NAN); }   // the reference has no finite-guard here
+    if (a.trace && st.iters < a.trace_cap) {
+        P* tr = a.trace + ((long long)b * a.trace_cap + st.iters) * 3;
+        tr[0] = st.u[0]; tr[1] = st.u[1]; tr[2] = loss;
+    }
+    const P b1 = P(0.9), b2 = P(0.999), eps = P(1e-8);
+    const int count = st.iters + 1;
+    for (int i = 0; i < 2; ++i) {
+        st.mu[i] = b1 * st.mu[i] + (P(1) - b1) * gr[i];
+        st.nu[i] = b2 * st.nu[i] + (P(1) - b2) * gr[i] * gr[i];
+        const P mh = st.mu[i] / (P(1) - pow_(b1, P(count)));
+        const P nh = st.nu[i] / (P(1) - pow_(b2, P(count)));
+        st.u[i] = st.u[i] - a.lr * mh / (sqrt_(nh) + eps);
+    }
+    const P pm = st.prev > P(1e-12) ? st.prev : P(1e-12);
+    const P rel_tol = a.tol * fabs(log_(pm));
+    const bool stop = isfinite((double)st.prev) ? (fabs(loss - st.prev) < rel_tol + P(1e-6)) : false;
+    st.prev = loss;
+    st.iters = count;
+    if (stop || count >= a.cap || last_slot) {
+        st.done = 1;
+        for (int i = 0; i < 2; ++i) {
+            const P sg = P(1) / (P(1) + exp_(-st.u[i]));
+            a.u_out[b * 2 + i] = st.u[i];
+            a.s_out[b * 2 + i] = sg * (P(1) - P(2) * P(1e-3)) + P(1e-3);
+        }
+        a.last_loss_out[b] = st.prev;
+        a.iters_out[b] = st.iters;
+    }
+}
+
+template <class P>
+__global__ void pupil_done_kernel(const PupilState<P>* st, int B, int* flag) {
+    int all = 1;
+    for (int b = threadIdx.x; b < B; b += 32) all &= st[b].done;
+    all = __all_sync(0xffffffffu, all);
+    if (threadIdx.x == 0) *flag = all;
+}
+
+static int pupil_geometry(int n, int B, int& run_len) {
+    // the evaluation is latency-bound (one thread walks run_len + warm-up frames, ~5000 evaluations possible), so
+    // runs are as short as the 64-frame warm-up allows; at most ~128k threads in flight
+    if (n < 256) { run_len = n; return 1; }
+    const long long cap_threads = 131072;
+    long long rl = ((long long)n * 2 * B + cap_threads - 1) / cap_threads;
+    if (rl < 64) rl = 64;
+    run_len = (int)((rl + 31) / 32 * 32);
+    return (n + run_len - 1) / run_len;
+}
+
+size_t pupil_optimize_workspace_bytes(int dtype, int B, int T) {
+    const size_t w = dtype == EKS_F32 ? 4 : 8;
+    int run_len;
+    const int nruns = pupil_geometry(T, B, run_len);
+    return 2048 + (size_t)B * 256 + (size_t)B * 4 + 256 + (size_t)B * nruns * 6 * sizeof(double) + 256 +
+           2 * ((size_t)B * nruns * 2 * 24 * w + 256);
+}
+
+template <class P>
+int pupil_optimize_run(PupilArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    static_assert(sizeof(PupilState<P>) <= 256, "workspace bound");
+    a.nruns = pupil_geometry(a.n, a.B, a.run_len);
+    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
+    EKS_REQUIRE(workspace && workspace_bytes >= pupil_optimize_workspace_bytes(dtype, a.B, a.T),
+                "pupil_optimize: workspace too small");
+    unsigned char* w = (unsigned char*)workspace;
+    auto take = [&](size_t bytes) { unsigned char* p = w; w += (bytes + 255) / 256 * 256; return p; };
+    a.st = (PupilState<P>*)take((size_t)a.B * 256);
+    a.warm = (int*)take((size_t)a.B * 4);
+    a.part = (double*)take((size_t)a.B * a.nruns * 6 * sizeof(double));
+    a.bnd_start = (P*)take((size_t)a.B * a.nruns * 2 * 24 * sizeof(P));
+    a.bnd_end = (P*)take((size_t)a.B * a.nruns * 2 * 24 * sizeof(P));
+    const int nthreads = a.B * a.nruns * 2;
+    a.total_slots = a.cap + (a.nruns > 1 ? RUNS_EXTRA : 0);
+    a.slot = -1;
+    pupil_adam_kernel<P><<<a.B, 32, 0, st>>>(a, 1);
+    // NOTE: the reference's cap is 5000 evaluations; the loop is unrolled on the stream in chunks and the host
+    // checks a completion flag between chunks so that converged problems do not pay for thousands of no-op
+    // launches (this entry point therefore synchronises the stream).
+    int h_done = 0;
+    int* d_flag = (int*)take(256);
+    const int chunk = 64;
+    for (int it = 0; it < a.total_slots; ++it) {
+        a.slot = it;
+        pupil_nll_runs_kernel<P><<<(nthreads + 31) / 32, 32, 0, st>>>(a);
+        pupil_adam_kernel<P><<<a.B, 32, 0, st>>>(a, 0);
+        if ((it + 1) % chunk == 0 || it + 1 == a.total_slots) {
+            pupil_done_kernel<P><<<1, 32, 0, st>>>(a.st, a.B, d_flag);
+            cudaError_t e = cudaMemcpyAsync(&h_done, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error("pupil_optimize: %s", cudaGetErrorString(e)); return (int)e; }
+            if (h_done) break;
+        }
+    }
+    return check_launch("pupil optimise kernels");
+}
+
 size_t generic_runs_smooth_extra_bytes(int dtype, int B, int D, int T) {
     int run_len;
     const int nruns = runs_geometry(T, B, run_len);
@@ -480,3 +725,48 @@ size_t generic_runs_smooth_extra_bytes(int dtype, int B, int D, int T) {
 }
 
 }  // namespace eks
+
+using namespace eks;
+
+extern "C" size_t eks_pupil_optimize_workspace_bytes(int dtype, int B, int T) {
+    return pupil_optimize_workspace_bytes(dtype, B, T);
+}
+
+extern "C" int eks_pupil_optimize(int dtype, int B, int T, const void* m0, const void* S0, const void* C,
+                                  const void* var3, const void* y_base, long long y_seq_stride,
+                                  const long long* y_off, const void* ymean, const void* var_base,
+                                  long long var_seq_stride, const long long* var_off, int n_spans,
+                                  const int* span_start, const int* span_end, double lr, double tol, int cap,
+                                  void* u_out, void* s_out, void* last_loss_out, int* iters_out, void* trace,
+                                  int trace_cap, void* workspace, size_t workspace_bytes, void* stream) {
+    EKS_REQUIRE(m0 && S0 && C && var3 && y_base && y_off && var_base && var_off && u_out && s_out && last_loss_out &&
+                    iters_out, "pupil_optimize: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 1 && cap >= 0, "pupil_optimize: bad dims");
+    GSpans sp;
+    if (n_spans <= 0) {
+        sp.n = 1; sp.start[0] = 0; sp.cum[0] = 0; sp.cum[1] = T; sp.total = T;
+    } else {
+        EKS_REQUIRE(n_spans <= G_MAX_SPANS, "at most %d frame spans supported on device", G_MAX_SPANS);
+        sp.n = n_spans; sp.cum[0] = 0;
+        for (int i = 0; i < n_spans; ++i) {
+            EKS_REQUIRE(span_start[i] >= 0 && span_end[i] <= T && span_start[i] < span_end[i], "bad span %d", i);
+            sp.start[i] = span_start[i];
+            sp.cum[i + 1] = sp.cum[i] + (span_end[i] - span_start[i]);
+        }
+        sp.total = sp.cum[n_spans];
+    }
+#define EKS_FILL(PT)                                                                                           \
+    PupilArgs<PT> a;                                                                                           \
+    memset(&a, 0, sizeof(a));                                                                                  \
+    a.B = B; a.T = T; a.n = sp.total; a.sp = sp;                                                               \
+    a.m0 = (const PT*)m0; a.S0 = (const PT*)S0; a.C = (const PT*)C; a.var3 = (const PT*)var3;                  \
+    a.y.base = y_base; a.y.seq_stride = y_seq_stride; a.var.base = var_base; a.var.seq_stride = var_seq_stride; \
+    for (int i = 0; i < MAX_CHAN; ++i) { a.y.chan_off[i] = i < 8 ? y_off[i] : 0; a.var.chan_off[i] = i < 8 ? var_off[i] : 0; } \
+    a.ymean = (const PT*)ymean; a.lr = (PT)lr; a.tol = (PT)tol; a.cap = cap;                                   \
+    a.u_out = (PT*)u_out; a.s_out = (PT*)s_out; a.last_loss_out = (PT*)last_loss_out; a.iters_out = iters_out; \
+    a.trace = (PT*)trace; a.trace_cap = trace_cap;                                                             \
+    return pupil_optimize_run<PT>(a, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (dtype == EKS_F32) { EKS_FILL(float) }
+    EKS_FILL(double)
+#undef EKS_FILL
+}

@@ -239,3 +239,26 @@ def reproject(ms: torch.Tensor, Vs: torch.Tensor, V: int, out: torch.Tensor, out
                               ptr(vo), int(pinhole_var_quirk), ptr(out), out_seq_stride, out_cam_stride, ptr(po),
                               stream_ptr()), 'eks_reproject')
     _count(1)
+
+
+def pupil_optimize(m0, S0, C, var3, y: PlaneView, var: PlaneView, T: int, ymean=None, spans=None, lr=5e-3,
+                   tol=1e-6, safety_cap=5000, trace_cap: int = 0):
+    """IBL pupil AR(1) parameter optimisation for B sessions.  Returns dict(u, s, loss, iters, trace)."""
+    dtype, dev = m0.dtype, m0.device
+    B = m0.shape[0]
+    u = torch.empty((B, 2), dtype=dtype, device=dev)
+    s = torch.empty((B, 2), dtype=dtype, device=dev)
+    loss = torch.empty(B, dtype=dtype, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    trace = torch.full((B, trace_cap, 3), float('nan'), dtype=dtype, device=dev) if trace_cap else None
+    nbytes = lib().eks_pupil_optimize_workspace_bytes(dt_code(dtype), B, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    yo, vo = i64_host(y.chan_off), i64_host(var.chan_off)
+    n, s0, s1 = _spans(spans, T)
+    check(lib().eks_pupil_optimize(dt_code(dtype), B, T, ptr(m0), ptr(S0), ptr(C), ptr(var3), ptr(y.base),
+                                   y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base), var.seq_stride, ptr(vo), n,
+                                   ptr(s0), ptr(s1), float(lr), float(tol), int(safety_cap), ptr(u), ptr(s),
+                                   ptr(loss), ptr(iters), ptr(trace), int(trace_cap), ptr(ws), nbytes,
+                                   stream_ptr()), 'eks_pupil_optimize')
+    _count(1 + 2 * int(iters.max().item()))
+    return dict(u=u, s=s, loss=loss, iters=iters, trace=trace)

@@ -143,6 +143,23 @@ int eks_reproject(int dtype, int B, int T, int D, int V, const void* ms, const v
                   const long long* var_chan_off_host, int pinhole_var_quirk, void* out, long long out_seq_stride,
                   long long out_cam_stride, const long long* plane_off_host, void* stream);
 
+/* IBL pupil model: replaces pupil_optimize_smooth (eks/ibl_pupil_smoother.py:452-607).  Per session b: 3 latent
+ * states [diameter, com_x, com_y], A = diag(s_d, s_c, s_c), Q = diag(var3 * (1 - s^2)), 8 observation channels
+ * through C [B][8][3], time-varying diagonal R_t from the var view (clipped at 1e-12), frames restricted to the
+ * spans.  Adam(lr) on u (s = sigmoid(u)(1 - 2e-3) + 1e-3, seed s = [0.99, 0.98]) with the reference's stop rule.
+ * Outputs per session: u_out [B][2], s_out [B][2] (the optimised s_d, s_c), last_loss_out [B], iters_out [B].
+ * trace (nullable): [B][trace_cap][3] rows (u0, u1, loss).  The final smoothing pass is eks_filter_smooth with
+ * A = diag(s), Q = diag(var3 (1 - s^2)) and s = 1.  This entry point synchronises the stream between chunks of
+ * 64 evaluations (the reference's cap is 5000). */
+size_t eks_pupil_optimize_workspace_bytes(int dtype, int B, int T);
+int eks_pupil_optimize(int dtype, int B, int T, const void* m0, const void* S0, const void* C, const void* var3,
+                       const void* y_base, long long y_seq_stride, const long long* y_chan_off_host,
+                       const void* ymean, const void* var_base, long long var_seq_stride,
+                       const long long* var_chan_off_host, int n_spans, const int* span_start_host,
+                       const int* span_end_host, double lr, double tol, int safety_cap, void* u_out, void* s_out,
+                       void* last_loss_out, int* iters_out, void* trace, int trace_cap, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

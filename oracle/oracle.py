@@ -399,3 +399,117 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
         out3d[:, k, 4] = Vs64[k][:, 1, 1]
         out3d[:, k, 5] = Vs64[k][:, 2, 2]
     return dict(cam_out=cam_out, out3d=out3d, s_finals=s_finals, info=info, ms=ms, Vs=Vs)
+
+
+# ----------------------------------------------------------------------------- IBL pupil model
+PUPIL_POINTS = ['pupil_top_r', 'pupil_bottom_r', 'pupil_right_r', 'pupil_left_r']
+PUPIL_C = np.array([[0, 1, 0], [-.5, 0, 1], [0, 1, 0], [.5, 0, 1], [.5, 1, 0], [0, 0, 1], [-.5, 1, 0], [0, 0, 1]],
+                   dtype=np.float64)
+
+
+def pupil_to_s(u, eps=1e-3):
+    """_to_stable_s, eks/ibl_pupil_smoother.py:518-520."""
+    return 1.0 / (1.0 + np.exp(-np.asarray(u, dtype=np.float64))) * (1.0 - 2 * eps) + eps
+
+
+def pupil_nll_grad(ys, m0, S0, C, var3, Rdiag, u, dtype=np.float64):
+    """-marginal_loglik of the pupil AR(1) model at u and its gradient (eks/ibl_pupil_smoother.py:551-563).
+    ys (T,8); Rdiag (T,8) (already clipped); u (2,)."""
+    ys, Rdiag = _c(ys, dtype), _c(Rdiag, dtype)
+    m0, S0, C, var3, u = _c(m0, dtype), _c(S0, dtype), _c(C, dtype), _c(var3, dtype), _c(u, dtype)
+    nll = np.empty(1, dtype=dtype)
+    grad = np.empty(2, dtype=dtype)
+    getattr(lib(), f'eks_oracle_pupil_nll_grad_{_sfx(dtype)}')(
+        _p(m0), _p(S0), _p(C), _p(var3), _p(ys), _p(Rdiag), ys.shape[0], _p(u), _p(nll), _p(grad))
+    return float(nll[0]), grad.astype(np.float64)
+
+
+def pupil_optimize(ys, m0, S0, C, var3, Rdiag, lr=5e-3, tol=1e-6, safety_cap=5000, dtype=np.float32, trace_cap=0):
+    """Adam on u from s0 = [0.99, 0.98] with the stop rule of eks/ibl_pupil_smoother.py:570-607."""
+    ys, Rdiag = _c(ys, dtype), _c(Rdiag, dtype)
+    m0, S0, C, var3 = _c(m0, dtype), _c(S0, dtype), _c(C, dtype), _c(var3, dtype)
+    u = np.empty(2, dtype=dtype)
+    loss = np.empty(1, dtype=dtype)
+    iters = np.zeros(1, dtype=np.int32)
+    trace = np.full((trace_cap, 3), np.nan, dtype=dtype) if trace_cap else None
+    getattr(lib(), f'eks_oracle_pupil_optimize_{_sfx(dtype)}')(
+        _p(m0), _p(S0), _p(C), _p(var3), _p(ys), _p(Rdiag), ys.shape[0], _real(dtype, lr), _real(dtype, tol),
+        int(safety_cap), _p(u), _p(loss), _p(iters), _p(trace), int(trace_cap))
+    return dict(u=u.astype(np.float64), s=pupil_to_s(u), loss=float(loss[0]), iters=int(iters[0]), trace=trace)
+
+
+def _pupil_points(preds8):
+    """(T,8) columns top/bottom/right/left x,y -> dict of (T,2) arrays."""
+    return {n: preds8[:, 2 * i:2 * i + 2] for i, n in enumerate(['top', 'bottom', 'right', 'left'])}
+
+
+def pupil_diameter(preds8):
+    """get_pupil_diameter, eks/ibl_pupil_smoother.py:70-100."""
+    p = _pupil_points(preds8)
+    dist = lambda a, b: np.sqrt(((p[a] - p[b]) ** 2).sum(axis=1))
+    ds = [dist('top', 'bottom'), dist('left', 'right')]
+    ds += [dist(a, b) * 2 ** 0.5 for a, b in [('top', 'left'), ('top', 'right'), ('bottom', 'left'), ('bottom', 'right')]]
+    with np.errstate(all='ignore'):
+        return np.nanmedian(np.stack(ds), axis=0)
+
+
+def pupil_location(preds8):
+    """get_pupil_location, eks/ibl_pupil_smoother.py:33-67."""
+    import warnings
+    p = _pupil_points(preds8)
+    out = np.zeros((preds8.shape[0], 2))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', category=RuntimeWarning)
+        xa = np.nanmedian(np.stack([p['top'][:, 0], p['bottom'][:, 0]], 1), axis=1)
+        xb = np.median(np.stack([p['right'][:, 0], p['left'][:, 0]], 1), axis=1)
+        out[:, 0] = np.nanmedian(np.stack([xa, xb], 1), axis=1)
+        ya = np.median(np.stack([p['top'][:, 1], p['bottom'][:, 1]], 1), axis=1)
+        yb = np.nanmedian(np.stack([p['right'][:, 1], p['left'][:, 1]], 1), axis=1)
+        out[:, 1] = np.nanmedian(np.stack([ya, yb], 1), axis=1)
+    return out
+
+
+def ibl_pupil(raw, smooth_params=None, s_frames=None, avg_mode='median', var_mode='confidence_weighted_var',
+              dtype=np.float32, trace_cap=0):
+    """ensemble_kalman_smoother_ibl_pupil restated (eks/ibl_pupil_smoother.py:197-359).
+    raw (M, T, 4, 3) in the fixed point order top, bottom, right, left.
+    Returns dict(out (4, 9, T) float64 in the reference's key-pair order top,right,bottom,left, s_finals, ms, Vs, info)."""
+    raw = np.asarray(raw, dtype=np.float64)
+    M, T, K, _ = raw.shape
+    ens = ensemble(raw[:, None], avg_mode=avg_mode, var_mode=var_mode, dtype=np.float64)[0]   # (T,K,5)
+    preds = ens[..., 0:2].reshape(T, -1).astype(np.float64)
+    evars = ens[..., 2:4].reshape(T, -1).astype(np.float64)
+    like = ens[..., 4].astype(np.float64)
+    diam, loc = pupil_diameter(preds), pupil_location(preds)
+    mx, my = loc[:, 0].mean(), loc[:, 1].mean()
+    xt, yt = loc[:, 0] - mx, loc[:, 1] - my
+    m0 = np.array([diam.mean(), 0.0, 0.0])
+    S0 = np.diag([np.nanvar(diam), np.nanvar(xt), np.nanvar(yt)])
+    var3 = np.array([diam.var(), xt.var(), yt.var()])
+    y = preds.copy()
+    y[:, 0::2] -= mx
+    y[:, 1::2] -= my
+    Rdiag = np.clip(evars, 1e-12, None)
+    info = {}
+    if smooth_params is not None and all(v is not None for v in smooth_params):
+        s = np.clip(np.asarray(smooth_params, dtype=np.float32), 1e-3, 1 - 1e-3).astype(np.float64)
+    else:
+        opt = pupil_optimize(crop_frames(y, s_frames), m0, S0, PUPIL_C, var3, crop_frames(Rdiag, s_frames),
+                             dtype=dtype, trace_cap=trace_cap)
+        s = opt['s']
+        info.update(opt)
+    sd = np.array([s[0], s[1], s[1]])
+    A, Q = np.diag(sd), np.diag(var3 * (1 - sd ** 2))
+    ms, Vs = smooth(y[None], m0[None], S0[None], A[None], PUPIL_C[None], Q[None], Rdiag[None], 1.0, dtype=dtype)
+    ms, Vs = ms[0].astype(np.float64), Vs[0].astype(np.float64)
+    ym = ms @ PUPIL_C.T
+    ym[:, 0::2] += mx
+    ym[:, 1::2] += my
+    yv = np.einsum('ij,tjk,lk->til', PUPIL_C, Vs, PUPIL_C)
+    order = [0, 2, 1, 3]                               # key pairs: top, right, bottom, left
+    ens_idx = [(0, 1), (4, 5), (2, 3), (6, 7)]
+    out = np.empty((4, 9, T))
+    for i, k in enumerate(order):
+        out[i] = [ym[:, 2 * k], ym[:, 2 * k + 1], like[:, i], preds[:, ens_idx[i][0]], preds[:, ens_idx[i][1]],
+                  evars[:, ens_idx[i][0]], evars[:, ens_idx[i][1]], yv[:, i, i], yv[:, i + 1, i + 1]]
+    return dict(out=out, s_finals=[float(s[0]), float(s[1])], ms=ms, Vs=Vs, info=info)

@@ -77,6 +77,32 @@ def multicam_case(name, cam_files, camera_names, keypoints=None, calibration=Non
     print(name, raw.shape, res['s_f64'], res['iters_f64'], res['iters_f32'])
 
 
+def pupil_case(name, files, **kw):
+    """IBL pupil smoother (eks/ibl_pupil_smoother.py) on the fixed point order; raw is the singlecam_ibl_pupil
+    golden's raw with keypoints re-ordered, so only the oracle outputs are stored."""
+    from oracle.oracle import PUPIL_POINTS
+    raw, kps = load_csvs(files, PUPIL_POINTS)
+    raw = raw.astype(np.float32).astype(np.float64)     # (M,T,4,3)
+    res = {'raw_from': np.array('singlecam_ibl_pupil'), 'keypoints': np.array(kps)}
+    for tag, dt in (('f64', np.float64), ('f32', np.float32)):
+        r = oracle.ibl_pupil(raw, dtype=dt, trace_cap=64, **kw)
+        res[f'out_{tag}'] = r['out'].astype(np.float64 if tag == 'f64' else np.float32)
+        res[f's_{tag}'] = np.asarray(r['s_finals'])
+        if 'iters' in r['info']:
+            res[f'iters_{tag}'] = np.asarray(r['info']['iters'])
+            res[f'loss_{tag}'] = np.asarray(r['info']['loss'])
+            res[f'trace_{tag}'] = r['info']['trace']
+    np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **res)
+    print(name, raw.shape, res['s_f64'], res['s_f32'], res.get('iters_f64'), res.get('iters_f32'))
+
+
+def pupil_goldens():
+    files = sorted(glob.glob(f'{REF}/ibl-pupil/*.csv'))
+    pupil_case('ibl_pupil', files)
+    pupil_case('ibl_pupil_sframes', files, s_frames=[(100, 700), (1200, None)])
+    pupil_case('ibl_pupil_fixed_s', files, smooth_params=[0.9, 0.95])
+
+
 def multicam_goldens():
     # BASELINE config 3 family: multicam linear on data/mirror-mouse-separate (2 cams x 10? seeds, 501 frames)
     d = f'{REF}/mirror-mouse-separate'
@@ -94,6 +120,9 @@ def multicam_goldens():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'pupil':
+        pupil_goldens()
+        sys.exit(0)
     # BASELINE config 1: `eks singlecam` on data/ibl-pupil (tests/integration/test_singlecam.py:4-10)
     singlecam_case('singlecam_ibl_pupil', sorted(glob.glob(f'{REF}/ibl-pupil/*.csv')))
     # fixed smoothing parameter and s_frames variants
@@ -105,3 +134,4 @@ if __name__ == '__main__':
     singlecam_case('singlecam_mirror_mouse', sorted(glob.glob(f'{REF}/mirror-mouse/*.csv')),
                    keypoints=None)
     multicam_goldens()
+    pupil_goldens()

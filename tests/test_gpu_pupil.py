@@ -1,0 +1,142 @@
+"""GPU parity tests of the IBL pupil smoother: CUDA path through the C ABI vs the CPU oracle."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import load_golden
+from test_pupil import pupil_raw_from_golden, synth_pupil
+
+pytestmark = pytest.mark.gpu
+RTOL64, RTOL32 = 1e-5, 1e-3
+
+
+def _marker_array(raw):
+    from eks_b200.marker_array import MarkerArray
+    return MarkerArray(np.ascontiguousarray(raw[:, None]), data_fields=['x', 'y', 'likelihood'], dtype=np.float64)
+
+
+def _run(raw, precision, **kw):
+    import eks_b200
+    from eks_b200.ibl_pupil_smoother import ensemble_kalman_smoother_ibl_pupil
+    from oracle.oracle import PUPIL_POINTS
+    eks_b200.set_precision(precision)
+    try:
+        df, s = ensemble_kalman_smoother_ibl_pupil(_marker_array(raw), PUPIL_POINTS, **kw)
+    finally:
+        eks_b200.set_precision('float32')
+    T = raw.shape[1]
+    out = df.to_numpy().reshape(T, 4, 9).transpose(1, 2, 0)     # (4, 9, T)
+    return out, s, df
+
+
+def _check(out, ref, rtol, label):
+    for c in range(9):
+        a, b = out[:, c], ref[:, c].astype(np.float64)
+        scale = np.maximum(np.abs(b), 1e-6 if c >= 5 else 1.0)
+        err = np.max(np.abs(a - b) / scale)
+        assert err <= rtol, f'{label}: column {c} rel err {err:.3e} > {rtol}'
+
+
+@pytest.mark.parametrize('name,kw', [('ibl_pupil', {}), ('ibl_pupil_sframes', dict(s_frames=[(100, 700), (1200, None)])),
+                                     ('ibl_pupil_fixed_s', dict(smooth_params=[0.9, 0.95]))])
+def test_ibl_pupil_fp64_matches_oracle(name, kw):
+    g = load_golden(name)
+    out, s, _ = _run(pupil_raw_from_golden(), 'float64', **kw)
+    np.testing.assert_allclose(s, g['s_f64'], rtol=RTOL64)
+    _check(out, g['out_f64'], RTOL64, name)
+
+
+@pytest.mark.parametrize('name,kw', [('ibl_pupil', {}), ('ibl_pupil_fixed_s', dict(smooth_params=[0.9, 0.95]))])
+def test_ibl_pupil_fp32(name, kw):
+    # the stop rule (|dloss| < 1e-6 |log loss| + 1e-6) sits below fp32 resolution of the loss, so the fp32 iteration
+    # count is rounding-noise dependent in the reference too; the bar is on s and the outputs
+    g = load_golden(name)
+    out, s, _ = _run(pupil_raw_from_golden(), 'float32', **kw)
+    np.testing.assert_allclose(s, g['s_f64'], rtol=RTOL32)
+    _check(out, g['out_f64'], RTOL32, name)
+
+
+def _device_model(raw, dtype):
+    """Build the pupil model arrays on the host exactly as the product does, return device tensors + host copies."""
+    from eks_b200 import ops
+    from eks_b200.ibl_pupil_smoother import PUPIL_C, pupil_model_arrays
+    from oracle import oracle
+    T = raw.shape[1]
+    ens = oracle.ensemble(raw[:, None], dtype=np.float64)[0]
+    preds, evars = ens[..., :2].reshape(T, 8), ens[..., 2:4].reshape(T, 8)
+    y, m0, S0, var3, _, _ = pupil_model_arrays(preds)
+    f = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda().to(dtype).contiguous()
+    yp, vp = f(y.T[None]), f(evars.T[None])
+    yv = ops.PlaneView(yp, 8 * T, [o * T for o in range(8)])
+    vv = ops.PlaneView(vp, 8 * T, [o * T for o in range(8)])
+    return dict(y=y, m0=m0, S0=S0, var3=var3, Rdiag=np.clip(evars, 1e-12, None), yv=yv, vv=vv,
+                dev=(f(m0[None]), f(S0[None]), f(PUPIL_C[None]), f(var3[None])))
+
+
+def test_pupil_optimizer_trace_fp64():
+    """Every Adam iterate (u, loss) of the device optimiser equals the oracle's, and so does the iteration count."""
+    from eks_b200 import ops
+    from oracle import oracle
+    raw = pupil_raw_from_golden()
+    mdl = _device_model(raw, torch.float64)
+    res = ops.pupil_optimize(*mdl['dev'], mdl['yv'], mdl['vv'], raw.shape[1], trace_cap=600)
+    ref = oracle.pupil_optimize(mdl['y'], mdl['m0'], mdl['S0'], oracle.PUPIL_C, mdl['var3'], mdl['Rdiag'],
+                                dtype=np.float64, trace_cap=600)
+    it = int(res['iters'][0])
+    assert it == ref['iters'], (it, ref['iters'])
+    tr = res['trace'][0, :it].cpu().numpy()
+    np.testing.assert_allclose(tr, ref['trace'][:it], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res['s'][0].cpu().numpy(), ref['s'], rtol=1e-9)
+
+
+@pytest.mark.parametrize('dtype,rtol', [(torch.float64, 1e-7), (torch.float32, 2e-3)])
+def test_pupil_long_sequence_run_parallel(dtype, rtol):
+    """Long sequences go through many short verified runs; the first iterates must still equal the sequential oracle."""
+    from eks_b200 import ops
+    from oracle import oracle
+    raw = synth_pupil(T=30000, seed=3)
+    mdl = _device_model(raw, dtype)
+    res = ops.pupil_optimize(*mdl['dev'], mdl['yv'], mdl['vv'], raw.shape[1], safety_cap=12, trace_cap=12)
+    ref = oracle.pupil_optimize(mdl['y'], mdl['m0'], mdl['S0'], oracle.PUPIL_C, mdl['var3'], mdl['Rdiag'],
+                                safety_cap=12, dtype=np.float64, trace_cap=12)
+    it = int(res['iters'][0])
+    assert it == ref['iters'] == 12
+    tr = res['trace'][0, :it].double().cpu().numpy()
+    np.testing.assert_allclose(tr[:, 2], ref['trace'][:it, 2], rtol=1e-9 if dtype == torch.float64 else 1e-5)
+    np.testing.assert_allclose(tr[:, :2], ref['trace'][:it, :2], rtol=rtol)
+
+
+def test_reference_style_random_input():
+    """Mirror of reference tests/test_ibl_pupil_smoother.py:174-211 (random inputs, 100 frames, s_frames (1,20))."""
+    from eks_b200.ibl_pupil_smoother import ensemble_kalman_smoother_ibl_pupil
+    from eks_b200.marker_array import input_dfs_to_markerArray
+    rng = np.random.default_rng(0)
+    bodyparts = ['pupil_top_r', 'pupil_bottom_r', 'pupil_right_r', 'pupil_left_r']
+    cols = [f'{b}_{c}' for b in bodyparts for c in ['x', 'y', 'likelihood']]
+    dfs = [pd.DataFrame(rng.normal(size=(100, 12)), columns=cols) for _ in range(2)]
+    ma = input_dfs_to_markerArray([dfs], bodyparts, [''])
+    for sp in ([0.5, 0.5], [None, None], None):
+        df, params = ensemble_kalman_smoother_ibl_pupil(ma, bodyparts, sp, [(1, 20)], avg_mode='mean', var_mode='var')
+        assert isinstance(df, pd.DataFrame) and df.shape == (100, 36)
+        assert len(params) == 2 and params[0] < 1 and params[1] < 1
+        if sp == [0.5, 0.5]:
+            assert params == sp
+        assert np.isfinite(df.to_numpy()).all()
+
+
+def test_fit_eks_pupil_writes_csv(tmp_path):
+    """fit_eks_pupil end to end on CSV files written from the golden's raw predictions."""
+    from eks_b200.ibl_pupil_smoother import fit_eks_pupil
+    from eks_b200.utils import make_dlc_pandas_index
+    from oracle.oracle import PUPIL_POINTS
+    raw = pupil_raw_from_golden()[:, :300]
+    for m in range(raw.shape[0]):
+        df = pd.DataFrame(raw[m].reshape(300, 12), columns=make_dlc_pandas_index(PUPIL_POINTS))
+        df.to_csv(tmp_path / f'pred{m}.csv')
+    out = tmp_path / 'out' / 'eks.csv'
+    df, s, dfs, bps = fit_eks_pupil(str(tmp_path), str(out), smooth_params=[0.99, 0.99])
+    assert out.exists() and df.shape == (300, 36) and bps == PUPIL_POINTS
+    back = pd.read_csv(out, header=[0, 1, 2], index_col=0)
+    np.testing.assert_allclose(back.to_numpy(), df.to_numpy(), rtol=1e-12)
+    np.testing.assert_allclose(s, [0.99, 0.99], rtol=1e-6)
