@@ -15,6 +15,10 @@ from eks_b200.core import (  # noqa: F401
     run_kalman_smoother,
     set_precision,
 )
+from eks_b200.ibl_pupil_smoother import (  # noqa: F401
+    ensemble_kalman_smoother_ibl_pupil,
+    fit_eks_pupil,
+)
 from eks_b200.marker_array import MarkerArray, input_dfs_to_markerArray  # noqa: F401
 from eks_b200.singlecam_smoother import (  # noqa: F401
     ensemble_kalman_smoother_singlecam,

