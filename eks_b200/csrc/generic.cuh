@@ -78,6 +78,6 @@ size_t generic_runs_optimize_workspace_bytes(int dtype, int n_blocks, int B, int
 template <class P>
 int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st);
 size_t generic_runs_smooth_extra_bytes(int dtype, int B, int D, int T);
-constexpr int GEN_RUNS_MIN_FRAMES = 4096;  // below this the sequential per-sequence kernels are used
+constexpr int GEN_RUNS_MIN_FRAMES = 512;   // below this the sequential per-sequence kernels are used
 
 }  // namespace eks

@@ -18,10 +18,14 @@
 #include "ekf_generic.cuh"
 #include "generic.cuh"
 #include "../../include/eks_b200.h"
+#include <cstdio>
+#include <vector>
+#include <cstdlib>
 
 namespace eks {
 
 constexpr int RUNS_W0 = 64;       // initial warm-up length (frames)
+constexpr int RUNS_WMAX32 = 16384;  // fp32: beyond this warm-up a remaining boundary mismatch is rounding noise, not memory
 constexpr int RUNS_EXTRA = 12;    // extra evaluation slots for warm-up escalations (64 * 4^10 > 10^7 frames)
 
 template <class P>
@@ -29,7 +33,8 @@ struct RunBlockState {
     AdamState<P> adam;
     P s, dsdlog;
     int done;
-    int redo;   // diagnostic: number of repeated evaluations
+    int redo;        // diagnostic: number of repeated evaluations
+    int unverified;  // diagnostic: evaluations accepted at the fp32 warm-up cap with a boundary mismatch left
 };
 
 template <class P>
@@ -44,9 +49,15 @@ struct RunArgs {
     P* bnd_start;             // [B][nruns][ns]
     P* bnd_end;               // [B][nruns][ns]
     int* flag;                // smoother: boundary mismatch flag
+    P tol;                    // boundary agreement tolerance
 };
 
-template <class P> __host__ __device__ inline P runs_tol() { return sizeof(P) == 4 ? P(2e-5) : P(1e-10); }
+template <class P> __host__ __device__ inline P runs_tol() { return sizeof(P) == 4 ? P(1e-4) : P(1e-10); }
+// host: default tolerance, overridable for experiments with EKS_RUNS_TOL32 / EKS_RUNS_TOL64
+template <class P> static P runs_tol_host() {
+    const char* e = getenv(sizeof(P) == 4 ? "EKS_RUNS_TOL32" : "EKS_RUNS_TOL64");
+    return e ? (P)atof(e) : runs_tol<P>();
+}
 // rounding floor: two different computation histories of the same quantity x differ by a few ulp of |x|
 template <class P> __host__ __device__ inline P runs_ulp() { return sizeof(P) == 4 ? P(64 * 1.2e-7) : P(64 * 2.3e-16); }
 
@@ -102,14 +113,14 @@ __global__ void __launch_bounds__(32) gen_nll_runs_kernel(const __grid_constant_
 // boundary agreement: |a - b| <= tol * scale, scale from the covariance (means), the variances (covariance)
 // and the magnitude of the sensitivities themselves
 template <class P>
-__device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval) {
-    const P tol = runs_tol<P>();
+__device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval, P tol) {
     bool ok = true;
     for (int i = 0; i < D; ++i) {
         const P sd = sqrt_(fabs(e[D + i * D + i]) + P(1e-30));
         ok = ok && (fabs(e[i] - s[i]) <= tol * sd + runs_ulp<P>() * fabs(e[i]));
         const P dsc = fabs(e[D + D * D + i]) + sd / sval;
-        ok = ok && (fabs(e[D + D * D + i] - s[D + D * D + i]) <= P(10) * tol * dsc);
+        // the sensitivity inherits the rounding floor of the mean it is driven by (innovations y - C m cancel)
+        ok = ok && (fabs(e[D + D * D + i] - s[D + D * D + i]) <= P(10) * tol * dsc + runs_ulp<P>() * fabs(e[i]) / sval);
         for (int j = 0; j < D; ++j) {
             const P pv = sqrt_(fabs(e[D + i * D + i] * e[D + j * D + j]) + P(1e-30));
             ok = ok && (fabs(e[D + i * D + j] - s[D + i * D + j]) <= tol * pv);
@@ -121,69 +132,85 @@ __device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval) {
 }
 
 // ---- per block: verify the run boundaries, then Adam step (or escalate the warm-up and repeat) ---------------
+// One CTA per block: threads stride over the runs of each member (boundary check, fixed-order partial sums);
+// thread 0 takes the Adam step.
+constexpr int ADAM_RUNS_NT = 128;
+
 template <class P>
-__global__ void __launch_bounds__(32) gen_adam_runs_kernel(const __grid_constant__ GArgs<P> a,
-                                                           const __grid_constant__ RunArgs<P> g, int first) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.n_blocks) return;
+__global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                                     const __grid_constant__ RunArgs<P> g, int first) {
+    __shared__ double scratch[32];
+    const int j = blockIdx.x, tid = threadIdx.x;
     RunBlockState<P>& bs = g.bstate[j];
     const int n = a.sp.total;
     if (first) {
+        if (tid != 0) return;
         adam_init(bs.adam, a.s_log0[j]);
         bs.done = (a.cap <= 0);
         bs.redo = 0;
-    } else {
-        if (bs.done) return;
-        bool verified = true;
-        for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
-            const int b = a.members[mi];
-            bool okb = true;
-            for (int r = 1; r < g.nruns && okb; ++r) {
-                const int t0 = r * g.run_len;
-                if (t0 >= n) break;
-                if (t0 - g.warm[b] <= 0) continue;  // this run started at frame 0: exact
-                okb = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
-                                          g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, bs.s);
-            }
-            if (!okb) {
-                verified = false;
-                g.warm[b] = (g.warm[b] >= n / 4) ? n : g.warm[b] * 4;
-            }
+        bs.unverified = 0;
+        if (bs.done) { a.s_log_out[j] = bs.adam.s_log; a.last_loss_out[j] = bs.adam.prev; a.iters_out[j] = 0; return; }
+        P dsdlog;
+        bs.s = adam_current_s(bs.adam, a.lo, a.hi, &dsdlog);
+        bs.dsdlog = dsdlog;
+        return;
+    }
+    if (bs.done) return;      // uniform across the CTA (written by thread 0 of an earlier launch)
+    const P sval = bs.s;
+    bool verified = true;
+    for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
+        const int b = a.members[mi];
+        const int warm = g.warm[b];
+        bool okb = true;
+        for (int r = 1 + tid; r < g.nruns; r += ADAM_RUNS_NT) {
+            const int t0 = r * g.run_len;
+            if (t0 >= n || t0 - warm <= 0) continue;   // past the end / started at frame 0: exact
+            okb = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
+                                      g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, sval, g.tol) && okb;
         }
-        const bool last_slot = (g.final_slot == g.total_slots - 1);
-        if (!verified && !last_slot) {
-            bs.redo += 1;  // same s again with longer warm-ups; no Adam step on an unverified loss
-        } else {
-            P loss = P(0), grad = P(0);
-            for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
-                const int b = a.members[mi];
-                double v = 0, dv = 0, bad = 0;
-                for (int r = 0; r < g.nruns; ++r) {
-                    const double* p = g.part + ((long long)b * g.nruns + r) * 3;
-                    v += p[0]; dv += p[1]; bad += p[2];
-                }
-                P vv = (P)v, gg = (P)dv;
-                if (bad > 0 || !isfinite(v) || !isfinite((double)vv)) { vv = P(1e12); gg = P(0); }  // core.py:650
-                loss += vv;
-                grad += gg * bs.dsdlog;
-            }
-            if (a.trace && bs.adam.iters < a.trace_cap) {
-                P* tr = a.trace + ((long long)j * a.trace_cap + bs.adam.iters) * 3;
-                tr[0] = bs.adam.s_log; tr[1] = loss; tr[2] = grad * a.lr;
-            }
-            adam_step(bs.adam, loss, grad, a.lr, a.tol, a.cap);
-            if (last_slot) bs.adam.done = true;
-            if (bs.adam.done) {
-                bs.done = 1;
-                a.s_log_out[j] = bs.adam.s_log;
-                a.last_loss_out[j] = bs.adam.prev;
-                a.iters_out[j] = bs.adam.iters;
-                return;
+        okb = __syncthreads_and(okb);
+        if (!okb) {
+            if (sizeof(P) == 4 && warm >= RUNS_WMAX32) {
+                if (tid == 0) bs.unverified += 1;
+            } else {
+                verified = false;
+                if (tid == 0) g.warm[b] = (warm >= n / 4) ? n : warm * 4;
             }
         }
     }
-    if (bs.done) {
-        a.s_log_out[j] = bs.adam.s_log; a.last_loss_out[j] = bs.adam.prev; a.iters_out[j] = 0;
+    const bool last_slot = (g.final_slot == g.total_slots - 1);
+    if (!verified && !last_slot) {
+        if (tid == 0) bs.redo += 1;   // same s again with longer warm-ups; no Adam step on an unverified loss
+        return;
+    }
+    P loss = P(0), grad = P(0);
+    for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
+        const int b = a.members[mi];
+        double v = 0, dv = 0, bad = 0;
+        for (int r = tid; r < g.nruns; r += ADAM_RUNS_NT) {
+            const double* p = g.part + ((long long)b * g.nruns + r) * 3;
+            v += p[0]; dv += p[1]; bad += p[2];
+        }
+        v = block_sum(v, scratch);
+        dv = block_sum(dv, scratch);
+        bad = block_sum(bad, scratch);
+        P vv = (P)v, gg = (P)dv;
+        if (bad > 0 || !isfinite(v) || !isfinite((double)vv)) { vv = P(1e12); gg = P(0); }  // core.py:650
+        loss += vv;
+        grad += gg * bs.dsdlog;
+    }
+    if (tid != 0) return;
+    if (a.trace && bs.adam.iters < a.trace_cap) {
+        P* tr = a.trace + ((long long)j * a.trace_cap + bs.adam.iters) * 3;
+        tr[0] = bs.adam.s_log; tr[1] = loss; tr[2] = grad * a.lr;
+    }
+    adam_step(bs.adam, loss, grad, a.lr, a.tol, a.cap);
+    if (last_slot) bs.adam.done = true;
+    if (bs.adam.done) {
+        bs.done = 1;
+        a.s_log_out[j] = bs.adam.s_log;
+        a.last_loss_out[j] = bs.adam.prev;
+        a.iters_out[j] = bs.adam.iters;
         return;
     }
     P dsdlog;
@@ -201,10 +228,12 @@ __global__ void gen_runs_init_kernel(int B, int n_blocks, const int* __restrict_
 }
 
 static int runs_geometry(int n, int B, int& run_len) {
-    // enough runs for ~16k threads, runs of at least 256 frames (warm-up of 64 stays below 25%)
-    int nruns = (16384 + B - 1) / B;
+    // The per-run work is a latency-bound sequential recursion, so the runs are made as short as the 64-frame
+    // warm-up makes sensible (run_len >= 64: at most 2x the frames) until ~96k threads are in flight; beyond
+    // that the runs grow and the warm-up overhead shrinks.
+    int nruns = (98304 + B - 1) / B;
     run_len = (n + nruns - 1) / nruns;
-    if (run_len < 256) run_len = 256;
+    if (run_len < 64) run_len = 64;
     run_len = (run_len + 31) / 32 * 32;
     return (n + run_len - 1) / run_len;
 }
@@ -228,11 +257,19 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
     const int slots = a.cap + RUNS_EXTRA;
     g.total_slots = slots;
     g.final_slot = -1;
-    gen_adam_runs_kernel<P><<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a, g, 1);
+    gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 1);
     for (int it = 0; it < slots; ++it) {
         g.final_slot = it;
         gen_nll_runs_kernel<P, DC, OC, FIXED, NL><<<(nthreads + 31) / 32, 32, 0, st>>>(a, g);
-        gen_adam_runs_kernel<P><<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a, g, 0);
+        gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 0);
+    }
+    if (getenv("EKS_DEBUG_RUNS")) {
+        cudaStreamSynchronize(st);
+        std::vector<int> w(a.B);
+        cudaMemcpy(w.data(), g.warm, a.B * sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[eks runs] optimiser: run_len %d nruns %d tol %g warm", g.run_len, g.nruns, (double)g.tol);
+        for (int b = 0; b < a.B && b < 16; ++b) fprintf(stderr, " %d", w[b]);
+        fprintf(stderr, "\n");
     }
     return check_launch("generic run-parallel optimise kernels");
 }
@@ -241,6 +278,7 @@ template <class P>
 int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     static_assert(sizeof(RunBlockState<P>) <= 128, "workspace bound");
     RunArgs<P> g;
+    g.tol = runs_tol_host<P>();
     const int n = a.sp.total;
     g.nruns = runs_geometry(n, a.B, g.run_len);
     g.ns = 2 * (a.D + a.D * a.D);
@@ -287,6 +325,7 @@ struct SmoothRunArgs {
     P* bnd_f_end;    // [B][nruns][nm] filter state after the run's last frame
     P* bnd_b;        // [B][nruns][nm] this run's estimate of the smoothed moments at frame t1 (next run's first)
     int* flag;       // [2]: forward / backward mismatch
+    P tol;
 };
 
 template <class P, int DC, int OC, bool FIXED, bool NL>
@@ -376,8 +415,7 @@ __global__ void __launch_bounds__(32) gen_rts_runs_kernel(const __grid_constant_
 }
 
 template <class P>
-__device__ inline bool moments_agree(const P* x, const P* y, int D) {
-    const P tol = runs_tol<P>();
+__device__ inline bool moments_agree(const P* x, const P* y, int D, P tol) {
     bool ok = true;
     for (int i = 0; i < D; ++i) {
         const P sd = sqrt_(fabs(x[D + i * D + i]) + P(1e-30));
@@ -405,13 +443,13 @@ __global__ void gen_smooth_check_kernel(const __grid_constant__ GArgs<P> a, cons
     if (which == 0) {
         if (r > 0 && t0 - g.warm > 0)
             ok = moments_agree<P>(g.bnd_f_end + ((long long)b * g.nruns + r - 1) * g.nm,
-                                  g.bnd_f_start + ((long long)b * g.nruns + r) * g.nm, D);
+                                  g.bnd_f_start + ((long long)b * g.nruns + r) * g.nm, D, g.tol);
     } else {
         if (t1 < T && t1 - 1 + g.warm < T - 1) {
             P y[EKS_MAX_STATE + EKS_MAX_STATE * EKS_MAX_STATE];
             for (int q = 0; q < D; ++q) y[q] = a.ms[((long long)b * T + t1) * D + q];
             for (int q = 0; q < D * D; ++q) y[D + q] = a.Vs[((long long)b * T + t1) * D * D + q];
-            ok = moments_agree<P>(y, g.bnd_b + ((long long)b * g.nruns + r) * g.nm, D);
+            ok = moments_agree<P>(y, g.bnd_b + ((long long)b * g.nruns + r) * g.nm, D, g.tol);
         }
     }
     if (!ok) atomicExch(g.flag + which, 1);
@@ -436,8 +474,11 @@ static int runs_smooth_launch(const GArgs<P>& a, SmoothRunArgs<P> g, cudaStream_
             set_error("generic run-parallel smoother: %s", cudaGetErrorString(e));
             return (int)e;
         }
+        if (getenv("EKS_DEBUG_RUNS"))
+            fprintf(stderr, "[eks runs] smoother attempt %d: warm %d run_len %d nruns %d flags %d %d\n", attempt, g.warm,
+                    g.run_len, g.nruns, h_flag[0], h_flag[1]);
         if (!h_flag[0] && !h_flag[1]) return 0;
-        if (g.warm >= a.T) break;  // already exact: nothing more to escalate
+        if (g.warm >= a.T || (sizeof(P) == 4 && g.warm >= RUNS_WMAX32)) break;  // exact / fp32 rounding floor  // already exact: nothing more to escalate
         g.warm = (g.warm >= a.T / 4) ? a.T : g.warm * 4;
     }
     return check_launch("generic run-parallel smoother kernels");
@@ -448,6 +489,7 @@ int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st) {
     SmoothRunArgs<P> g;
     g.nruns = runs_geometry(a.T, a.B, g.run_len);
     g.warm = RUNS_W0;
+    g.tol = runs_tol_host<P>();
     g.nm = a.D + a.D * a.D;
     // boundary records live behind the filtered moments in the caller's workspace (sized by
     // eks_filter_smooth_workspace_bytes)
@@ -493,7 +535,7 @@ struct PupilArgs {
     const P *m0, *S0, *C, *var3;    // [B][3], [B][3][3], [B][8][3], [B][3]
     PlaneView y, var;
     const P* ymean;                 // [B][8] or null
-    P lr, tol;
+    P lr, tol, btol;
     int cap;
     int run_len, nruns, slot, total_slots;
     PupilState<P>* st;              // [B]
@@ -602,9 +644,10 @@ __global__ void __launch_bounds__(32) pupil_adam_kernel(const __grid_constant__ 
         if (t0 >= n || t0 - warm <= 0) continue;
         for (int k = 0; k < 2; ++k)
             verified = runs_boundary_ok<P>(a.bnd_end + (((long long)b * a.nruns + r - 1) * 2 + k) * 24,
-                                           a.bnd_start + (((long long)b * a.nruns + r) * 2 + k) * 24, 3, P(1)) && verified;
+                                           a.bnd_start + (((long long)b * a.nruns + r) * 2 + k) * 24, 3, P(1), a.btol) && verified;
     }
     verified = __all_sync(0xffffffffu, verified);
+    if (sizeof(P) == 4 && warm >= RUNS_WMAX32) verified = true;   // fp32 rounding floor
     const bool last_slot = (a.slot == a.total_slots - 1);
     if (!verified && !last_slot) {
         if (lane == 0) {
@@ -683,6 +726,7 @@ template <class P>
 int pupil_optimize_run(PupilArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     static_assert(sizeof(PupilState<P>) <= 256, "workspace bound");
     a.nruns = pupil_geometry(a.n, a.B, a.run_len);
+    a.btol = runs_tol_host<P>();
     const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
     EKS_REQUIRE(workspace && workspace_bytes >= pupil_optimize_workspace_bytes(dtype, a.B, a.T),
                 "pupil_optimize: workspace too small");

@@ -185,7 +185,7 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
     # decoupled path: block-table + Adam-init kernels, then one NLL launch per allowed evaluation (launches of
     # already converged blocks exit immediately); generic path: one persistent kernel
     diag = structure == STRUCT_DIAG and D == 2 and O == 2 and model.ncam == 0 and n <= 1
-    runs = (not diag) and T >= 4096     # verified run-parallel generic path: (NLL + Adam) per evaluation slot
+    runs = (not diag) and T >= 512     # verified run-parallel generic path: (NLL + Adam) per evaluation slot
     _count(2 + int(safety_cap) if diag else (2 + 2 * (int(safety_cap) + 12) if runs else 1))
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
@@ -203,7 +203,7 @@ def filter_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.T
                                   ptr(model.Q), ptr(model.C), model.ncam, ptr(model.cams), ptr(y.base),
                                   y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base), var.seq_stride, ptr(vo),
                                   ptr(s), ptr(ms), ptr(Vs), ptr(ws), nbytes, stream_ptr()), 'eks_filter_smooth')
-    _count(4 if T >= 4096 else 1)
+    _count(4 if T >= 512 else 1)
     return ms, Vs
 
 

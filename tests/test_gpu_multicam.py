@@ -145,9 +145,9 @@ def _linear_case(K, T, seed, r_scale=1.0, q_scale=1.0):
             np.tile(W, (K, 1, 1)), np.tile(Q, (K, 1, 1)), ev)
 
 
-@pytest.mark.parametrize('T', [4096, 13001])
+@pytest.mark.parametrize('T', [512, 777, 4096, 13001])
 def test_run_parallel_generic_linear_matches_oracle(T):
-    """T >= 4096 switches the generic path to verified run-parallel execution (generic_runs.cu): results must
+    """T >= 512 switches the generic path to verified run-parallel execution (generic_runs.cu): results must
     equal the sequential oracle -- identical Adam iteration counts in fp64."""
     import eks_b200
     from oracle import oracle
