@@ -55,6 +55,13 @@ _SIGS = {
                                   c_void_p]),
 }
 _OPTIONAL_SIGS = {
+    'eks_mc_prestage_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'eks_mc_center': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,
+                              c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'eks_mc_pca_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
+    'eks_mc_latent_init': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'eks_pupil_optimize_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'eks_pupil_optimize': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                    c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int, c_void_p, c_void_p,

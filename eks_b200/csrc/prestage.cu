@@ -144,9 +144,18 @@ __global__ void __launch_bounds__(256) select_hist_kernel(PlaneView var, int O, 
     }
 }
 
+// numpy's virtual index of the 'linear' percentile method, evaluated in the array's precision exactly as
+// numpy does for floating-point input and a Python-float q: (n - 1) * (q / 100), both operations in P
+// (numpy/lib/_function_base_impl.py: percentile -> true_divide(q, dtype(100)); _QuantileMethods['linear'])
+template <class P>
+__device__ inline P virtual_index(int n, double q) {
+    return (P)(n - 1) * ((P)q / P(100));
+}
+
 template <class P>
 __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* __restrict__ state,
                                                           int* __restrict__ hist, double floor_lo, double floor_hi,
+                                                          double q /* percent; < 0: nanmedian */,
                                                           P* __restrict__ out) {
     using KT = KeyT<P>;
     using key_t = typename KT::type;
@@ -166,8 +175,16 @@ __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* _
             int n = 0;
             for (int i = 0; i < NBINS; ++i) n += sh[0][i];
             st.n_valid = n;
-            st.rank[0] = (n - 1) / 2;
-            st.rank[1] = n / 2;
+            if (q < 0) {
+                st.rank[0] = (n - 1) / 2;
+                st.rank[1] = n / 2;
+            } else {  // np.percentile, method 'linear': virtual index (n - 1) q / 100 between two order statistics
+                const P pos = virtual_index<P>(n, q);
+                const int lo = (int)floor((double)pos);
+                if (pos >= (P)(n - 1)) st.rank[0] = st.rank[1] = n - 1;       // _get_indexes: above bounds
+                else if (pos < P(0)) st.rank[0] = st.rank[1] = 0;
+                else { st.rank[0] = lo; st.rank[1] = lo + 1; }
+            }
             st.prefix[0] = st.prefix[1] = 0;
         } else {
             same = (st.prefix[0] == st.prefix[1]);
@@ -190,10 +207,17 @@ __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* _
             if (st.n_valid == 0) med = P(nan(""));
             else {
                 const P a = KT::unkey((key_t)st.prefix[0]), c = KT::unkey((key_t)st.prefix[1]);
-                med = (a + c) * P(0.5);
-                // floors: build_R_from_vars clip (1e-12) then min_R_var (np.clip keeps NaN)
-                med = (P)fmax((double)med, floor_lo);
-                med = (P)fmax((double)med, floor_hi);
+                if (q < 0) {
+                    med = (a + c) * P(0.5);
+                    // floors: build_R_from_vars clip (1e-12) then min_R_var (np.clip keeps NaN)
+                    med = (P)fmax((double)med, floor_lo);
+                    med = (P)fmax((double)med, floor_hi);
+                } else {  // numpy _lerp(a, c, gamma) in the array's precision
+                    const P pos = virtual_index<P>(st.n_valid, q);
+                    const P g = pos - (P)floor((double)pos);
+                    const P d = c - a;
+                    med = (g >= P(0.5)) ? c - d * (P(1) - g) : a + d * g;
+                }
             }
             out[prob] = med;
         }
@@ -202,7 +226,7 @@ __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* _
 
 template <class P>
 int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total, double min_var, P* out,
-                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                void* workspace, size_t workspace_bytes, cudaStream_t st, double q = -1.0) {
     const int nprob = B * O;
     const size_t need = (size_t)nprob * (sizeof(SelState) + 2 * NBINS * sizeof(int));
     EKS_REQUIRE(workspace && workspace_bytes >= need, "const_R_median: workspace too small (%zu < %zu)",
@@ -213,9 +237,413 @@ int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total
     const int nchunks = (n_total + SEL_CHUNK - 1) / SEL_CHUNK;
     for (int level = 0; level < KeyT<P>::nlevels; ++level) {
         select_hist_kernel<P><<<dim3(nchunks, nprob), 256, 0, st>>>(var, O, sp, n_total, level, state, hist);
-        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, 1e-12, min_var, out);
+        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, 1e-12, min_var, q, out);
     }
     return check_launch("select kernels");
+}
+
+
+// ====================================================================================================
+// Multi-camera pre-stage: centring (eks/utils.py:293-365), the data passes of the per-keypoint
+// PCA fit (eks/stats.py:9-64 -> sklearn PCA: mean + covariance of the variance-filtered frames; the tiny
+// eigen-decomposition stays on the host) and the latent-space initialisation (eks/multicam_smoother.py:554-597).
+// A "problem" b = (session, keypoint) owns O = 2 * cameras channel planes.  All sums are fp64, reduced in a fixed
+// order (per-chunk partials, then one warp per problem), so results are run-to-run deterministic.
+// ====================================================================================================
+constexpr int MC_CHUNK = 1024;
+constexpr int MC_NT = 256;
+constexpr int MC_SUB = MC_CHUNK / MC_NT;
+
+struct McWork {
+    void* maxvar;      // [B][T]   max over channels of the ensemble variance
+    void* thr;         // [B]      percentile threshold
+    int* cnt;          // [B][nchunk] good frames per chunk
+    int* last;         // [B][nchunk] last good frame of the chunk (-1: none)
+    int* pre;          // [B][nchunk] good frames before the chunk
+    int* lastbefore;   // [B][nchunk] last good frame before the chunk (-1: none)
+    int* ngood;        // [B]
+    int* minf;         // [B] min over the session's keypoints of ngood
+    double* part;      // [B][nchunk][MC_PART_MAX]
+    void* sel;         // radix-select state + histograms for B problems
+    int nchunk;
+};
+constexpr int MC_PART_MAX = MAX_CHAN + MAX_CHAN * (MAX_CHAN + 1) / 2;   // 152 >= 2 + 3 L + L (L + 1) / 2
+
+static size_t mc_align(size_t x) { return (x + 255) / 256 * 256; }
+
+static size_t mc_carve(int dtype, int B, int T, void* workspace, McWork* w) {
+    const size_t real = dtype == EKS_F32 ? 4 : 8;
+    const int nchunk = (T + MC_CHUNK - 1) / MC_CHUNK;
+    unsigned char* p = (unsigned char*)workspace;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* q = p ? p + off : nullptr; off += mc_align(bytes); return q; };
+    void* maxvar = take((size_t)B * T * real);
+    void* thr = take((size_t)B * real);
+    int* cnt = (int*)take((size_t)B * nchunk * 4);
+    int* last = (int*)take((size_t)B * nchunk * 4);
+    int* pre = (int*)take((size_t)B * nchunk * 4);
+    int* lastbefore = (int*)take((size_t)B * nchunk * 4);
+    int* ngood = (int*)take((size_t)B * 4);
+    int* minf = (int*)take((size_t)B * 4);
+    double* part = (double*)take((size_t)B * nchunk * MC_PART_MAX * 8);
+    void* sel = take((size_t)B * (sizeof(SelState) + 2 * NBINS * sizeof(int)));
+    if (w) *w = McWork{maxvar, thr, cnt, last, pre, lastbefore, ngood, minf, part, sel, nchunk};
+    return off;
+}
+
+__device__ inline int block_sum_int(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int r = 0;
+    for (int i = 0; i < nwarp; ++i) r += scratch[i];
+    return r;
+}
+__device__ inline int block_max_int(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = __reduce_max_sync(0xffffffffu, v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (int i = 1; i < nwarp; ++i) r = max(r, scratch[i]);
+    return r;
+}
+
+template <class P>
+__global__ void __launch_bounds__(MC_NT) mc_maxvar_kernel(PlaneView var, int O, int T, P* __restrict__ mv) {
+    const int b = blockIdx.y;
+    const P* base = reinterpret_cast<const P*>(var.base) + (long long)b * var.seq_stride;
+    const int t1 = min(T, (int)(blockIdx.x + 1) * MC_CHUNK);
+    for (int t = blockIdx.x * MC_CHUNK + threadIdx.x; t < t1; t += MC_NT) {
+        P m = base[var.chan_off[0] + t];
+        for (int o = 1; o < O; ++o) {
+            const P v = base[var.chan_off[o] + t];
+            m = (v > m || isnan(v)) ? v : m;      // np.max: NaN propagates
+        }
+        mv[(long long)b * T + t] = m;
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(MC_NT) mc_count_kernel(const P* __restrict__ mv, const P* __restrict__ thr, int T,
+                                                        int nchunk, int* __restrict__ cnt, int* __restrict__ last) {
+    __shared__ int scratch[32];
+    const int b = blockIdx.y, c = blockIdx.x;
+    const P th = thr[b];
+    const int t1 = min(T, (c + 1) * MC_CHUNK);
+    int n = 0, l = -1;
+    for (int t = c * MC_CHUNK + threadIdx.x; t < t1; t += MC_NT)
+        if (mv[(long long)b * T + t] <= th) { ++n; l = t; }
+    n = block_sum_int(n, scratch);
+    l = block_max_int(l, scratch);
+    if (threadIdx.x == 0) { cnt[(long long)b * nchunk + c] = n; last[(long long)b * nchunk + c] = l; }
+}
+
+// one CTA per session: chunk prefixes per keypoint, then the session's minimum good-frame count
+__global__ void __launch_bounds__(MC_NT) mc_scan_kernel(int K, int nchunk, const int* __restrict__ cnt,
+                                                       const int* __restrict__ last, int* __restrict__ pre,
+                                                       int* __restrict__ lastbefore, int* __restrict__ ngood,
+                                                       int* __restrict__ minf) {
+    __shared__ int ssum[MC_NT], smax[MC_NT];
+    __shared__ int carry_sum, carry_max, s_min;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_min = 0x7fffffff;
+    for (int k = 0; k < K; ++k) {
+        const long long b = (long long)s * K + k;
+        if (tid == 0) { carry_sum = 0; carry_max = -1; }
+        __syncthreads();
+        for (int base = 0; base < nchunk; base += MC_NT) {
+            const int i = base + tid;
+            const int v = i < nchunk ? cnt[b * nchunk + i] : 0;
+            const int m = i < nchunk ? last[b * nchunk + i] : -1;
+            ssum[tid] = v; smax[tid] = m;
+            __syncthreads();
+            for (int d = 1; d < MC_NT; d <<= 1) {          // inclusive Hillis-Steele scans
+                const int a = tid >= d ? ssum[tid - d] : 0;
+                const int x = tid >= d ? smax[tid - d] : -1;
+                __syncthreads();
+                ssum[tid] += a; smax[tid] = max(smax[tid], x);
+                __syncthreads();
+            }
+            if (i < nchunk) {
+                pre[b * nchunk + i] = carry_sum + ssum[tid] - v;
+                lastbefore[b * nchunk + i] = max(carry_max, tid > 0 ? smax[tid - 1] : -1);
+            }
+            __syncthreads();
+            if (tid == MC_NT - 1) { carry_sum += ssum[tid]; carry_max = max(carry_max, smax[tid]); }
+            __syncthreads();
+        }
+        if (tid == 0) { ngood[b] = carry_sum; s_min = min(s_min, carry_sum); }
+        __syncthreads();
+    }
+    if (tid < K) minf[(long long)s * K + tid] = s_min;
+    for (int k = MC_NT; k < K; k += MC_NT) if (k + tid < K) minf[(long long)s * K + k + tid] = s_min;
+}
+
+// in-chunk bookkeeping shared by the three data passes: good flag, rank among the good frames, previous good frame
+struct McSel {
+    int run_cnt, run_last;   // carried across the sub-tiles of the chunk (uniform)
+};
+template <class P>
+__device__ inline void mc_flags(const P* __restrict__ mv_b, P th, int t, int T, McSel& st, int* wcnt, int* wlast,
+                                bool& good, int& rank, int& prev) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    good = (t < T) && (mv_b[t] <= th);
+    const unsigned bal = __ballot_sync(0xffffffffu, good);
+    const unsigned lower = bal & ((1u << lane) - 1u);
+    __syncthreads();                                      // previous sub-tile's readers are done
+    if (lane == 0) { wcnt[warp] = __popc(bal); wlast[warp] = bal ? (t - lane) + (31 - __clz(bal)) : -1; }
+    __syncthreads();
+    int off = st.run_cnt, pl = st.run_last;
+    for (int w = 0; w < warp; ++w) { off += wcnt[w]; pl = max(pl, wlast[w]); }
+    rank = off + __popc(lower);
+    prev = lower ? (t - lane) + (31 - __clz(lower)) : pl;
+    int tot = 0, tl = -1;
+    for (int w = 0; w < MC_NT / 32; ++w) { tot += wcnt[w]; tl = max(tl, wlast[w]); }
+    st.run_cnt += tot;
+    st.run_last = max(st.run_last, tl);
+}
+
+// pass 1: sum of the selected frames (first minf good frames) per channel
+template <class P>
+__global__ void __launch_bounds__(MC_NT) mc_mean_kernel(PlaneView y, int O, int T, McWork w) {
+    __shared__ int wcnt[MC_NT / 32], wlast[MC_NT / 32];
+    __shared__ double scratch[32];
+    const int b = blockIdx.y, c = blockIdx.x;
+    const P* yb = reinterpret_cast<const P*>(y.base) + (long long)b * y.seq_stride;
+    const P* mv_b = reinterpret_cast<const P*>(w.maxvar) + (long long)b * T;
+    const P th = reinterpret_cast<const P*>(w.thr)[b];
+    const int minf = w.minf[b];
+    McSel st{w.pre[(long long)b * w.nchunk + c], w.lastbefore[(long long)b * w.nchunk + c]};
+    double acc[MAX_CHAN];
+    for (int o = 0; o < MAX_CHAN; ++o) acc[o] = 0;
+    for (int j = 0; j < MC_SUB; ++j) {
+        const int t = c * MC_CHUNK + j * MC_NT + threadIdx.x;
+        bool good; int rank, prev;
+        mc_flags<P>(mv_b, th, t, T, st, wcnt, wlast, good, rank, prev);
+        if (good && rank < minf)
+            for (int o = 0; o < O; ++o) acc[o] += (double)yb[y.chan_off[o] + t];
+    }
+    double* out = w.part + ((long long)b * w.nchunk + c) * MC_PART_MAX;
+    for (int o = 0; o < O; ++o) {
+        const double v = block_sum(acc[o], scratch);
+        if (threadIdx.x == 0) out[o] = v;
+    }
+}
+
+// one warp per problem: fixed-order sum of the per-chunk partials
+__device__ inline double mc_part_sum(const McWork& w, int b, int i) {
+    double v = 0;
+    for (int c = threadIdx.x & 31; c < w.nchunk; c += 32) v += w.part[((long long)b * w.nchunk + c) * MC_PART_MAX + i];
+    return warp_sum(v);
+}
+
+template <class P>
+__global__ void __launch_bounds__(32) mc_mean_final_kernel(int O, McWork w, P* __restrict__ ymean,
+                                                           int* __restrict__ n_good_out) {
+    const int b = blockIdx.x;
+    const int n = w.minf[b];
+    for (int o = 0; o < O; ++o) {
+        const double v = mc_part_sum(w, b, o);
+        if (threadIdx.x == 0) ymean[(long long)b * O + o] = (P)(v / (double)n);
+    }
+    if (threadIdx.x == 0 && n_good_out) { n_good_out[2 * b] = w.ngood[b]; n_good_out[2 * b + 1] = n; }
+}
+
+// pass 2: first and second moments of the centred selected frames (the PCA fit's data pass)
+template <class P, int OC>
+__global__ void __launch_bounds__(MC_NT) mc_cov_kernel(PlaneView y, int O, int T, const P* __restrict__ ymean, McWork w) {
+    constexpr int NACC = OC + OC * (OC + 1) / 2;
+    __shared__ int wcnt[MC_NT / 32], wlast[MC_NT / 32];
+    __shared__ double scratch[32];
+    const int b = blockIdx.y, c = blockIdx.x;
+    const P* yb = reinterpret_cast<const P*>(y.base) + (long long)b * y.seq_stride;
+    const P* mv_b = reinterpret_cast<const P*>(w.maxvar) + (long long)b * T;
+    const P th = reinterpret_cast<const P*>(w.thr)[b];
+    const int minf = w.minf[b];
+    McSel st{w.pre[(long long)b * w.nchunk + c], w.lastbefore[(long long)b * w.nchunk + c]};
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0;
+    for (int j = 0; j < MC_SUB; ++j) {
+        const int t = c * MC_CHUNK + j * MC_NT + threadIdx.x;
+        bool good; int rank, prev;
+        mc_flags<P>(mv_b, th, t, T, st, wcnt, wlast, good, rank, prev);
+        if (good && rank < minf) {
+            double x[OC];
+#pragma unroll
+            for (int o = 0; o < OC; ++o) x[o] = o < O ? (double)(yb[y.chan_off[o] + t] - ymean[(long long)b * O + o]) : 0.0;
+            int q = OC;
+#pragma unroll
+            for (int i = 0; i < OC; ++i) {
+                acc[i] += x[i];
+#pragma unroll
+                for (int k = i; k < OC; ++k) acc[q++] += x[i] * x[k];
+            }
+        }
+    }
+    double* out = w.part + ((long long)b * w.nchunk + c) * MC_PART_MAX;
+#pragma unroll 1
+    for (int i = 0; i < NACC; ++i) {
+        const double v = block_sum(acc[i], scratch);
+        if (threadIdx.x == 0) out[i] = v;
+    }
+}
+
+// moments_out [B][1 + O + O*O]: n, sum x_o, sum x_i x_j (full symmetric matrix)
+template <int OC>
+__global__ void __launch_bounds__(32) mc_cov_final_kernel(int O, McWork w, double* __restrict__ moments_out) {
+    const int b = blockIdx.x;
+    double* out = moments_out + (long long)b * (1 + O + O * O);
+    if (threadIdx.x == 0) out[0] = (double)w.minf[b];
+    for (int i = 0; i < O; ++i) {
+        const double v = mc_part_sum(w, b, i);
+        if (threadIdx.x == 0) out[1 + i] = v;
+    }
+    int q = OC;
+    for (int i = 0; i < OC; ++i)
+        for (int k = i; k < OC; ++k, ++q) {
+            if (i >= O || k >= O) continue;
+            const double v = mc_part_sum(w, b, q);
+            if (threadIdx.x == 0) { out[1 + O + i * O + k] = v; out[1 + O + k * O + i] = v; }
+        }
+}
+
+// pass 3: latent coordinates of ALL good frames: their variance and the covariance of consecutive differences
+template <class P, int LC>
+__global__ void __launch_bounds__(MC_NT) mc_latent_kernel(PlaneView y, int O, int L, int T, const P* __restrict__ ymean,
+                                                         const P* __restrict__ pca_mean, const P* __restrict__ comps,
+                                                         McWork w) {
+    constexpr int NACC = 2 + 3 * LC + LC * (LC + 1) / 2;
+    __shared__ int wcnt[MC_NT / 32], wlast[MC_NT / 32];
+    __shared__ double scratch[32];
+    __shared__ P sC[MAX_CHAN * LC], sMu[MAX_CHAN], sPm[MAX_CHAN];
+    const int b = blockIdx.y, c = blockIdx.x;
+    for (int i = threadIdx.x; i < O * LC; i += MC_NT) {
+        const int o = i / LC, l = i - o * LC;
+        sC[i] = l < L ? comps[((long long)b * O + o) * L + l] : P(0);
+    }
+    for (int i = threadIdx.x; i < O; i += MC_NT) { sMu[i] = ymean[(long long)b * O + i]; sPm[i] = pca_mean[(long long)b * O + i]; }
+    __syncthreads();
+    const P* yb = reinterpret_cast<const P*>(y.base) + (long long)b * y.seq_stride;
+    const P* mv_b = reinterpret_cast<const P*>(w.maxvar) + (long long)b * T;
+    const P th = reinterpret_cast<const P*>(w.thr)[b];
+    McSel st{w.pre[(long long)b * w.nchunk + c], w.lastbefore[(long long)b * w.nchunk + c]};
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0;
+    auto latent = [&](int t, P* z) {   // pca.transform of the centred prediction: ((y - mean) - pca.mean_) @ components^T
+#pragma unroll
+        for (int l = 0; l < LC; ++l) z[l] = P(0);
+        for (int o = 0; o < O; ++o) {
+            const P x = (yb[y.chan_off[o] + t] - sMu[o]) - sPm[o];
+#pragma unroll
+            for (int l = 0; l < LC; ++l) z[l] += x * sC[o * LC + l];
+        }
+    };
+    for (int j = 0; j < MC_SUB; ++j) {
+        const int t = c * MC_CHUNK + j * MC_NT + threadIdx.x;
+        bool good; int rank, prev;
+        mc_flags<P>(mv_b, th, t, T, st, wcnt, wlast, good, rank, prev);
+        if (good) {
+            P z[LC];
+            latent(t, z);
+            acc[0] += 1.0;
+#pragma unroll
+            for (int l = 0; l < LC; ++l) { acc[2 + l] += (double)z[l]; acc[2 + LC + l] += (double)z[l] * (double)z[l]; }
+            if (prev >= 0) {
+                P zp[LC];
+                latent(prev, zp);
+                double d[LC];
+#pragma unroll
+                for (int l = 0; l < LC; ++l) d[l] = (double)(z[l] - zp[l]);
+                acc[1] += 1.0;
+                int q = 2 + 3 * LC;
+#pragma unroll
+                for (int i = 0; i < LC; ++i) {
+                    acc[2 + 2 * LC + i] += d[i];
+#pragma unroll
+                    for (int k = i; k < LC; ++k) acc[q++] += d[i] * d[k];
+                }
+            }
+        }
+    }
+    double* out = w.part + ((long long)b * w.nchunk + c) * MC_PART_MAX;
+#pragma unroll 1
+    for (int i = 0; i < NACC; ++i) {
+        const double v = block_sum(acc[i], scratch);
+        if (threadIdx.x == 0) out[i] = v;
+    }
+}
+
+// S0 = diag(np.var(good_pcs)), Q = np.cov(diff(good_pcs).T) / max|.|  (eks/multicam_smoother.py:574-588)
+template <class P, int LC>
+__global__ void __launch_bounds__(32) mc_latent_final_kernel(int L, McWork w, P* __restrict__ S0, P* __restrict__ Q) {
+    constexpr int NACC = 2 + 3 * LC + LC * (LC + 1) / 2;
+    const int b = blockIdx.x;
+    double a[NACC];
+    for (int i = 0; i < NACC; ++i) a[i] = mc_part_sum(w, b, i);
+    if (threadIdx.x != 0) return;
+    const double n = a[0], nd = a[1];
+    P* S = S0 + (long long)b * L * L;
+    P* Qb = Q + (long long)b * L * L;
+    for (int i = 0; i < L * L; ++i) { S[i] = P(0); Qb[i] = P(0); }
+    for (int l = 0; l < L; ++l) {
+        const double mu = a[2 + l] / n;
+        S[l * L + l] = (P)(a[2 + LC + l] / n - mu * mu);
+    }
+    double cov[LC * LC], mx = 0;
+    int q = 2 + 3 * LC;
+    for (int i = 0; i < LC; ++i)
+        for (int k = i; k < LC; ++k, ++q) {
+            const double v = (a[q] - a[2 + 2 * LC + i] * a[2 + 2 * LC + k] / nd) / (nd - 1.0);
+            cov[i * LC + k] = cov[k * LC + i] = v;
+            if (i < L && k < L) mx = fmax(mx, fabs(v));
+        }
+    for (int i = 0; i < L; ++i)
+        for (int k = 0; k < L; ++k) Qb[i * L + k] = (P)(mx > 0 ? cov[i * LC + k] / mx : cov[i * LC + k]);
+}
+
+template <class P>
+static int mc_center_run(int S, int K, int O, int T, const PlaneView& y, const PlaneView& var, double q, P* ymean,
+                         int* n_good_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int B = S * K;
+    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
+    McWork w;
+    const size_t need = mc_carve(dtype, B, T, workspace, &w);
+    EKS_REQUIRE(workspace && workspace_bytes >= need, "mc_center: workspace too small (%zu < %zu)", workspace_bytes, need);
+    const dim3 grid(w.nchunk, B);
+    mc_maxvar_kernel<P><<<grid, MC_NT, 0, st>>>(var, O, T, (P*)w.maxvar);
+    PlaneView mvv;
+    mvv.base = w.maxvar; mvv.seq_stride = T;
+    for (int i = 0; i < MAX_CHAN; ++i) mvv.chan_off[i] = 0;
+    Spans sp; sp.n = 1; sp.start[0] = 0; sp.cum[0] = 0; sp.cum[1] = T;
+    const size_t sel_bytes = (size_t)B * (sizeof(SelState) + 2 * NBINS * sizeof(int));
+    if (int rc = run_const_R<P>(mvv, B, 1, sp, T, 0.0, (P*)w.thr, w.sel, sel_bytes, st, q)) return rc;
+    mc_count_kernel<P><<<grid, MC_NT, 0, st>>>((const P*)w.maxvar, (const P*)w.thr, T, w.nchunk, w.cnt, w.last);
+    mc_scan_kernel<<<S, MC_NT, 0, st>>>(K, w.nchunk, w.cnt, w.last, w.pre, w.lastbefore, w.ngood, w.minf);
+    mc_mean_kernel<P><<<grid, MC_NT, 0, st>>>(y, O, T, w);
+    mc_mean_final_kernel<P><<<B, 32, 0, st>>>(O, w, ymean, n_good_out);
+    return check_launch("multicam centring kernels");
+}
+
+template <class P, int OC>
+static int mc_cov_run(int B, int O, int T, const PlaneView& y, const P* ymean, double* moments_out, const McWork& w,
+                      cudaStream_t st) {
+    mc_cov_kernel<P, OC><<<dim3(w.nchunk, B), MC_NT, 0, st>>>(y, O, T, ymean, w);
+    mc_cov_final_kernel<OC><<<B, 32, 0, st>>>(O, w, moments_out);
+    return check_launch("multicam PCA moment kernels");
+}
+
+template <class P, int LC>
+static int mc_latent_run(int B, int O, int L, int T, const PlaneView& y, const P* ymean, const P* pca_mean,
+                         const P* comps, P* S0, P* Q, const McWork& w, cudaStream_t st) {
+    mc_latent_kernel<P, LC><<<dim3(w.nchunk, B), MC_NT, 0, st>>>(y, O, L, T, ymean, pca_mean, comps, w);
+    mc_latent_final_kernel<P, LC><<<B, 32, 0, st>>>(L, w, S0, Q);
+    return check_launch("multicam latent initialisation kernels");
 }
 
 }  // namespace eks
@@ -274,4 +702,70 @@ extern "C" int eks_const_R_median(const void* var_base, long long seq_stride, co
     if (dtype == EKS_F32)
         return run_const_R<float>(v, B, O, sp, n_total, min_var, (float*)Rconst_out, workspace, workspace_bytes, st);
     return run_const_R<double>(v, B, O, sp, n_total, min_var, (double*)Rconst_out, workspace, workspace_bytes, st);
+}
+
+
+extern "C" size_t eks_mc_prestage_workspace_bytes(int dtype, int B, int O, int T) {
+    (void)O;
+    return mc_carve(dtype, B, T, nullptr, nullptr);
+}
+
+extern "C" int eks_mc_center(int dtype, int S, int K, int O, int T, const void* y_base, long long y_seq_stride,
+                             const long long* y_chan_off, const void* var_base, long long var_seq_stride,
+                             const long long* var_chan_off, double quantile_keep, void* ymean_out, int* n_good_out,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    EKS_REQUIRE(y_base && y_chan_off && var_base && var_chan_off && ymean_out, "mc_center: null pointer");
+    EKS_REQUIRE(S >= 1 && K >= 1 && T >= 1 && O >= 1 && O <= MAX_CHAN, "mc_center: bad dims");
+    EKS_REQUIRE(quantile_keep >= 0.0 && quantile_keep <= 100.0, "Percentiles must be in the range [0, 100]");
+    const PlaneView y = make_view(y_base, y_seq_stride, y_chan_off, O);
+    const PlaneView v = make_view(var_base, var_seq_stride, var_chan_off, O);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == EKS_F32)
+        return mc_center_run<float>(S, K, O, T, y, v, quantile_keep, (float*)ymean_out, n_good_out, workspace,
+                                    workspace_bytes, st);
+    return mc_center_run<double>(S, K, O, T, y, v, quantile_keep, (double*)ymean_out, n_good_out, workspace,
+                                 workspace_bytes, st);
+}
+
+extern "C" int eks_mc_pca_moments(int dtype, int B, int O, int T, const void* y_base, long long y_seq_stride,
+                                  const long long* y_chan_off, const void* ymean, double* moments_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    EKS_REQUIRE(y_base && y_chan_off && ymean && moments_out, "mc_pca_moments: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 1 && O >= 1 && O <= MAX_CHAN, "mc_pca_moments: bad dims");
+    McWork w;
+    const size_t need = mc_carve(dtype, B, T, workspace, &w);
+    EKS_REQUIRE(workspace && workspace_bytes >= need, "mc_pca_moments: workspace too small");
+    const PlaneView y = make_view(y_base, y_seq_stride, y_chan_off, O);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EKS_MC_COV(PT)                                                                                  \
+    if (O <= 4) return mc_cov_run<PT, 4>(B, O, T, y, (const PT*)ymean, moments_out, w, st);             \
+    if (O <= 6) return mc_cov_run<PT, 6>(B, O, T, y, (const PT*)ymean, moments_out, w, st);             \
+    if (O <= 8) return mc_cov_run<PT, 8>(B, O, T, y, (const PT*)ymean, moments_out, w, st);             \
+    return mc_cov_run<PT, MAX_CHAN>(B, O, T, y, (const PT*)ymean, moments_out, w, st);
+    if (dtype == EKS_F32) { EKS_MC_COV(float) }
+    EKS_MC_COV(double)
+#undef EKS_MC_COV
+}
+
+extern "C" int eks_mc_latent_init(int dtype, int B, int O, int L, int T, const void* y_base, long long y_seq_stride,
+                                  const long long* y_chan_off, const void* ymean, const void* pca_mean,
+                                  const void* components, void* S0_out, void* Q_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    EKS_REQUIRE(y_base && y_chan_off && ymean && pca_mean && components && S0_out && Q_out,
+                "mc_latent_init: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 1 && O >= 1 && O <= MAX_CHAN && L >= 1 && L <= EKS_MAX_STATE, "mc_latent_init: bad dims");
+    McWork w;
+    const size_t need = mc_carve(dtype, B, T, workspace, &w);
+    EKS_REQUIRE(workspace && workspace_bytes >= need, "mc_latent_init: workspace too small");
+    const PlaneView y = make_view(y_base, y_seq_stride, y_chan_off, O);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EKS_MC_LAT(PT)                                                                                             \
+    if (L <= 3)                                                                                                    \
+        return mc_latent_run<PT, 3>(B, O, L, T, y, (const PT*)ymean, (const PT*)pca_mean, (const PT*)components,   \
+                                    (PT*)S0_out, (PT*)Q_out, w, st);                                               \
+    return mc_latent_run<PT, EKS_MAX_STATE>(B, O, L, T, y, (const PT*)ymean, (const PT*)pca_mean,                  \
+                                            (const PT*)components, (PT*)S0_out, (PT*)Q_out, w, st);
+    if (dtype == EKS_F32) { EKS_MC_LAT(float) }
+    EKS_MC_LAT(double)
+#undef EKS_MC_LAT
 }

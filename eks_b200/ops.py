@@ -262,3 +262,46 @@ def pupil_optimize(m0, S0, C, var3, y: PlaneView, var: PlaneView, T: int, ymean=
                                    stream_ptr()), 'eks_pupil_optimize')
     _count(1 + 2 * int(iters.max().item()))
     return dict(u=u, s=s, loss=loss, iters=iters, trace=trace)
+
+
+# ----------------------------------------------------------------------------- multi-camera pre-stage
+def mc_center(y: PlaneView, var: PlaneView, S: int, K: int, T: int, quantile_keep: float):
+    """center_predictions on the device -> (ymean (B,O), n_good (B,2) int32 [good frames, frames used], workspace)."""
+    dtype, dev = y.base.dtype, y.base.device
+    B, O = S * K, y.n_chan
+    ymean = torch.empty((B, O), dtype=dtype, device=dev)
+    n_good = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    nbytes = lib().eks_mc_prestage_workspace_bytes(dt_code(dtype), B, O, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    yo, vo = i64_host(y.chan_off), i64_host(var.chan_off)
+    check(lib().eks_mc_center(dt_code(dtype), S, K, O, T, ptr(y.base), y.seq_stride, ptr(yo), ptr(var.base),
+                              var.seq_stride, ptr(vo), float(quantile_keep), ptr(ymean), ptr(n_good), ptr(ws), nbytes,
+                              stream_ptr()), 'eks_mc_center')
+    _count(2 + (6 if dtype == torch.float32 else 12) + 4)
+    return ymean, n_good, ws
+
+
+def mc_pca_moments(y: PlaneView, ymean: torch.Tensor, T: int, ws: torch.Tensor) -> torch.Tensor:
+    """-> (B, 1 + O + O*O) float64: n, sum x, sum x x^T of the centred variance-filtered frames."""
+    B, O = ymean.shape
+    mom = torch.empty((B, 1 + O + O * O), dtype=torch.float64, device=ymean.device)
+    yo = i64_host(y.chan_off)
+    check(lib().eks_mc_pca_moments(dt_code(ymean.dtype), B, O, T, ptr(y.base), y.seq_stride, ptr(yo), ptr(ymean),
+                                   ptr(mom), ptr(ws), ws.numel(), stream_ptr()), 'eks_mc_pca_moments')
+    _count(2)
+    return mom
+
+
+def mc_latent_init(y: PlaneView, ymean: torch.Tensor, pca_mean: torch.Tensor, comps: torch.Tensor, T: int,
+                   ws: torch.Tensor):
+    """comps (B,O,L) = pca.components_.T -> (S0 (B,L,L), Q (B,L,L))."""
+    B, O, L = comps.shape
+    dtype, dev = ymean.dtype, ymean.device
+    S0 = torch.empty((B, L, L), dtype=dtype, device=dev)
+    Q = torch.empty((B, L, L), dtype=dtype, device=dev)
+    yo = i64_host(y.chan_off)
+    check(lib().eks_mc_latent_init(dt_code(dtype), B, O, L, T, ptr(y.base), y.seq_stride, ptr(yo), ptr(ymean),
+                                   ptr(pca_mean), ptr(comps), ptr(S0), ptr(Q), ptr(ws), ws.numel(), stream_ptr()),
+          'eks_mc_latent_init')
+    _count(2)
+    return S0, Q

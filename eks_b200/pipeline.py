@@ -123,3 +123,111 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
         o[:, 7, :] = Vs[:, :, 0, 0]
         o[:, 8, :] = Vs[:, :, 1, 1]
     return SinglecamResult(out, s_finals, iters, loss, ymean.view(S, K, 2))
+
+
+# ===================================================================================================
+# Multi-camera (linear PCA latent) pipeline, device resident
+# ===================================================================================================
+@dataclass
+class MulticamResult:
+    out: torch.Tensor        # (S, K, V, 9, T) planes per camera, see ops.OUT_COLS
+    ms: torch.Tensor         # (S*K, T, L) smoothed latent means
+    Vs: torch.Tensor         # (S*K, T, L, L) smoothed latent covariances
+    s_finals: torch.Tensor   # (S, K) float64
+    iters: torch.Tensor | None
+    loss: torch.Tensor | None
+    ymean: torch.Tensor      # (S*K, 2V) centring offsets
+    C: torch.Tensor          # (S*K, 2V, L) observation matrices (PCA components)
+    S0: torch.Tensor         # (S*K, L, L)
+    Q: torch.Tensor          # (S*K, L, L)
+    n_good: torch.Tensor     # (S*K, 2) int32: good frames, frames used for the PCA fit
+
+
+def pca_from_moments(mom, O: int, L: int):
+    """sklearn PCA(n_components=L).fit restated on the sufficient statistics (n, sum x, sum x x^T):
+    covariance_eigh branch of sklearn/decomposition/_pca.py::_fit_full + svd_flip(u_based_decision=False).
+    mom: (B, 1+O+O*O) float64 numpy.  Returns (pca_mean (B,O), components (B,L,O)) float64."""
+    import numpy as np
+    B = mom.shape[0]
+    means = np.empty((B, O))
+    comps = np.empty((B, L, O))
+    for b in range(B):
+        n = mom[b, 0]
+        mean = mom[b, 1:1 + O] / n
+        cov = (mom[b, 1 + O:].reshape(O, O) - n * np.outer(mean, mean)) / (n - 1.0)
+        _, vec = np.linalg.eigh(cov)
+        vt = vec[:, ::-1].T[:L].copy()
+        idx = np.argmax(np.abs(vt), axis=1)
+        sign = np.sign(vt[np.arange(L), idx])
+        sign[sign == 0] = 1.0
+        means[b], comps[b] = mean, vt * sign[:, None]
+    return means, comps
+
+
+def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, quantile_keep_pca: float = 50.0,
+                             n_latent: int = 3, avg_mode='median', var_mode='confidence_weighted_var',
+                             dtype=torch.float32, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
+                             min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None) -> MulticamResult:
+    """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551; linear model, inflate_vars=False) for S
+    sessions at once, every per-frame stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.
+
+    The only host work is the O x O eigen-decomposition per keypoint (O = 2V <= 16) on the moments the device
+    reduced -- one small device->host copy and one host->device copy of the components."""
+    import numpy as np
+    assert raw.is_cuda and raw.dim() == 6 and raw.shape[-1] == 3
+
+    def stage(name):
+        class _S:
+            def __enter__(self_):
+                if timers is not None:
+                    self_.e0 = torch.cuda.Event(enable_timing=True)
+                    self_.e0.record()
+
+            def __exit__(self_, *exc):
+                if timers is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    timers.setdefault(name, []).append((self_.e0, e1))
+        return _S()
+    raw = raw.contiguous()
+    S, M, V, T, K, _ = raw.shape
+    dev = raw.device
+    B, O, L = S * K, 2 * V, n_latent
+    if out is None:
+        out = torch.empty((S, K, V, 9, T), dtype=dtype, device=dev)
+    assert out.shape == (S, K, V, 9, T) and out.dtype == dtype and out.is_contiguous()
+    with stage('ensemble'):
+        ops.ensemble_stats(raw, out, K * V * 9 * T, 9 * T, V * 9 * T, [c * T for c in ops.ENS_TO_OUT],
+                           avg_mode=avg_mode, var_mode=var_mode)
+    yv = PlaneView(out, V * 9 * T, [v * 9 * T + (3 + j) * T for v in range(V) for j in range(2)])
+    vv = PlaneView(out, V * 9 * T, [v * 9 * T + (5 + j) * T for v in range(V) for j in range(2)])
+    with stage('center'):
+        ymean, n_good, ws = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
+    with stage('pca'):
+        mom = ops.mc_pca_moments(yv, ymean, T, ws).cpu().numpy()
+        pca_mean, comps = pca_from_moments(mom, O, L)
+        C = torch.as_tensor(np.ascontiguousarray(np.swapaxes(comps, 1, 2)), device=dev).to(dtype).contiguous()
+        pm = torch.as_tensor(pca_mean, device=dev).to(dtype).contiguous()
+    with stage('latent_init'):
+        S0, Q = ops.mc_latent_init(yv, ymean, pm, C, T, ws)
+    eye = torch.eye(L, dtype=dtype, device=dev).expand(B, L, L).contiguous()
+    model = Model(torch.zeros((B, L), dtype=dtype, device=dev), S0, eye, Q, C)
+    iters = loss = None
+    if smooth_param is not None:
+        s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)
+        s_finals = (s.expand(K) if s.dim() == 0 or s.numel() == 1 else s).expand(S, K).contiguous()
+    else:
+        with stage('initial_guess'):
+            _, s_log0 = ops.initial_guess(vv, B, T)
+        with stage('const_R_median'):
+            Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
+        with stage('optimize_s'):
+            opt = ops.optimize_s(model, yv, T, Rconst, s_log0, ymean=ymean, spans=spans, lr=lr,
+                                 s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap)
+        s_finals = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1])).view(S, K)
+        iters, loss = opt['iters'].view(S, K), opt['loss'].view(S, K)
+    with stage('filter_smooth'):
+        ms, Vs = ops.filter_smooth(model, yv, vv, T, s_finals.reshape(B).to(dtype), ymean=ymean)
+    with stage('reproject'):
+        ops.reproject(ms, Vs, V, out, V * 9 * T, 9 * T, [0, T, 7 * T, 8 * T], C=C, ymean=ymean, var=vv)
+    return MulticamResult(out, ms, Vs, s_finals, iters, loss, ymean, C, S0, Q, n_good)

@@ -160,6 +160,35 @@ int eks_pupil_optimize(int dtype, int B, int T, const void* m0, const void* S0, 
                        void* last_loss_out, int* iters_out, void* trace, int trace_cap, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Multi-camera pre-stage on the device.  A problem b = session * K + keypoint owns O = 2 * cameras
+ * channel planes of ensemble means (y view) and ensemble variances (var view).  The three calls share ONE workspace
+ * (eks_mc_prestage_workspace_bytes) and must be issued in this order on one stream:
+ *
+ * eks_mc_center: replaces center_predictions (eks/utils.py:293-365).  max over channels of the variance per frame,
+ *   threshold = np.percentile(., quantile_keep) per keypoint (numpy 'linear' method, evaluated in the working
+ *   precision exactly as numpy does), good frames = max-variance <= threshold, n = min over the session's keypoints
+ *   of the good-frame counts, ymean_out [B][O] = mean over the FIRST n good frames.  n_good_out (nullable) [B][2] =
+ *   (good frames, n).  The centred predictions themselves are never materialised: every consumer takes ymean.
+ * eks_mc_pca_moments: the data pass of sklearn PCA.fit on those n centred frames (eks/stats.py:9-64):
+ *   moments_out [B][1 + O + O*O] (double) = n, sum_t x_t, sum_t x_t x_t^T with x = y - ymean.  The O x O
+ *   eigen-decomposition (and sklearn's sign convention) is host work on these moments.
+ * eks_mc_latent_init: replaces pca.transform + initialize_kalman_filter_pca (eks/multicam_smoother.py:554-597).
+ *   z_t = ((y_t - ymean) - pca_mean) @ components for ALL good frames; S0_out [B][L][L] = diag(np.var(z)),
+ *   Q_out [B][L][L] = np.cov of the differences of consecutive good frames, divided by its largest |entry|.
+ *   components [B][O][L] (= pca.components_.T, the observation matrix C), pca_mean [B][O]. */
+size_t eks_mc_prestage_workspace_bytes(int dtype, int B, int O, int T);
+int eks_mc_center(int dtype, int S, int K, int O, int T, const void* y_base, long long y_seq_stride,
+                  const long long* y_chan_off_host, const void* var_base, long long var_seq_stride,
+                  const long long* var_chan_off_host, double quantile_keep, void* ymean_out, int* n_good_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int eks_mc_pca_moments(int dtype, int B, int O, int T, const void* y_base, long long y_seq_stride,
+                       const long long* y_chan_off_host, const void* ymean, double* moments_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int eks_mc_latent_init(int dtype, int B, int O, int L, int T, const void* y_base, long long y_seq_stride,
+                       const long long* y_chan_off_host, const void* ymean, const void* pca_mean,
+                       const void* components, void* S0_out, void* Q_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

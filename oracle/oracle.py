@@ -339,34 +339,31 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
              avg_mode='median', var_mode='confidence_weighted_var', dtype=np.float32, trace_cap=0):
     """ensemble_kalman_smoother_multicam restated (eks/multicam_smoother.py:279-551), inflate_vars=False.
 
-    raw: (M,V,T,K,3).  The one-off host pre-stage (centring, sklearn PCA, triangulation + geometric init)
-    is shared with the product's host utilities -- it is not on the hot path; the
-    hot path (ensemble, s-optimisation, filter/smoother, reprojection) is the oracle's own.
+    raw: (M,V,T,K,3).  Linear model: centring and PCA initialisation are the oracle's own restatement
+    (mc_center_predictions / mc_pca_init, NumPy + scikit-learn's PCA).  Nonlinear model: triangulation and the
+    geometric initialisation are one-off host steps shared with the product's host utilities.
     Returns dict(cam_out (V,T,K,9), out3d (T,K,2*D), s_finals, info)."""
-    from eks_b200.marker_array import MarkerArray, mA_to_stacked_array
-    from eks_b200.multicam_smoother import (initialize_kalman_filter_geometric, initialize_kalman_filter_pca,
-                                            make_projection_from_camgroup, triangulate_3d_models)
-    from eks_b200.stats import compute_pca
-    from eks_b200.utils import center_predictions
     raw = np.asarray(raw)
     M, V, T, K, _ = raw.shape
     ens = ensemble(raw, avg_mode, var_mode, dtype=dtype)                    # (V,T,K,5)
-    ema = MarkerArray(ens[None], data_fields=['x', 'y', 'var_x', 'var_y', 'likelihood'])
-    unsm, evars = ema.slice_fields('x', 'y'), ema.slice_fields('var_x', 'var_y')
-    mask, cen, good, means = center_predictions(ema, quantile_keep_pca)
+    stacked = lambda lo, hi: np.transpose(ens[..., lo:hi], (2, 1, 0, 3)).reshape(K, T, 2 * V)   # channel o = 2 v + xy
     cams = None
     if camgroup is not None:
+        # triangulation + geometric init are one-off host pre-stages shared with the product (SURVEY 8 row f3)
+        from eks_b200.marker_array import MarkerArray
+        from eks_b200.multicam_smoother import (initialize_kalman_filter_geometric, make_projection_from_camgroup,
+                                                triangulate_3d_models)
         tri = triangulate_3d_models(MarkerArray(raw, data_fields=['x', 'y', 'likelihood']), camgroup)
         m0s, S0s, As, Qs, Cs = initialize_kalman_filter_geometric(tri.mean(axis=0))
         cams = make_projection_from_camgroup(camgroup)[0].cams
-        ys = np.stack([mA_to_stacked_array(unsm, k) for k in range(K)])
+        ys = stacked(0, 2)
         D = 3
     else:
-        pcas, good_pcs = compute_pca(mask, cen, good, n_components=n_latent)
-        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_pca(good_pcs, pcas, n_latent)
-        ys = np.stack([mA_to_stacked_array(cen, k) for k in range(K)])
+        mask_o, cen_o, good_o, means_o, _ = mc_center_predictions(ens, quantile_keep_pca)
+        m0s, S0s, As, Qs, Cs = mc_pca_init(mask_o, cen_o, good_o, n_latent)
+        ys = cen_o
         D = n_latent
-    ev = np.stack([mA_to_stacked_array(evars, k) for k in range(K)])         # (K,T,2V)
+    ev = stacked(2, 4)                                                        # (K,T,2V)
     s_finals, ms, Vs, info = run_kalman_smoother(ys, m0s, S0s, As, Cs, Qs, np.swapaxes(ev, 0, 1),
                                                  s_frames=s_frames, smooth_param=smooth_param, cams=cams,
                                                  dtype=dtype, trace_cap=trace_cap)
@@ -378,7 +375,7 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
             cov = np.einsum('tij,tjk,tlk->til', J, Vs64[k], J)
         else:
             Ck = np.asarray(Cs[k], dtype=np.float64)
-            uv = ms64[k] @ Ck.T + means.array[0, :, 0, k, :].reshape(-1)[None, :]
+            uv = ms64[k] @ Ck.T + means_o[k].astype(np.float64)[None, :]
             cov = np.einsum('ij,tjk,lk->til', Ck, Vs64[k], Ck)
         for c in range(V):
             cam_out[c, :, k, 0] = uv[:, 2 * c]
@@ -399,6 +396,48 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
         out3d[:, k, 4] = Vs64[k][:, 1, 1]
         out3d[:, k, 5] = Vs64[k][:, 2, 2]
     return dict(cam_out=cam_out, out3d=out3d, s_finals=s_finals, info=info, ms=ms, Vs=Vs)
+
+
+
+# ----------------------------------------------------------------------------- multi-camera pre-stage (linear model)
+def mc_center_predictions(ens, quantile_keep_pca):
+    """center_predictions restated (eks/utils.py:293-365).  ens (V,T,K,5) [x,y,var_x,var_y,lik].
+    Returns (mask (T,K) bool, centered (K,T,2V), good_centered list of (n,2V), means (K,2V), n_used)."""
+    V, T, K, _ = ens.shape
+    max_vars = ens[..., 2:4].max(axis=(0, 3))                                  # (T,K)
+    thr = np.percentile(max_vars, quantile_keep_pca, axis=0)
+    mask = max_vars <= thr
+    good = [np.where(mask[:, k])[0] for k in range(K)]
+    n_used = min(len(g) for g in good)
+    preds = np.transpose(ens[..., 0:2], (2, 1, 0, 3)).reshape(K, T, 2 * V)      # channel o = 2 v + xy
+    means = np.empty((K, 2 * V), dtype=ens.dtype)
+    centered = np.empty_like(preds)
+    good_centered = []
+    for k in range(K):
+        gp = preds[k][good[k][:n_used]]
+        means[k] = gp.mean(axis=0)
+        centered[k] = preds[k] - means[k]
+        good_centered.append(gp - means[k])
+    return mask, centered, good_centered, means, n_used
+
+
+def mc_pca_init(mask, centered, good_centered, n_latent=3):
+    """compute_pca + initialize_kalman_filter_pca restated (eks/stats.py:9-64, eks/multicam_smoother.py:554-597)
+    with scikit-learn's PCA itself (the reference's dependency).  Returns (m0s, S0s, As, Qs, Cs)."""
+    from sklearn.decomposition import PCA
+    K = len(good_centered)
+    m0s = np.zeros((K, n_latent))
+    As = np.tile(np.eye(n_latent), (K, 1, 1))
+    S0s, Qs, Cs = [], [], []
+    for k in range(K):
+        pca = PCA(n_components=n_latent).fit(good_centered[k])
+        pcs = pca.transform(centered[k])[np.where(mask[:, k])[0]]
+        S0s.append(np.diag(pcs.var(axis=0)))
+        cov = np.atleast_2d(np.cov(np.diff(pcs, axis=0).T))
+        mx = np.abs(cov).max()
+        Qs.append(cov / mx if mx > 0 else cov)
+        Cs.append(pca.components_.T)
+    return m0s, np.stack(S0s), As, np.stack(Qs), np.stack(Cs)
 
 
 # ----------------------------------------------------------------------------- IBL pupil model

@@ -1,0 +1,132 @@
+"""GPU parity tests of the device-resident multi-camera pipeline: centring, PCA moments, latent
+initialisation and the whole linear multicam smoother against the CPU oracle (NumPy + scikit-learn PCA)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL64, RTOL32 = 1e-5, 1e-3
+
+
+def synth_multicam(M=5, V=2, K=3, T=3000, seed=0):
+    rng = np.random.default_rng(seed)
+    lat = np.cumsum(rng.normal(0, 0.3, (T, K, 3)), axis=0)
+    W = rng.standard_normal((K, 2 * V, 3))
+    truth = np.einsum('tkl,kol->tko', lat, W) + rng.uniform(50, 300, (1, K, 2 * V))
+    occ = rng.random((T, K)) < 0.05
+    sigma = np.where(occ, 4.0, 0.5)[:, :, None]
+    raw = np.empty((M, V, T, K, 3))
+    for m in range(M):
+        noisy = truth + rng.standard_normal((T, K, 2 * V)) * sigma
+        raw[m, :, :, :, :2] = noisy.reshape(T, K, V, 2).transpose(2, 0, 1, 3)
+        raw[m, :, :, :, 2] = np.where(occ[None], rng.uniform(0.1, 0.5, (V, T, K)), rng.uniform(0.9, 1.0, (V, T, K)))
+    return raw.astype(np.float32).astype(np.float64)
+
+
+def _run(raw, dtype, **kw):
+    from eks_b200.pipeline import multicam_smooth_sessions
+    t = torch.as_tensor(raw).cuda().to(dtype)
+    res = multicam_smooth_sessions(t[None], dtype=dtype, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _cam_out(res, s=0):
+    return res.out[s].permute(1, 3, 0, 2).double().cpu().numpy()     # (V,T,K,9)
+
+
+def _check(out, ref, rtol, label):
+    for c in range(9):
+        a, b = out[..., c], ref[..., c]
+        scale = np.maximum(np.abs(b), 1e-6 if c >= 5 else 1.0)
+        err = np.max(np.abs(a - b) / scale)
+        assert err <= rtol, f'{label}: column {c} rel err {err:.3e} > {rtol}'
+
+
+@pytest.mark.parametrize('V,T,q', [(2, 3000, 50.0), (3, 2500, 95.0), (2, 1024, 100.0), (4, 777, 25.0)])
+def test_prestage_matches_oracle_fp64(V, T, q):
+    from eks_b200 import ops
+    from eks_b200.pipeline import pca_from_moments
+    from oracle import oracle
+    raw = synth_multicam(V=V, T=T, seed=T)
+    M, _, _, K, _ = raw.shape
+    ens = oracle.ensemble(raw, dtype=np.float64)                         # (V,T,K,5)
+    mask, cen, good, means, n_used = oracle.mc_center_predictions(ens, q)
+    m0s, S0s, As, Qs, Cs = oracle.mc_pca_init(mask, cen, good, 3)
+    dev = torch.device('cuda')
+    planes = lambda lo: torch.as_tensor(np.ascontiguousarray(
+        np.transpose(ens[..., lo:lo + 2], (2, 0, 3, 1)).reshape(K, 2 * V, T))).to(dev)    # [K][2V][T]
+    yv = ops.PlaneView(planes(0), 2 * V * T, [o * T for o in range(2 * V)])
+    vv = ops.PlaneView(planes(2), 2 * V * T, [o * T for o in range(2 * V)])
+    ymean, n_good, ws = ops.mc_center(yv, vv, 1, K, T, q)
+    np.testing.assert_array_equal(n_good[:, 0].cpu().numpy(), mask.sum(axis=0))
+    np.testing.assert_array_equal(n_good[:, 1].cpu().numpy(), np.full(K, n_used))
+    np.testing.assert_allclose(ymean.cpu().numpy(), means, rtol=1e-12)
+    mom = ops.mc_pca_moments(yv, ymean, T, ws).cpu().numpy()
+    pm, comps = pca_from_moments(mom, 2 * V, 3)
+    np.testing.assert_allclose(np.swapaxes(comps, 1, 2), Cs, rtol=1e-7, atol=1e-9)
+    C = torch.as_tensor(np.ascontiguousarray(np.swapaxes(comps, 1, 2))).to(dev)
+    S0, Q = ops.mc_latent_init(yv, ymean, torch.as_tensor(pm).to(dev), C, T, ws)
+    np.testing.assert_allclose(S0.cpu().numpy(), S0s, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qs, rtol=1e-7, atol=1e-10)
+
+
+def test_mirror_mouse_separate_fp64_matches_golden():
+    g = load_golden('multicam_mirror_mouse_separate')
+    res = _run(g['raw'].astype(np.float64), torch.float64, quantile_keep_pca=95.0)
+    assert list(res.iters[0].cpu().numpy()) == list(g['iters_f64'])
+    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), g['s_f64'], rtol=RTOL64)
+    _check(_cam_out(res), g['cam_out_f64'], RTOL64, 'mirror-mouse-separate fp64')
+    K = res.ms.shape[0]
+    out3d = g['out3d_f64']                                                 # (T,K,6)
+    ms = res.ms.cpu().numpy()
+    Vs = res.Vs.cpu().numpy()
+    for k in range(K):
+        np.testing.assert_allclose(ms[k], out3d[:, k, :3], rtol=RTOL64, atol=1e-6 * np.abs(out3d[:, k, :3]).max())
+        for d in range(3):
+            np.testing.assert_allclose(Vs[k][:, d, d], out3d[:, k, 3 + d], rtol=RTOL64)
+
+
+def test_mirror_mouse_separate_fp32():
+    g = load_golden('multicam_mirror_mouse_separate')
+    res = _run(g['raw'], torch.float32, quantile_keep_pca=95.0)
+    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), g['s_f64'], rtol=2e-2)   # fp32 stop rule is a knife edge
+    from oracle import oracle
+    ref = oracle.multicam(g['raw'].astype(np.float64), quantile_keep_pca=95.0, dtype=np.float64,
+                          smooth_param=res.s_finals[0].cpu().numpy())
+    _check(_cam_out(res), ref['cam_out'], RTOL32, 'mirror-mouse-separate fp32')
+
+
+@pytest.mark.parametrize('V', [2, 3])
+def test_synthetic_vs_oracle_fp64(V):
+    from oracle import oracle
+    raw = synth_multicam(V=V, T=2200, seed=11 + V)
+    res = _run(raw, torch.float64, quantile_keep_pca=50.0)
+    ref = oracle.multicam(raw, quantile_keep_pca=50.0, dtype=np.float64)
+    assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
+    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=RTOL64)
+    _check(_cam_out(res), ref['cam_out'], RTOL64, f'synthetic V={V}')
+
+
+def test_sessions_batch_equals_single():
+    from eks_b200.pipeline import multicam_smooth_sessions
+    raws = [synth_multicam(T=1500, seed=s) for s in (1, 2)]
+    both = multicam_smooth_sessions(torch.as_tensor(np.stack(raws)).cuda().float())
+    for i, r in enumerate(raws):
+        one = _run(r, torch.float32)
+        torch.testing.assert_close(both.out[i], one.out[0], rtol=0, atol=0)
+        torch.testing.assert_close(both.s_finals[i], one.s_finals[0], rtol=0, atol=0)
+
+
+def test_fixed_smooth_param_and_spans():
+    from oracle import oracle
+    raw = synth_multicam(T=1800, seed=5)
+    res = _run(raw, torch.float64, smooth_param=3.0)
+    ref = oracle.multicam(raw, dtype=np.float64, smooth_param=3.0)
+    _check(_cam_out(res), ref['cam_out'], RTOL64, 'fixed s')
+    res = _run(raw, torch.float64, spans=[(100, 900), (1200, 1800)])
+    ref = oracle.multicam(raw, dtype=np.float64, s_frames=[(100, 900), (1200, None)])
+    assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
+    _check(_cam_out(res), ref['cam_out'], RTOL64, 's_frames')
