@@ -251,6 +251,39 @@ def project_3d_covariance_to_2d(ms_k, Vs_k, h_cam: PinholeProjection, inflated_v
     return o[2], o[3]
 
 
+
+def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames, avg_mode,
+                            var_mode, n_latent) -> tuple:
+    """Linear PCA-latent model without variance inflation: every per-frame stage runs on the device
+    (eks_b200.pipeline.multicam_smooth_sessions); the host only packs the DataFrames."""
+    from eks_b200.pipeline import multicam_smooth_sessions
+    from eks_b200.utils import normalize_spans
+    dev = require_cuda()
+    dtype = core.get_precision()
+    M, V, T, K, _ = marker_array.shape
+    t0 = time.perf_counter()
+    raw = torch.as_tensor(marker_array.array).to(device=dev, dtype=dtype)
+    sp = None
+    if smooth_param is not None:
+        sp = [float(smooth_param)] * K if isinstance(smooth_param, (int, float)) else [float(x) for x in smooth_param]
+    res = multicam_smooth_sessions(raw[None], smooth_param=sp, spans=normalize_spans(T, s_frames),
+                                   quantile_keep_pca=quantile_keep_pca, n_latent=n_latent, avg_mode=avg_mode,
+                                   var_mode=var_mode, dtype=dtype)
+    out = res.out[0].permute(1, 3, 0, 2).contiguous().double().cpu().numpy()        # (V,T,K,9)
+    ms = res.ms.double().cpu().numpy()                                              # (K,T,L)
+    Vd = torch.diagonal(res.Vs, dim1=2, dim2=3).double().cpu().numpy()              # (K,T,L)
+    s_finals = res.s_finals[0].cpu().numpy()
+    logger.debug(f'[profile] device pipeline (upload, smooth, download): {time.perf_counter() - t0:.3f}s')
+    t0 = time.perf_counter()
+    pdindex = make_dlc_pandas_index(keypoint_names, labels=LABELS)
+    camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex) for c in range(V)]
+    labels_3d = ['x', 'y', 'z', 'x_posterior_var', 'y_posterior_var', 'z_posterior_var']
+    arr3d = np.concatenate([np.concatenate([ms[k][:, :3], Vd[k][:, :3]], axis=1) for k in range(K)], axis=1)
+    df_3d = pd.DataFrame(arr3d, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d))
+    logger.debug(f'[profile] packaging: {time.perf_counter() - t0:.3f}s')
+    return camera_dfs, s_finals, df_3d
+
+
 # ----------------------------------------------------------------------------- main entry point
 def ensemble_kalman_smoother_multicam(
     marker_array: MarkerArray,
@@ -275,6 +308,10 @@ def ensemble_kalman_smoother_multicam(
     dtype = core.get_precision()
     M, V, T, K, _ = marker_array.shape
     t_total = time.perf_counter()
+
+    if camgroup is None and not inflate_vars and pca_object is None:
+        return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
+                                       avg_mode, var_mode, n_latent)
 
     t0 = time.perf_counter()
     ema = ensemble(marker_array, avg_mode=avg_mode, var_mode=var_mode)
