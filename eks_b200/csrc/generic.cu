@@ -240,9 +240,9 @@ extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m
 }
 
 extern "C" size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T) {
-    (void)O;
     const size_t a1 = diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
-    const size_t a2 = T >= GEN_RUNS_MIN_FRAMES ? generic_runs_optimize_workspace_bytes(dtype, n_blocks, B, D, T) : 0;
+    const size_t a2 = T >= GEN_RUNS_MIN_FRAMES ? generic_runs_optimize_workspace_bytes(dtype, n_blocks, B, D, T) +
+                                                     linear_steady_workspace_bytes(dtype, B, D, O, T) : 0;
     return a1 > a2 ? a1 : a2;
 }
 

@@ -26,7 +26,8 @@ namespace eks {
 
 constexpr int RUNS_W0 = 64;       // initial warm-up length (frames)
 constexpr int RUNS_WMAX32 = 16384;  // fp32: beyond this warm-up a remaining boundary mismatch is rounding noise, not memory
-constexpr int RUNS_EXTRA = 12;    // extra evaluation slots for warm-up escalations (64 * 4^10 > 10^7 frames)
+constexpr int RUNS_EXTRA = 12;
+constexpr int RUNS_RED_NT = 256;   // runs per CTA of the verification / reduction kernel    // extra evaluation slots for warm-up escalations (64 * 4^10 > 10^7 frames)
 
 template <class P>
 struct RunBlockState {
@@ -50,6 +51,8 @@ struct RunArgs {
     P* bnd_end;               // [B][nruns][ns]
     int* flag;                // smoother: boundary mismatch flag
     P tol;                    // boundary agreement tolerance
+    double* part2;            // [B][nred][4]: per-256-run sums of part + boundary mismatch flag
+    int nred;                 // ceil(nruns / RUNS_RED_NT)
 };
 
 template <class P> __host__ __device__ inline P runs_tol() { return sizeof(P) == 4 ? P(1e-4) : P(1e-10); }
@@ -131,9 +134,37 @@ __device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval, P
     return ok;
 }
 
-// ---- per block: verify the run boundaries, then Adam step (or escalate the warm-up and repeat) ---------------
-// One CTA per block: threads stride over the runs of each member (boundary check, fixed-order partial sums);
-// thread 0 takes the Adam step.
+// ---- verification + reduction: one thread per run compares its start record with the previous run's end record;
+// each CTA reduces 256 runs' partial sums in a fixed order.
+template <class P>
+__global__ void __launch_bounds__(RUNS_RED_NT) gen_runs_reduce_kernel(const __grid_constant__ GArgs<P> a,
+                                                                      const __grid_constant__ RunArgs<P> g) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.y, r = blockIdx.x * RUNS_RED_NT + threadIdx.x;
+    const int blk = g.seq_block[b];
+    if (blk < 0 || g.bstate[blk].done) return;
+    const int n = a.sp.total;
+    bool ok = true;
+    double v = 0, dv = 0, bad = 0;
+    if (r < g.nruns) {
+        const int t0 = r * g.run_len;
+        if (r >= 1 && t0 < n && t0 - g.warm[b] > 0)   // runs that started at frame 0 are exact
+            ok = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
+                                     g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, g.bstate[blk].s, g.tol);
+        const double* p = g.part + ((long long)b * g.nruns + r) * 3;
+        v = p[0]; dv = p[1]; bad = p[2];
+    }
+    const int all_ok = __syncthreads_and(ok);
+    v = block_sum(v, scratch);
+    dv = block_sum(dv, scratch);
+    bad = block_sum(bad, scratch);
+    if (threadIdx.x == 0) {
+        double* o = g.part2 + ((long long)b * g.nred + blockIdx.x) * 4;
+        o[0] = v; o[1] = dv; o[2] = bad; o[3] = all_ok ? 0.0 : 1.0;
+    }
+}
+
+// ---- per block: Adam step on the verified loss (or escalate the warm-up and repeat the evaluation) ----------
 constexpr int ADAM_RUNS_NT = 128;
 
 template <class P>
@@ -156,20 +187,21 @@ __global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __gri
         return;
     }
     if (bs.done) return;      // uniform across the CTA (written by thread 0 of an earlier launch)
-    const P sval = bs.s;
     bool verified = true;
+    P loss = P(0), grad = P(0);
     for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
         const int b = a.members[mi];
         const int warm = g.warm[b];
-        bool okb = true;
-        for (int r = 1 + tid; r < g.nruns; r += ADAM_RUNS_NT) {
-            const int t0 = r * g.run_len;
-            if (t0 >= n || t0 - warm <= 0) continue;   // past the end / started at frame 0: exact
-            okb = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
-                                      g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, sval, g.tol) && okb;
+        double v = 0, dv = 0, bad = 0, mism = 0;
+        for (int c = tid; c < g.nred; c += ADAM_RUNS_NT) {
+            const double* p = g.part2 + ((long long)b * g.nred + c) * 4;
+            v += p[0]; dv += p[1]; bad += p[2]; mism += p[3];
         }
-        okb = __syncthreads_and(okb);
-        if (!okb) {
+        v = block_sum(v, scratch);
+        dv = block_sum(dv, scratch);
+        bad = block_sum(bad, scratch);
+        mism = block_sum(mism, scratch);
+        if (mism > 0) {
             if (sizeof(P) == 4 && warm >= RUNS_WMAX32) {
                 if (tid == 0) bs.unverified += 1;
             } else {
@@ -177,29 +209,17 @@ __global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __gri
                 if (tid == 0) g.warm[b] = (warm >= n / 4) ? n : warm * 4;
             }
         }
-    }
-    const bool last_slot = (g.final_slot == g.total_slots - 1);
-    if (!verified && !last_slot) {
-        if (tid == 0) bs.redo += 1;   // same s again with longer warm-ups; no Adam step on an unverified loss
-        return;
-    }
-    P loss = P(0), grad = P(0);
-    for (int mi = a.block_off[j]; mi < a.block_off[j + 1]; ++mi) {
-        const int b = a.members[mi];
-        double v = 0, dv = 0, bad = 0;
-        for (int r = tid; r < g.nruns; r += ADAM_RUNS_NT) {
-            const double* p = g.part + ((long long)b * g.nruns + r) * 3;
-            v += p[0]; dv += p[1]; bad += p[2];
-        }
-        v = block_sum(v, scratch);
-        dv = block_sum(dv, scratch);
-        bad = block_sum(bad, scratch);
         P vv = (P)v, gg = (P)dv;
         if (bad > 0 || !isfinite(v) || !isfinite((double)vv)) { vv = P(1e12); gg = P(0); }  // core.py:650
         loss += vv;
         grad += gg * bs.dsdlog;
     }
+    const bool last_slot = (g.final_slot == g.total_slots - 1);
     if (tid != 0) return;
+    if (!verified && !last_slot) {
+        bs.redo += 1;   // same s again with longer warm-ups; no Adam step on an unverified loss
+        return;
+    }
     if (a.trace && bs.adam.iters < a.trace_cap) {
         P* tr = a.trace + ((long long)j * a.trace_cap + bs.adam.iters) * 3;
         tr[0] = bs.adam.s_log; tr[1] = loss; tr[2] = grad * a.lr;
@@ -248,8 +268,10 @@ size_t generic_runs_optimize_workspace_bytes(int dtype, int n_blocks, int B, int
     bytes += 2 * ((size_t)B * sizeof(int) + 256);
     bytes += (size_t)B * nruns * 3 * sizeof(double) + 256;
     bytes += 2 * ((size_t)B * nruns * ns * w + 256);
+    bytes += (size_t)B * ((nruns + RUNS_RED_NT - 1) / RUNS_RED_NT) * 4 * sizeof(double) + 256;
     return bytes;
 }
+size_t linear_steady_workspace_bytes(int dtype, int B, int D, int O, int T);
 
 template <class P, int DC, int OC, bool FIXED, bool NL>
 static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st) {
@@ -261,6 +283,7 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
     for (int it = 0; it < slots; ++it) {
         g.final_slot = it;
         gen_nll_runs_kernel<P, DC, OC, FIXED, NL><<<(nthreads + 31) / 32, 32, 0, st>>>(a, g);
+        gen_runs_reduce_kernel<P><<<dim3(g.nred, a.B), RUNS_RED_NT, 0, st>>>(a, g);
         gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 0);
     }
     if (getenv("EKS_DEBUG_RUNS")) {
@@ -274,46 +297,6 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
     return check_launch("generic run-parallel optimise kernels");
 }
 
-template <class P>
-int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    static_assert(sizeof(RunBlockState<P>) <= 128, "workspace bound");
-    RunArgs<P> g;
-    g.tol = runs_tol_host<P>();
-    const int n = a.sp.total;
-    g.nruns = runs_geometry(n, a.B, g.run_len);
-    g.ns = 2 * (a.D + a.D * a.D);
-    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
-    EKS_REQUIRE(workspace && workspace_bytes >= generic_runs_optimize_workspace_bytes(dtype, a.n_blocks, a.B, a.D, a.T),
-                "optimize_s: workspace too small for the run-parallel generic path");
-    unsigned char* w = (unsigned char*)workspace;
-    auto take = [&](size_t bytes) { unsigned char* p = w; w += (bytes + 255) / 256 * 256; return p; };
-    g.bstate = (RunBlockState<P>*)take((size_t)a.n_blocks * 128);
-    g.warm = (int*)take((size_t)a.B * sizeof(int));
-    int* seq_block = (int*)take((size_t)a.B * sizeof(int));
-    g.seq_block = seq_block;
-    g.part = (double*)take((size_t)a.B * g.nruns * 3 * sizeof(double));
-    g.bnd_start = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
-    g.bnd_end = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
-    g.flag = nullptr;
-    cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);
-    const int nmax = a.B > a.n_blocks ? a.B : a.n_blocks;
-    gen_runs_init_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(a.B, a.n_blocks, a.block_off, a.members, seq_block,
-                                                             g.warm, RUNS_W0);
-    const int D = a.D, O = a.O;
-    if (a.ncam > 0) {
-        if (O == 4) return runs_optimize_launch<P, 3, 4, true, true>(a, g, st);
-        if (O == 6) return runs_optimize_launch<P, 3, 6, true, true>(a, g, st);
-        if (O == 8) return runs_optimize_launch<P, 3, 8, true, true>(a, g, st);
-        return runs_optimize_launch<P, 3, EKS_MAX_CHAN, false, true>(a, g, st);
-    }
-    if (D == 2 && O == 2) return runs_optimize_launch<P, 2, 2, true, false>(a, g, st);
-    if (D == 3 && O == 4) return runs_optimize_launch<P, 3, 4, true, false>(a, g, st);
-    if (D == 3 && O == 6) return runs_optimize_launch<P, 3, 6, true, false>(a, g, st);
-    if (D == 3 && O == 8) return runs_optimize_launch<P, 3, 8, true, false>(a, g, st);
-    return runs_optimize_launch<P, EKS_MAX_STATE, EKS_MAX_CHAN, false, false>(a, g, st);
-}
-template int generic_runs_optimize<float>(const GArgs<float>&, void*, size_t, cudaStream_t);
-template int generic_runs_optimize<double>(const GArgs<double>&, void*, size_t, cudaStream_t);
 
 // =====================================================================================================
 // final pass: forward filter runs, then RTS runs (right-to-left, warm-up on the right), both verified
@@ -514,6 +497,354 @@ int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st) {
 }
 template int generic_runs_smooth<float>(const GArgs<float>&, cudaStream_t);
 template int generic_runs_smooth<double>(const GArgs<double>&, cudaStream_t);
+
+// =====================================================================================================
+// Linear models with a CONSTANT observation noise (the loss path of every linear model, eks/core.py:702-709):
+// the covariance recursion is data independent, so ONE thread per sequence runs it (with its s-sensitivity) from
+// S0 until it reaches its fixed point, tabulating the per-channel gains k_g, 1/s_g (and d/ds) of the sequential
+// scalar updates for the transient frames.  The run threads then only carry the mean and its sensitivity:
+//     e_g = y_g - h_g . mu,  mu += k_g e_g  (g = 0..O-1),  mu <- A mu          (same order as ekf_step)
+// with the tabulated gains (t < n_tr) or the steady ones -- ~100 FMAs per frame instead of a full EKF step.
+// The data independent part of the NLL (sum of log s_g) is added analytically.  Warm-up, boundary verification,
+// escalation and the Adam step are those of the generic run-parallel path above.
+// =====================================================================================================
+template <class P>
+struct LinArgs {
+    int ent, ncap;          // values per table entry = O (2 D + 2); table capacity in frames
+    P* table;               // [B][ncap + 1][ent]: entries of frames 0..ncap-1, then the steady entry
+    P* pinf;                // [B][2 (D + D^2)]: boundary-record template (0, P_inf, 0, dP_inf)
+    int* ntr;               // [B] transient length
+    double* cnll;           // [B][3]: data independent NLL, its derivative, bad flag
+};
+
+// one sequential-scalar-update covariance step on the predicted covariance Pm (dual), recording the gains
+template <class P, int DC, int OC, bool FIXED>
+__device__ inline bool lin_cov_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const P* rconst, Dual<P> s,
+                                    Dual<P>* Pm, P* ent, Dual<P>& lsum) {
+    using S = Dual<P>;
+    const int D = dm.D(), O = dm.O();
+    bool ok = true;
+    lsum = S(P(0));
+#pragma unroll
+    for (int g = 0; g < OC; ++g) {
+        if (g >= O) break;
+        S h[DC], Ph[DC];
+#pragma unroll
+        for (int j = 0; j < DC; ++j) if (j < D) h[j] = S(mdl.C[g * D + j]);
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            if (i < D) {
+                S acc = S(P(0));
+#pragma unroll
+                for (int j = 0; j < DC; ++j) if (j < D) acc += Pm[i * D + j] * h[j];
+                Ph[i] = acc;
+            }
+        }
+        S si = S(rconst[g]);
+#pragma unroll
+        for (int j = 0; j < DC; ++j) if (j < D) si += h[j] * Ph[j];
+        if (!(si.v > 0) || !isfinite((double)si.v)) ok = false;
+        const S isi = S(P(1)) / si;
+        lsum += log_(si);
+        P* e = ent + g * (2 * D + 2);
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            if (i < D) {
+                const S k = Ph[i] * isi;
+                e[i] = k.v; e[D + i] = k.d;
+#pragma unroll
+                for (int j = 0; j < DC; ++j) if (j < D) Pm[i * D + j] -= k * Ph[j];
+            }
+        }
+        e[2 * D] = isi.v; e[2 * D + 1] = isi.d;
+    }
+#pragma unroll
+    for (int i = 0; i < DC; ++i)
+#pragma unroll
+        for (int j = 0; j < DC; ++j)
+            if (i < D && j < D && j > i) {
+                const S a = S(P(0.5)) * (Pm[i * D + j] + Pm[j * D + i]);
+                Pm[i * D + j] = a; Pm[j * D + i] = a;
+            }
+    S AP[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i)
+#pragma unroll
+        for (int j = 0; j < DC; ++j)
+            if (i < D && j < D) {
+                S a2 = S(P(0));
+#pragma unroll
+                for (int k = 0; k < DC; ++k) if (k < D) a2 += S(mdl.A[i * D + k]) * Pm[k * D + j];
+                AP[i * D + j] = a2;
+            }
+#pragma unroll
+    for (int i = 0; i < DC; ++i)
+#pragma unroll
+        for (int j = 0; j < DC; ++j)
+            if (i < D && j < D) {
+                S acc = S(P(0));
+#pragma unroll
+                for (int k = 0; k < DC; ++k) if (k < D) acc += AP[i * D + k] * S(mdl.A[j * D + k]);
+                Pm[i * D + j] = acc + s * S(mdl.Q[i * D + j]);
+            }
+    return ok;
+}
+
+template <class P, int DC, int OC, bool FIXED>
+__global__ void __launch_bounds__(32) lin_prep_kernel(const __grid_constant__ GArgs<P> a,
+                                                      const __grid_constant__ RunArgs<P> g,
+                                                      const __grid_constant__ LinArgs<P> l) {
+    using S = Dual<P>;
+    const int b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const int blk = g.seq_block[b];
+    if (blk < 0 || g.bstate[blk].done) return;
+    Dims<DC, OC, FIXED> dm{a.D, a.O};
+    const int D = dm.D(), O = dm.O(), n = a.sp.total;
+    SeqModel<P> mdl;
+    SeqObs<P> ob;
+    make_seq(a, b, mdl, ob, false);
+    const S s(g.bstate[blk].s, P(1));
+    S Pm[DC * DC];
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = S(mdl.S0[i]);
+    const P HALF_LOG2PI = P(0.91893853320467274178032973640562);
+    const P tol = P(8) * (sizeof(P) == 4 ? P(1.1920929e-7) : P(2.220446049250313e-16));
+    P* tab = l.table + (long long)b * (l.ncap + 1) * l.ent;
+    double c0 = 0, c1 = 0;
+    bool ok = true;
+    P prev_cv = P(INFINITY), prev_cd = P(INFINITY);
+    int stall = 0, t = 0;
+    const int cap = n < l.ncap ? n : l.ncap;
+    bool conv = false;
+    for (; t < cap && !conv; ++t) {
+        P old_v[DC * DC], old_d[DC * DC];
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) { old_v[i] = Pm[i].v; old_d[i] = Pm[i].d; }
+        S lsum;
+        ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)t * l.ent, lsum) && ok;
+        c0 += (double)(P(O) * HALF_LOG2PI) + 0.5 * (double)lsum.v;
+        c1 += 0.5 * (double)lsum.d;
+        // distance to the fixed point from the last two steps (geometric convergence), or the rounding floor
+        P cv = 0, cd = 0, sv = 0, sdv = 0;
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i)
+            if (i < D * D) {
+                cv = fmax(cv, fabs(Pm[i].v - old_v[i])); cd = fmax(cd, fabs(Pm[i].d - old_d[i]));
+                sv = fmax(sv, fabs(Pm[i].v)); sdv = fmax(sdv, fabs(Pm[i].d));
+            }
+        const P rv = fmin(cv / prev_cv, P(0.999)), rd = fmin(cd / prev_cd, P(0.999));
+        const bool cvok = (cv == P(0)) || (isfinite((double)prev_cv) && cv * rv / (P(1) - rv) <= tol * sv);
+        const bool cdok = (cd == P(0)) || (isfinite((double)prev_cd) && cd * rd / (P(1) - rd) <= tol * sdv);
+        if (cv >= prev_cv && cd >= prev_cd) ++stall;
+        conv = (cvok && cdok) || stall >= 24;
+        prev_cv = cv; prev_cd = cd;
+    }
+    const int ntr = t;
+    // steady entry from the converged predicted covariance; boundary-record template
+    P* pinf = l.pinf + (long long)b * g.ns;
+    for (int q = 0; q < D; ++q) { pinf[q] = P(0); pinf[D + D * D + q] = P(0); }
+    for (int q = 0; q < D * D; ++q) { pinf[D + q] = Pm[q].v; pinf[2 * D + D * D + q] = Pm[q].d; }
+    S lsum;
+    ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)l.ncap * l.ent, lsum) && ok;
+    const double rest = (double)(n - ntr);
+    c0 += rest * ((double)(P(O) * HALF_LOG2PI) + 0.5 * (double)lsum.v);
+    c1 += rest * 0.5 * (double)lsum.d;
+    l.ntr[b] = ntr;
+    l.cnll[3 * b] = c0; l.cnll[3 * b + 1] = c1; l.cnll[3 * b + 2] = ok ? 0.0 : 1.0;
+}
+
+template <class P, int DC, int OC, bool FIXED>
+__global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GArgs<P> a,
+                                                      const __grid_constant__ RunArgs<P> g,
+                                                      const __grid_constant__ LinArgs<P> l) {
+    constexpr int ENTC = OC * (2 * DC + 2);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * g.nruns) return;
+    const int b = idx / g.nruns, r = idx - b * g.nruns;
+    const int blk = g.seq_block[b];
+    if (blk < 0 || g.bstate[blk].done) return;
+    const int n = a.sp.total;
+    const int t0 = r * g.run_len, t1 = min(n, t0 + g.run_len);
+    double* part = g.part + ((long long)b * g.nruns + r) * 3;
+    if (t0 >= n) { part[0] = 0; part[1] = 0; part[2] = 0; return; }
+    const int start = max(0, t0 - g.warm[b]);
+    Dims<DC, OC, FIXED> dm{a.D, a.O};
+    const int D = dm.D(), O = dm.O(), ES = 2 * D + 2;
+    SeqModel<P> mdl;
+    SeqObs<P> ob;
+    make_seq(a, b, mdl, ob, false);
+    FrameMap fm{a.sp};
+    const int ntr = l.ntr[b];
+    const P* tab = l.table + (long long)b * (l.ncap + 1) * l.ent;
+    P Cm[OC * DC], Am[DC * DC];
+#pragma unroll
+    for (int i = 0; i < OC * DC; ++i) if (i < O * D) Cm[i] = mdl.C[i];
+#pragma unroll
+    for (int i = 0; i < DC * DC; ++i) if (i < D * D) Am[i] = mdl.A[i];
+    P ent[ENTC];
+    bool steady_loaded = false;
+    P mu[DC], dmu[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) if (i < D) { mu[i] = start == 0 ? mdl.m0[i] : P(0); dmu[i] = P(0); }
+    P q = P(0), dq = P(0);
+    const P* pinf = l.pinf + (long long)b * g.ns;
+    P* bs = g.bnd_start + ((long long)b * g.nruns + r) * g.ns;
+    P* be = g.bnd_end + ((long long)b * g.nruns + r) * g.ns;
+    for (int i = start; i < t1; ++i) {
+        if (i == t0) {
+            for (int k = 0; k < g.ns; ++k) bs[k] = pinf[k];
+            for (int k = 0; k < D; ++k) { bs[k] = mu[k]; bs[D + D * D + k] = dmu[k]; }
+            q = P(0); dq = P(0);
+        }
+        if (i < ntr) {
+            const P* e = tab + (long long)i * l.ent;
+#pragma unroll
+            for (int k = 0; k < ENTC; ++k) if (k < O * ES) ent[k] = e[k];
+        } else if (!steady_loaded) {
+            const P* e = tab + (long long)l.ncap * l.ent;
+#pragma unroll
+            for (int k = 0; k < ENTC; ++k) if (k < O * ES) ent[k] = e[k];
+            steady_loaded = true;
+        }
+        const long long f = fm(i);
+#pragma unroll
+        for (int c = 0; c < OC; ++c) {
+            if (c < O) {
+                P y = ob.y_base[ob.y_off[c] + f];
+                if (ob.ymean) y -= ob.ymean[c];
+                P e = y, de = P(0);
+#pragma unroll
+                for (int j = 0; j < DC; ++j) if (j < D) { e -= Cm[c * D + j] * mu[j]; de -= Cm[c * D + j] * dmu[j]; }
+                const P* en = ent + c * ES;
+                const P isi = en[2 * D], disi = en[2 * D + 1];
+                q += e * e * isi;
+                dq += P(2) * e * de * isi + e * e * disi;
+#pragma unroll
+                for (int j = 0; j < DC; ++j) if (j < D) { mu[j] += en[j] * e; dmu[j] += en[D + j] * e + en[j] * de; }
+            }
+        }
+        P nm[DC], ndm[DC];
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            if (j < D) {
+                P s1 = P(0), s2 = P(0);
+#pragma unroll
+                for (int k = 0; k < DC; ++k) if (k < D) { s1 += Am[j * D + k] * mu[k]; s2 += Am[j * D + k] * dmu[k]; }
+                nm[j] = s1; ndm[j] = s2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DC; ++j) if (j < D) { mu[j] = nm[j]; dmu[j] = ndm[j]; }
+    }
+    for (int k = 0; k < g.ns; ++k) be[k] = pinf[k];
+    for (int k = 0; k < D; ++k) { be[k] = mu[k]; be[D + D * D + k] = dmu[k]; }
+    double v = 0.5 * (double)q, dv = 0.5 * (double)dq, bad = 0;
+    if (r == 0) { v += l.cnll[3 * b]; dv += l.cnll[3 * b + 1]; bad = l.cnll[3 * b + 2]; }
+    part[0] = v; part[1] = dv; part[2] = bad;
+}
+
+static int lin_table_cap(int dtype, int B, int D, int O, int n) {
+    // transient table: at most ~256 MB, between 1024 and 16384 frames per sequence
+    const size_t ent_bytes = (size_t)O * (2 * D + 2) * (dtype == EKS_F32 ? 4 : 8);
+    long long cap = (long long)((256ull << 20) / ((size_t)B * ent_bytes));
+    if (cap > 16384) cap = 16384;
+    if (cap < 1024) cap = 1024;
+    if (cap > n) cap = n;
+    return (int)cap;
+}
+
+size_t linear_steady_workspace_bytes(int dtype, int B, int D, int O, int T) {
+    const size_t w = dtype == EKS_F32 ? 4 : 8;
+    const int cap = lin_table_cap(dtype, B, D, O, T);
+    return (size_t)B * (cap + 1) * O * (2 * D + 2) * w + 256 + (size_t)B * 2 * (D + D * D) * w + 256 +
+           (size_t)B * 4 + 256 + (size_t)B * 3 * 8 + 256;
+}
+
+template <class P, int DC, int OC, bool FIXED>
+static int lin_optimize_launch(const GArgs<P>& a, RunArgs<P> g, const LinArgs<P>& l, cudaStream_t st) {
+    const int nthreads = a.B * g.nruns;
+    const int slots = a.cap + RUNS_EXTRA;
+    g.total_slots = slots;
+    g.final_slot = -1;
+    gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 1);
+    for (int it = 0; it < slots; ++it) {
+        g.final_slot = it;
+        lin_prep_kernel<P, DC, OC, FIXED><<<a.B, 32, 0, st>>>(a, g, l);
+        lin_runs_kernel<P, DC, OC, FIXED><<<(nthreads + 63) / 64, 64, 0, st>>>(a, g, l);
+        gen_runs_reduce_kernel<P><<<dim3(g.nred, a.B), RUNS_RED_NT, 0, st>>>(a, g);
+        gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 0);
+    }
+    if (getenv("EKS_DEBUG_RUNS")) {
+        cudaStreamSynchronize(st);
+        std::vector<int> w(a.B), nt(a.B);
+        cudaMemcpy(w.data(), g.warm, a.B * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(nt.data(), l.ntr, a.B * sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[eks runs] linear steady optimiser: run_len %d nruns %d cap %d (warm, n_tr)", g.run_len, g.nruns,
+                l.ncap);
+        for (int b = 0; b < a.B && b < 16; ++b) fprintf(stderr, " (%d, %d)", w[b], nt[b]);
+        fprintf(stderr, "\n");
+    }
+    return check_launch("linear steady-state optimise kernels");
+}
+
+template <class P>
+int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    static_assert(sizeof(RunBlockState<P>) <= 128, "workspace bound");
+    RunArgs<P> g;
+    g.tol = runs_tol_host<P>();
+    const int n = a.sp.total;
+    g.nruns = runs_geometry(n, a.B, g.run_len);
+    g.ns = 2 * (a.D + a.D * a.D);
+    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
+    EKS_REQUIRE(workspace && workspace_bytes >= generic_runs_optimize_workspace_bytes(dtype, a.n_blocks, a.B, a.D, a.T) +
+                                                    (a.ncam == 0 ? linear_steady_workspace_bytes(dtype, a.B, a.D, a.O, a.T) : 0),
+                "optimize_s: workspace too small for the run-parallel generic path");
+    unsigned char* w = (unsigned char*)workspace;
+    auto take = [&](size_t bytes) { unsigned char* p = w; w += (bytes + 255) / 256 * 256; return p; };
+    g.bstate = (RunBlockState<P>*)take((size_t)a.n_blocks * 128);
+    g.warm = (int*)take((size_t)a.B * sizeof(int));
+    int* seq_block = (int*)take((size_t)a.B * sizeof(int));
+    g.seq_block = seq_block;
+    g.part = (double*)take((size_t)a.B * g.nruns * 3 * sizeof(double));
+    g.bnd_start = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
+    g.bnd_end = (P*)take((size_t)a.B * g.nruns * g.ns * sizeof(P));
+    g.nred = (g.nruns + RUNS_RED_NT - 1) / RUNS_RED_NT;
+    g.part2 = (double*)take((size_t)a.B * g.nred * 4 * sizeof(double));
+    g.flag = nullptr;
+    cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);
+    const int nmax = a.B > a.n_blocks ? a.B : a.n_blocks;
+    gen_runs_init_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(a.B, a.n_blocks, a.block_off, a.members, seq_block,
+                                                             g.warm, RUNS_W0);
+    const int D = a.D, O = a.O;
+    if (a.ncam == 0 && !getenv("EKS_NO_STEADY")) {   // linear model, constant R: steady-state mean recursion
+        LinArgs<P> l;
+        l.ent = O * (2 * D + 2);
+        l.ncap = lin_table_cap(dtype, a.B, D, O, n);
+        l.table = (P*)take((size_t)a.B * (l.ncap + 1) * l.ent * sizeof(P));
+        l.pinf = (P*)take((size_t)a.B * g.ns * sizeof(P));
+        l.ntr = (int*)take((size_t)a.B * sizeof(int));
+        l.cnll = (double*)take((size_t)a.B * 3 * sizeof(double));
+        if (D == 2 && O == 2) return lin_optimize_launch<P, 2, 2, true>(a, g, l, st);
+        if (D == 3 && O == 4) return lin_optimize_launch<P, 3, 4, true>(a, g, l, st);
+        if (D == 3 && O == 6) return lin_optimize_launch<P, 3, 6, true>(a, g, l, st);
+        if (D == 3 && O == 8) return lin_optimize_launch<P, 3, 8, true>(a, g, l, st);
+        return lin_optimize_launch<P, EKS_MAX_STATE, EKS_MAX_CHAN, false>(a, g, l, st);
+    }
+    if (a.ncam > 0) {
+        if (O == 4) return runs_optimize_launch<P, 3, 4, true, true>(a, g, st);
+        if (O == 6) return runs_optimize_launch<P, 3, 6, true, true>(a, g, st);
+        if (O == 8) return runs_optimize_launch<P, 3, 8, true, true>(a, g, st);
+        return runs_optimize_launch<P, 3, EKS_MAX_CHAN, false, true>(a, g, st);
+    }
+    if (D == 2 && O == 2) return runs_optimize_launch<P, 2, 2, true, false>(a, g, st);
+    if (D == 3 && O == 4) return runs_optimize_launch<P, 3, 4, true, false>(a, g, st);
+    if (D == 3 && O == 6) return runs_optimize_launch<P, 3, 6, true, false>(a, g, st);
+    if (D == 3 && O == 8) return runs_optimize_launch<P, 3, 8, true, false>(a, g, st);
+    return runs_optimize_launch<P, EKS_MAX_STATE, EKS_MAX_CHAN, false, false>(a, g, st);
+}
+template int generic_runs_optimize<float>(const GArgs<float>&, void*, size_t, cudaStream_t);
+template int generic_runs_optimize<double>(const GArgs<double>&, void*, size_t, cudaStream_t);
 
 // =====================================================================================================
 // IBL pupil model (eks/ibl_pupil_smoother.py:363-607): 3 states [diameter, com_x, com_y], AR(1) dynamics

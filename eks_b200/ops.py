@@ -186,7 +186,8 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
     # already converged blocks exit immediately); generic path: one persistent kernel
     diag = structure == STRUCT_DIAG and D == 2 and O == 2 and model.ncam == 0 and n <= 1
     runs = (not diag) and T >= 512     # verified run-parallel generic path: (NLL + Adam) per evaluation slot
-    _count(2 + int(safety_cap) if diag else (2 + 2 * (int(safety_cap) + 12) if runs else 1))
+    per_slot = 4 if model.ncam == 0 else 3   # (prep,) runs, verify/reduce, Adam
+    _count(2 + int(safety_cap) if diag else (2 + per_slot * (int(safety_cap) + 12) if runs else 1))
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
 
