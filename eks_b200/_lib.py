@@ -55,6 +55,12 @@ _SIGS = {
                                   c_void_p]),
 }
 _OPTIONAL_SIGS = {
+    'eks_mc_valid_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                     c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_double, c_double,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'eks_mc_inflate_step': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
+                                    c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double,
+                                    c_void_p, c_void_p, c_void_p]),
     'eks_mc_prestage_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'eks_mc_center': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,
                               c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

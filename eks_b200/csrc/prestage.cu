@@ -646,6 +646,177 @@ static int mc_latent_run(int B, int O, int L, int T, const PlaneView& y, const P
     return check_launch("multicam latent initialisation kernels");
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// Mahalanobis variance inflation (eks/stats.py:67-157 compute_mahalanobis, eks/multicam_smoother.py:653-764).
+// One iteration of the reference's while-loop is: (1) rows with max-variance < percentile (and, optionally, min
+// likelihood >= threshold) feed a FactorAnalysis fit -- the device reduces their moments, the O x O fit is host
+// work; (2) per frame: posterior B = (W^T diag(1/(v+eps)) W)^-1, reconstruction, per-view Mahalanobis distance,
+// variances of flagged views times `scalar` (in place), a flag per problem if anything was inflated.
+// The per-frame algebra runs in fp64 like the reference's NumPy code.
+// ----------------------------------------------------------------------------------------------------
+template <class P, int OC>
+__global__ void __launch_bounds__(MC_NT) mc_valid_moments_kernel(PlaneView y, PlaneView lik, int V, int O, int T,
+                                                                 const P* __restrict__ ymean, double lik_thr,
+                                                                 int use_q, const int* __restrict__ active, McWork w) {
+    constexpr int NACC = 1 + OC + OC * (OC + 1) / 2;
+    __shared__ double scratch[32];
+    const int b = blockIdx.y, c = blockIdx.x;
+    if (active && !active[b]) return;
+    const P* yb = reinterpret_cast<const P*>(y.base) + (long long)b * y.seq_stride;
+    const P* lb = lik.base ? reinterpret_cast<const P*>(lik.base) + (long long)b * lik.seq_stride : nullptr;
+    const P* mv_b = reinterpret_cast<const P*>(w.maxvar) + (long long)b * T;
+    const P th = reinterpret_cast<const P*>(w.thr)[b];
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0;
+    const int t1 = min(T, (c + 1) * MC_CHUNK);
+    for (int t = c * MC_CHUNK + threadIdx.x; t < t1; t += MC_NT) {
+        bool valid = use_q ? (mv_b[t] < th) : true;          // strict, stats.py:119
+        if (lb) {
+            P ml = lb[lik.chan_off[0] + t];
+            for (int v = 1; v < V; ++v) { const P x = lb[lik.chan_off[v] + t]; ml = (x < ml || isnan(x)) ? x : ml; }
+            valid = valid && ((double)ml >= lik_thr);
+        }
+        if (!valid) continue;
+        double x[OC];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) x[o] = o < O ? (double)(yb[y.chan_off[o] + t] - ymean[(long long)b * O + o]) : 0.0;
+        acc[0] += 1.0;
+        int q = 1 + OC;
+#pragma unroll
+        for (int i = 0; i < OC; ++i) {
+            acc[1 + i] += x[i];
+#pragma unroll
+            for (int k = i; k < OC; ++k) acc[q++] += x[i] * x[k];
+        }
+    }
+    double* out = w.part + ((long long)b * w.nchunk + c) * MC_PART_MAX;
+#pragma unroll 1
+    for (int i = 0; i < NACC; ++i) {
+        const double v = block_sum(acc[i], scratch);
+        if (threadIdx.x == 0) out[i] = v;
+    }
+}
+
+template <int OC>
+__global__ void __launch_bounds__(32) mc_valid_moments_final_kernel(int O, McWork w, const int* __restrict__ active,
+                                                                    double* __restrict__ moments_out) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    double* out = moments_out + (long long)b * (1 + O + O * O);
+    const double n = mc_part_sum(w, b, 0);
+    if (threadIdx.x == 0) out[0] = n;
+    for (int i = 0; i < O; ++i) {
+        const double v = mc_part_sum(w, b, 1 + i);
+        if (threadIdx.x == 0) out[1 + i] = v;
+    }
+    int q = 1 + OC;
+    for (int i = 0; i < OC; ++i)
+        for (int k = i; k < OC; ++k, ++q) {
+            if (i >= O || k >= O) continue;
+            const double v = mc_part_sum(w, b, q);
+            if (threadIdx.x == 0) { out[1 + O + i * O + k] = v; out[1 + O + k * O + i] = v; }
+        }
+}
+
+// in-place inverse of a symmetric positive definite L x L matrix (L <= 6) by Gauss-Jordan with no pivoting;
+// returns false if a pivot is not positive/finite
+template <int LC>
+__device__ inline bool spd_inverse(double* Mx, int L) {
+    double inv[LC * LC];
+    for (int i = 0; i < L; ++i) for (int j = 0; j < L; ++j) inv[i * L + j] = i == j ? 1.0 : 0.0;
+    for (int c = 0; c < L; ++c) {
+        const double piv = Mx[c * L + c];
+        if (!(fabs(piv) > 0) || !isfinite(piv)) return false;
+        const double ip = 1.0 / piv;
+        for (int j = 0; j < L; ++j) { Mx[c * L + j] *= ip; inv[c * L + j] *= ip; }
+        for (int i = 0; i < L; ++i) {
+            if (i == c) continue;
+            const double f = Mx[i * L + c];
+            for (int j = 0; j < L; ++j) { Mx[i * L + j] -= f * Mx[c * L + j]; inv[i * L + j] -= f * inv[c * L + j]; }
+        }
+    }
+    for (int i = 0; i < L * L; ++i) Mx[i] = inv[i];
+    return true;
+}
+
+template <class P, int OC, int LC>
+__global__ void __launch_bounds__(MC_NT) mc_inflate_kernel(PlaneView y, PlaneView var, int V, int O, int L, int T,
+                                                           const P* __restrict__ ymean, const double* __restrict__ Wm,
+                                                           const double* __restrict__ mu, double eps, double threshold,
+                                                           double scalar, const int* __restrict__ active,
+                                                           int* __restrict__ flags) {
+    __shared__ double sW[OC * LC], sMu[OC];
+    __shared__ int any_block;
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    for (int i = threadIdx.x; i < O * L; i += MC_NT) sW[i] = Wm[(long long)b * O * L + i];
+    for (int i = threadIdx.x; i < O; i += MC_NT) sMu[i] = mu[(long long)b * O + i];
+    if (threadIdx.x == 0) any_block = 0;
+    __syncthreads();
+    const P* yb = reinterpret_cast<const P*>(y.base) + (long long)b * y.seq_stride;
+    P* vb = const_cast<P*>(reinterpret_cast<const P*>(var.base)) + (long long)b * var.seq_stride;
+    bool any = false;
+    const int t1 = min(T, (int)(blockIdx.x + 1) * MC_CHUNK);
+    for (int t = blockIdx.x * MC_CHUNK + threadIdx.x; t < t1; t += MC_NT) {
+        double x[OC], v[OC], iv[OC];
+        for (int o = 0; o < O; ++o) {
+            x[o] = (double)(yb[y.chan_off[o] + t] - ymean[(long long)b * O + o]) - sMu[o];
+            v[o] = (double)vb[var.chan_off[o] + t];
+            iv[o] = 1.0 / (v[o] + eps);
+        }
+        double Bm[LC * LC], rhs[LC];
+        for (int i = 0; i < L; ++i) {
+            double r = 0;
+            for (int o = 0; o < O; ++o) r += sW[o * L + i] * iv[o] * x[o];
+            rhs[i] = r;
+            for (int j = 0; j < L; ++j) {
+                double a2 = 0;
+                for (int o = 0; o < O; ++o) a2 += sW[o * L + i] * iv[o] * sW[o * L + j];
+                Bm[i * L + j] = a2;
+            }
+        }
+        const bool okB = spd_inverse<LC>(Bm, L);
+        double z[LC];
+        for (int i = 0; i < L; ++i) { double r = 0; for (int j = 0; j < L; ++j) r += Bm[i * L + j] * rhs[j]; z[i] = r; }
+        bool flag[OC / 2];
+        bool anyv = false;
+        for (int c = 0; c < V; ++c) {
+            double d[2], WB[2][LC], Q[2][2];
+            for (int a2 = 0; a2 < 2; ++a2) {
+                const int o = 2 * c + a2;
+                double xh = 0;
+                for (int i = 0; i < L; ++i) xh += sW[o * L + i] * z[i];
+                d[a2] = x[o] - xh;
+                for (int j = 0; j < L; ++j) { double r = 0; for (int i = 0; i < L; ++i) r += sW[o * L + i] * Bm[i * L + j]; WB[a2][j] = r; }
+            }
+            for (int a2 = 0; a2 < 2; ++a2)
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    double r = 0;
+                    for (int j = 0; j < L; ++j) r += WB[a2][j] * sW[(2 * c + e2) * L + j];
+                    Q[a2][e2] = r + (a2 == e2 ? v[2 * c + a2] : 0.0);
+                }
+            const double det = Q[0][0] * Q[1][1] - Q[0][1] * Q[1][0];
+            const double m = (d[0] * (Q[1][1] * d[0] - Q[0][1] * d[1]) + d[1] * (Q[0][0] * d[1] - Q[1][0] * d[0])) / det;
+            flag[c] = okB && (m > threshold);        // NaN compares false, like numpy
+            anyv = anyv || flag[c];
+        }
+        if (V == 2 && anyv) { flag[0] = true; flag[1] = true; }     // multicam_smoother.py:755-757
+        if (anyv) {
+            any = true;
+            for (int c = 0; c < V; ++c)
+                if (flag[c]) {
+                    vb[var.chan_off[2 * c] + t] = (P)((double)vb[var.chan_off[2 * c] + t] * scalar);
+                    vb[var.chan_off[2 * c + 1] + t] = (P)((double)vb[var.chan_off[2 * c + 1] + t] * scalar);
+                }
+        }
+    }
+    if (any) any_block = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && any_block) atomicExch(flags + b, 1);
+}
+
 }  // namespace eks
 
 using namespace eks;
@@ -768,4 +939,76 @@ extern "C" int eks_mc_latent_init(int dtype, int B, int O, int L, int T, const v
     if (dtype == EKS_F32) { EKS_MC_LAT(float) }
     EKS_MC_LAT(double)
 #undef EKS_MC_LAT
+}
+
+
+extern "C" int eks_mc_valid_moments(int dtype, int B, int V, int T, const void* y_base, long long y_seq_stride,
+                                    const long long* y_chan_off, const void* ymean, const void* var_base,
+                                    long long var_seq_stride, const long long* var_chan_off, const void* lik_base,
+                                    long long lik_seq_stride, const long long* lik_chan_off, double lik_threshold,
+                                    double v_quantile, const int* active, double* moments_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    const int O = 2 * V;
+    EKS_REQUIRE(y_base && y_chan_off && ymean && var_base && var_chan_off && moments_out, "mc_valid_moments: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 1 && V >= 1 && O <= MAX_CHAN, "mc_valid_moments: bad dims");
+    McWork w;
+    const size_t need = mc_carve(dtype, B, T, workspace, &w);
+    EKS_REQUIRE(workspace && workspace_bytes >= need, "mc_valid_moments: workspace too small");
+    const PlaneView y = make_view(y_base, y_seq_stride, y_chan_off, O);
+    const PlaneView var = make_view(var_base, var_seq_stride, var_chan_off, O);
+    PlaneView lik;
+    lik.base = nullptr; lik.seq_stride = 0;
+    if (lik_base) lik = make_view(lik_base, lik_seq_stride, lik_chan_off, V);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(w.nchunk, B);
+    const int use_q = v_quantile >= 0.0;
+    const size_t sel_bytes = (size_t)B * (sizeof(SelState) + 2 * NBINS * sizeof(int));
+    Spans sp; sp.n = 1; sp.start[0] = 0; sp.cum[0] = 0; sp.cum[1] = T;
+    PlaneView mvv;
+    mvv.base = w.maxvar; mvv.seq_stride = T;
+    for (int i = 0; i < MAX_CHAN; ++i) mvv.chan_off[i] = 0;
+#define EKS_MC_VM(PT, OCV)                                                                                          \
+    {                                                                                                               \
+        if (use_q) {                                                                                                \
+            mc_maxvar_kernel<PT><<<grid, MC_NT, 0, st>>>(var, O, T, (PT*)w.maxvar);                                 \
+            if (int rc = run_const_R<PT>(mvv, B, 1, sp, T, 0.0, (PT*)w.thr, w.sel, sel_bytes, st, v_quantile)) return rc; \
+        }                                                                                                           \
+        mc_valid_moments_kernel<PT, OCV><<<grid, MC_NT, 0, st>>>(y, lik, V, O, T, (const PT*)ymean, lik_threshold,  \
+                                                                 use_q, active, w);                                 \
+        mc_valid_moments_final_kernel<OCV><<<B, 32, 0, st>>>(O, w, active, moments_out);                            \
+        return check_launch("Mahalanobis moment kernels");                                                          \
+    }
+#define EKS_MC_VM_O(PT)                      \
+    if (O <= 4) EKS_MC_VM(PT, 4)             \
+    if (O <= 6) EKS_MC_VM(PT, 6)             \
+    if (O <= 8) EKS_MC_VM(PT, 8)             \
+    EKS_MC_VM(PT, MAX_CHAN)
+    if (dtype == EKS_F32) { EKS_MC_VM_O(float) }
+    EKS_MC_VM_O(double)
+#undef EKS_MC_VM_O
+#undef EKS_MC_VM
+}
+
+extern "C" int eks_mc_inflate_step(int dtype, int B, int V, int L, int T, const void* y_base, long long y_seq_stride,
+                                   const long long* y_chan_off, const void* ymean, void* var_base,
+                                   long long var_seq_stride, const long long* var_chan_off, const double* loading,
+                                   const double* mean, double epsilon, double threshold, double scalar,
+                                   const int* active, int* flags_out, void* stream) {
+    const int O = 2 * V;
+    EKS_REQUIRE(y_base && y_chan_off && ymean && var_base && var_chan_off && loading && mean && flags_out,
+                "mc_inflate_step: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 1 && V >= 2 && O <= MAX_CHAN && L >= 1 && L <= EKS_MAX_STATE,
+                "must have >=2 views to inflate variance");
+    const PlaneView y = make_view(y_base, y_seq_stride, y_chan_off, O);
+    const PlaneView var = make_view(var_base, var_seq_stride, var_chan_off, O);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(flags_out, 0, (size_t)B * sizeof(int), st);
+    const dim3 grid((T + MC_CHUNK - 1) / MC_CHUNK, B);
+    if (dtype == EKS_F32)
+        mc_inflate_kernel<float, MAX_CHAN, EKS_MAX_STATE><<<grid, MC_NT, 0, st>>>(
+            y, var, V, O, L, T, (const float*)ymean, loading, mean, epsilon, threshold, scalar, active, flags_out);
+    else
+        mc_inflate_kernel<double, MAX_CHAN, EKS_MAX_STATE><<<grid, MC_NT, 0, st>>>(
+            y, var, V, O, L, T, (const double*)ymean, loading, mean, epsilon, threshold, scalar, active, flags_out);
+    return check_launch("Mahalanobis inflation kernel");
 }

@@ -253,7 +253,7 @@ def project_3d_covariance_to_2d(ms_k, Vs_k, h_cam: PinholeProjection, inflated_v
 
 
 def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames, avg_mode,
-                            var_mode, n_latent) -> tuple:
+                            var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None) -> tuple:
     """Linear PCA-latent model without variance inflation: every per-frame stage runs on the device
     (eks_b200.pipeline.multicam_smooth_sessions); the host only packs the DataFrames."""
     from eks_b200.pipeline import multicam_smooth_sessions
@@ -268,7 +268,8 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
         sp = [float(smooth_param)] * K if isinstance(smooth_param, (int, float)) else [float(x) for x in smooth_param]
     res = multicam_smooth_sessions(raw[None], smooth_param=sp, spans=normalize_spans(T, s_frames),
                                    quantile_keep_pca=quantile_keep_pca, n_latent=n_latent, avg_mode=avg_mode,
-                                   var_mode=var_mode, dtype=dtype)
+                                   var_mode=var_mode, dtype=dtype, inflate_vars=inflate_vars,
+                                   inflate_vars_kwargs=inflate_vars_kwargs)
     out = res.out[0].permute(1, 3, 0, 2).contiguous().double().cpu().numpy()        # (V,T,K,9)
     ms = res.ms.double().cpu().numpy()                                              # (K,T,L)
     Vd = torch.diagonal(res.Vs, dim1=2, dim2=3).double().cpu().numpy()              # (K,T,L)
@@ -309,9 +310,11 @@ def ensemble_kalman_smoother_multicam(
     M, V, T, K, _ = marker_array.shape
     t_total = time.perf_counter()
 
-    if camgroup is None and not inflate_vars and pca_object is None:
+    if camgroup is None and pca_object is None:
+        if inflate_vars and inflate_vars_kwargs.get('mean', None) is not None:      # :355-357
+            inflate_vars_kwargs['mean'] = np.zeros_like(inflate_vars_kwargs['mean'])
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
-                                       avg_mode, var_mode, n_latent)
+                                       avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs)
 
     t0 = time.perf_counter()
     ema = ensemble(marker_array, avg_mode=avg_mode, var_mode=var_mode)

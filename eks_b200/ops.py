@@ -306,3 +306,33 @@ def mc_latent_init(y: PlaneView, ymean: torch.Tensor, pca_mean: torch.Tensor, co
           'eks_mc_latent_init')
     _count(2)
     return S0, Q
+
+
+def mc_valid_moments(y: PlaneView, ymean: torch.Tensor, var: PlaneView, T: int, ws: torch.Tensor, v_quantile=50.0,
+                     lik: PlaneView | None = None, lik_threshold: float = 0.9, active: torch.Tensor | None = None):
+    """Moments (n, sum x, sum x x^T) of the rows that feed the FactorAnalysis fit -> (B, 1 + O + O*O) float64."""
+    B, O = ymean.shape
+    mom = torch.zeros((B, 1 + O + O * O), dtype=torch.float64, device=ymean.device)
+    yo, vo = i64_host(y.chan_off), i64_host(var.chan_off)
+    lo = i64_host(lik.chan_off) if lik is not None else None
+    check(lib().eks_mc_valid_moments(dt_code(ymean.dtype), B, O // 2, T, ptr(y.base), y.seq_stride, ptr(yo), ptr(ymean),
+                                     ptr(var.base), var.seq_stride, ptr(vo), ptr(lik.base) if lik is not None else None,
+                                     lik.seq_stride if lik is not None else 0, ptr(lo), float(lik_threshold),
+                                     -1.0 if v_quantile is None else float(v_quantile), ptr(active), ptr(mom),
+                                     ptr(ws), ws.numel(), stream_ptr()), 'eks_mc_valid_moments')
+    _count(2 + (1 + (6 if ymean.dtype == torch.float32 else 12) if v_quantile is not None else 0))
+    return mom
+
+
+def mc_inflate_step(y: PlaneView, ymean: torch.Tensor, var: PlaneView, T: int, loading: torch.Tensor,
+                    mean: torch.Tensor, epsilon=1e-6, threshold=5.0, scalar=10.0, active: torch.Tensor | None = None):
+    """One Mahalanobis inflation pass, variances updated in place -> flags (B,) int32 (1 = something inflated)."""
+    B, O, L = loading.shape
+    flags = torch.empty(B, dtype=torch.int32, device=ymean.device)
+    yo, vo = i64_host(y.chan_off), i64_host(var.chan_off)
+    check(lib().eks_mc_inflate_step(dt_code(ymean.dtype), B, O // 2, L, T, ptr(y.base), y.seq_stride, ptr(yo),
+                                    ptr(ymean), ptr(var.base), var.seq_stride, ptr(vo), ptr(loading), ptr(mean),
+                                    float(epsilon), float(threshold), float(scalar), ptr(active), ptr(flags),
+                                    stream_ptr()), 'eks_mc_inflate_step')
+    _count(1)
+    return flags

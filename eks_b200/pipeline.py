@@ -164,10 +164,78 @@ def pca_from_moments(mom, O: int, L: int):
     return means, comps
 
 
+def fa_from_moments(mom_b, O: int, L: int, tol: float = 1e-2, max_iter: int = 1000):
+    """sklearn FactorAnalysis(n_components=L).fit restated on the sufficient statistics (n, sum x, sum x x^T)
+    (sklearn/decomposition/_factor_analysis.py::fit): the SVD of X / (sqrt(psi) sqrt(n)) is taken through the
+    eigen-decomposition of its O x O Gram matrix (exact here: the randomized solver's sketch, n_components + 10
+    columns, spans all O <= 16 features).  Returns (mean (O,), loading (O,L) = components_.T) float64."""
+    import numpy as np
+    n = mom_b[0]
+    mean = mom_b[1:1 + O] / n
+    cov = mom_b[1 + O:].reshape(O, O) / n - np.outer(mean, mean)
+    var = np.diag(cov).copy()
+    psi = np.ones(O)
+    old_ll, small = -np.inf, 1e-12
+    llconst = O * np.log(2.0 * np.pi) + L
+    W = np.zeros((L, O))
+    for _ in range(max_iter):
+        sqrt_psi = np.sqrt(psi) + small
+        gram = cov / np.outer(sqrt_psi, sqrt_psi)
+        lam, vec = np.linalg.eigh(gram)
+        s = np.maximum(lam[::-1][:L], 0.0)
+        vt = vec[:, ::-1][:, :L].T
+        unexp_var = np.trace(gram) - s.sum()
+        W = np.sqrt(np.maximum(s - 1.0, 0.0))[:, None] * vt * sqrt_psi
+        with np.errstate(divide='ignore'):
+            ll = (llconst + np.sum(np.log(s)) + unexp_var + np.sum(np.log(psi))) * (-n / 2.0)
+        if ll - old_ll < tol:
+            break
+        old_ll = ll
+        psi = np.maximum(var - np.sum(W ** 2, axis=0), small)
+    return mean, W.T.copy()
+
+
+def mc_inflate_variances(yv: PlaneView, vv: PlaneView, ymean: torch.Tensor, T: int, ws: torch.Tensor, n_latent: int,
+                         lik: PlaneView | None = None, likelihood_threshold: float | None = 0.9,
+                         v_quantile_threshold: float | None = 50.0, epsilon: float = 1e-6, loading_matrix=None,
+                         mean=None, threshold: float = 5.0, scalar: float = 10.0, max_rounds: int = 64) -> int:
+    """The while-loop of mA_compute_maha (eks/multicam_smoother.py:684-712) for all problems at once: the
+    variance planes of `vv` are inflated in place.  Returns the number of rounds."""
+    import numpy as np
+    B, O = ymean.shape
+    dev = ymean.device
+    active = torch.ones(B, dtype=torch.int32, device=dev)
+    fixed = loading_matrix is not None and mean is not None
+    Wh = np.zeros((B, O, n_latent))
+    muh = np.zeros((B, O))
+    if fixed:
+        Wh[:] = np.asarray(loading_matrix, dtype=np.float64)
+        muh[:] = np.asarray(mean, dtype=np.float64)
+    use_lik = lik is not None and likelihood_threshold is not None
+    rounds = 0
+    while rounds < max_rounds:
+        rounds += 1
+        if not fixed:
+            mom = ops.mc_valid_moments(yv, ymean, vv, T, ws, v_quantile=v_quantile_threshold,
+                                       lik=lik if use_lik else None,
+                                       lik_threshold=likelihood_threshold if use_lik else 0.0, active=active).cpu().numpy()
+            act = active.cpu().numpy()
+            for b in range(B):
+                if act[b]:
+                    muh[b], Wh[b] = fa_from_moments(mom[b], O, n_latent)
+        flags = ops.mc_inflate_step(yv, ymean, vv, T, torch.as_tensor(Wh, device=dev), torch.as_tensor(muh, device=dev),
+                                    epsilon=epsilon, threshold=threshold, scalar=scalar, active=active)
+        active = active * (flags != 0).to(torch.int32)
+        if int(active.sum().item()) == 0:
+            break
+    return rounds
+
+
 def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, quantile_keep_pca: float = 50.0,
                              n_latent: int = 3, avg_mode='median', var_mode='confidence_weighted_var',
                              dtype=torch.float32, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
-                             min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None) -> MulticamResult:
+                             min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None,
+                             inflate_vars: bool = False, inflate_vars_kwargs: dict | None = None) -> MulticamResult:
     """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551; linear model, inflate_vars=False) for S
     sessions at once, every per-frame stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.
 
@@ -210,6 +278,13 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
         pm = torch.as_tensor(pca_mean, device=dev).to(dtype).contiguous()
     with stage('latent_init'):
         S0, Q = ops.mc_latent_init(yv, ymean, pm, C, T, ws)
+    if inflate_vars:   # in place on the ensemble-variance planes: the reference outputs the inflated variances
+        kw = dict(inflate_vars_kwargs or {})
+        lik = None
+        if kw.pop('likelihoods', None) is not None:
+            lik = PlaneView(out, V * 9 * T, [v * 9 * T + 2 * T for v in range(V)])
+        with stage('inflate_vars'):
+            mc_inflate_variances(yv, vv, ymean, T, ws, kw.pop('n_latent', L), lik=lik, **kw)
     eye = torch.eye(L, dtype=dtype, device=dev).expand(B, L, L).contiguous()
     model = Model(torch.zeros((B, L), dtype=dtype, device=dev), S0, eye, Q, C)
     iters = loss = None

@@ -189,6 +189,30 @@ int eks_mc_latent_init(int dtype, int B, int O, int L, int T, const void* y_base
                        const void* components, void* S0_out, void* Q_out, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* Mahalanobis variance inflation, one iteration of the while-loop of mA_compute_maha
+ * (eks/multicam_smoother.py:653-725) for B problems at once; V cameras, O = 2 V channels.
+ *
+ * eks_mc_valid_moments: the data pass of the FactorAnalysis fit inside compute_mahalanobis (eks/stats.py:103-124):
+ *   rows with max_o var < np.percentile(max_o var, v_quantile) (strict; v_quantile < 0 disables) and, when a
+ *   likelihood view (V channels) is given, min likelihood >= lik_threshold.  moments_out [B][1 + O + O*O] (double) =
+ *   n, sum x, sum x x^T with x = y - ymean.  Problems with active[b] == 0 (nullable: all active) are skipped.
+ *   Uses the workspace of eks_mc_prestage_workspace_bytes.  The O x O factor-analysis iteration is host work.
+ * eks_mc_inflate_step: stats.py:126-157 + inflate_variance (multicam_smoother.py:728-764), fp64 per-frame algebra:
+ *   B_t = (W^T diag(1/(v_t + epsilon)) W)^-1, z_t, reconstruction, per-view 2x2 posterior predictive covariance and
+ *   Mahalanobis distance; the variances of views with distance > threshold (both views when V == 2 and either is
+ *   flagged) are multiplied by `scalar` IN PLACE in the var view; flags_out[b] = 1 if problem b inflated anything.
+ *   loading [B][O][L] and mean [B][O] are device arrays of doubles (FactorAnalysis components_.T and mean_). */
+int eks_mc_valid_moments(int dtype, int B, int V, int T, const void* y_base, long long y_seq_stride,
+                         const long long* y_chan_off_host, const void* ymean, const void* var_base,
+                         long long var_seq_stride, const long long* var_chan_off_host, const void* lik_base,
+                         long long lik_seq_stride, const long long* lik_chan_off_host, double lik_threshold,
+                         double v_quantile, const int* active, double* moments_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int eks_mc_inflate_step(int dtype, int B, int V, int L, int T, const void* y_base, long long y_seq_stride,
+                        const long long* y_chan_off_host, const void* ymean, void* var_base, long long var_seq_stride,
+                        const long long* var_chan_off_host, const double* loading, const double* mean, double epsilon,
+                        double threshold, double scalar, const int* active, int* flags_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

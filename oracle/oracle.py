@@ -336,7 +336,8 @@ def singlecam(raw, smooth_param=None, s_frames=None, blocks=None, avg_mode='medi
 
 
 def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_param=None, s_frames=None,
-             avg_mode='median', var_mode='confidence_weighted_var', dtype=np.float32, trace_cap=0):
+             avg_mode='median', var_mode='confidence_weighted_var', dtype=np.float32, trace_cap=0,
+             inflate_vars=False, inflate_vars_kwargs=None):
     """ensemble_kalman_smoother_multicam restated (eks/multicam_smoother.py:279-551), inflate_vars=False.
 
     raw: (M,V,T,K,3).  Linear model: centring and PCA initialisation are the oracle's own restatement
@@ -364,6 +365,15 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
         ys = cen_o
         D = n_latent
     ev = stacked(2, 4)                                                        # (K,T,2V)
+    ev_out = ev                                                               # variances of the output columns
+    if inflate_vars:   # eks/multicam_smoother.py:353-361 (on the CENTRED predictions, also for the nonlinear model)
+        kw = dict(inflate_vars_kwargs or {})
+        cen_i = mc_center_predictions(ens, quantile_keep_pca)[1]
+        likes = np.transpose(ens[..., 4], (2, 1, 0)) if kw.pop('likelihoods', None) is not None else None   # (K,T,V)
+        ev = np.stack([mc_inflate_variance(cen_i[k], ev[k], n_latent=n_latent,
+                                           likes=None if likes is None else likes[k], **kw)[0] for k in range(K)])
+        if cams is None:
+            ev_out = ev
     s_finals, ms, Vs, info = run_kalman_smoother(ys, m0s, S0s, As, Cs, Qs, np.swapaxes(ev, 0, 1),
                                                  s_frames=s_frames, smooth_param=smooth_param, cams=cams,
                                                  dtype=dtype, trace_cap=trace_cap)
@@ -382,7 +392,7 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
             cam_out[c, :, k, 1] = uv[:, 2 * c + 1]
             cam_out[c, :, k, 2] = ens[c, :, k, 4]
             cam_out[c, :, k, 3:5] = ens[c, :, k, 0:2]
-            cam_out[c, :, k, 5:7] = ens[c, :, k, 2:4]
+            cam_out[c, :, k, 5:7] = ev_out[k][:, 2 * c:2 * c + 2]       # linear: the inflated variances (:505-508)
             if cams is not None:  # :943-944 -- always variance columns 0 / 1
                 cam_out[c, :, k, 7] = cov[:, 2 * c, 2 * c] + ev[k][:, 0]
                 cam_out[c, :, k, 8] = cov[:, 2 * c + 1, 2 * c + 1] + ev[k][:, 1]
@@ -438,6 +448,52 @@ def mc_pca_init(mask, centered, good_centered, n_latent=3):
         Qs.append(cov / mx if mx > 0 else cov)
         Cs.append(pca.components_.T)
     return m0s, np.stack(S0s), As, np.stack(Qs), np.stack(Cs)
+
+
+def mc_inflate_variance(centered, evars, n_latent=3, likes=None, likelihood_threshold=0.9, v_quantile_threshold=50.0,
+                        epsilon=1e-6, loading_matrix=None, mean=None, threshold=5.0, scalar=10.0):
+    """mA_compute_maha + compute_mahalanobis + inflate_variance restated for ONE keypoint
+    (eks/multicam_smoother.py:653-764, eks/stats.py:67-157), with scikit-learn's FactorAnalysis itself and the
+    per-frame loops written as batched float64 NumPy.  centered, evars: (T, 2V).  Returns the inflated variances."""
+    from sklearn.decomposition import FactorAnalysis
+    x = np.asarray(centered)
+    v = np.array(evars, copy=True)
+    V = x.shape[1] // 2
+    assert V >= 2, 'must have >=2 views to inflate variance'
+    rounds = 0
+    while True:
+        rounds += 1
+        if loading_matrix is None or mean is None:
+            valid = np.ones(x.shape[0], dtype=bool)
+            if likes is not None and likelihood_threshold is not None:
+                valid = np.min(likes, axis=1) >= likelihood_threshold
+            if v_quantile_threshold is not None:
+                ev_max = v.max(axis=1)
+                valid = valid & (ev_max < np.percentile(ev_max, v_quantile_threshold))
+            fa = FactorAnalysis(n_components=n_latent).fit(x[valid])
+            W, mu = fa.components_.T.astype(np.float64), fa.mean_.astype(np.float64)
+        else:
+            W, mu = np.asarray(loading_matrix, dtype=np.float64), np.asarray(mean, dtype=np.float64)
+        v64, x64 = v.astype(np.float64), x.astype(np.float64)
+        iv = 1.0 / (v64 + epsilon)
+        Bm = np.linalg.inv(np.einsum('oi,to,oj->tij', W, iv, W))
+        z = np.einsum('tij,oj,to->ti', Bm, W, iv * (x64 - mu))
+        diff = x64 - (z @ W.T + mu)
+        flag = np.zeros((x.shape[0], V), dtype=bool)
+        for c in range(V):
+            Wc = W[2 * c:2 * c + 2]
+            Q = np.einsum('ai,tij,bj->tab', Wc, Bm, Wc)
+            Q[:, 0, 0] += v64[:, 2 * c]
+            Q[:, 1, 1] += v64[:, 2 * c + 1]
+            d = diff[:, 2 * c:2 * c + 2]
+            with np.errstate(all='ignore'):
+                flag[:, c] = np.einsum('ta,tab,tb->t', d, np.linalg.inv(Q), d) > threshold
+        full = np.repeat(flag, 2, axis=1)
+        if V == 2:
+            full |= full.any(axis=1, keepdims=True)
+        v[full] *= scalar
+        if not full.any():
+            return v, rounds
 
 
 # ----------------------------------------------------------------------------- IBL pupil model

@@ -10,13 +10,18 @@ pytestmark = pytest.mark.gpu
 RTOL64, RTOL32 = 1e-5, 1e-3
 
 
-def synth_multicam(M=5, V=2, K=3, T=3000, seed=0):
+def synth_multicam(M=5, V=2, K=3, T=3000, seed=0, outlier_frac=0.0):
     rng = np.random.default_rng(seed)
     lat = np.cumsum(rng.normal(0, 0.3, (T, K, 3)), axis=0)
     W = rng.standard_normal((K, 2 * V, 3))
     truth = np.einsum('tkl,kol->tko', lat, W) + rng.uniform(50, 300, (1, K, 2 * V))
     occ = rng.random((T, K)) < 0.05
     sigma = np.where(occ, 4.0, 0.5)[:, :, None]
+    if outlier_frac > 0:   # confident but geometrically inconsistent predictions in one view (all seeds agree)
+        out = rng.random((T, K)) < outlier_frac
+        view = rng.integers(0, V, (T, K))
+        for v in range(V):
+            truth[:, :, 2 * v] += np.where(out & (view == v), rng.uniform(8, 25, (T, K)), 0.0)
     raw = np.empty((M, V, T, K, 3))
     for m in range(M):
         noisy = truth + rng.standard_normal((T, K, 2 * V)) * sigma
@@ -130,3 +135,53 @@ def test_fixed_smooth_param_and_spans():
     ref = oracle.multicam(raw, dtype=np.float64, s_frames=[(100, 900), (1200, None)])
     assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
     _check(_cam_out(res), ref['cam_out'], RTOL64, 's_frames')
+
+
+@pytest.mark.parametrize('V,kw', [(2, {}), (3, {}), (2, {'likelihoods': True, 'likelihood_threshold': 0.6}),
+                                  (3, {'v_quantile_threshold': 80.0, 'epsilon': 1e-4})])
+def test_variance_inflation_matches_oracle_fp64(V, kw):
+    """Mahalanobis variance inflation on the device (FactorAnalysis moments + per-frame kernel) vs the oracle, which
+    runs scikit-learn's FactorAnalysis and the reference's per-frame algebra in NumPy."""
+    from oracle import oracle
+    raw = synth_multicam(V=V, T=2600, seed=21 + V, outlier_frac=0.03)
+    res = _run(raw, torch.float64, inflate_vars=True, inflate_vars_kwargs=dict(kw))
+    ref = oracle.multicam(raw, dtype=np.float64, inflate_vars=True, inflate_vars_kwargs=dict(kw))
+    out = _cam_out(res)
+    infl = ref['cam_out'][..., 5:7]
+    base = oracle.multicam(raw, dtype=np.float64, smooth_param=1.0)['cam_out'][..., 5:7]
+    assert (infl != base).sum() > 50, 'test data must trigger inflation'
+    np.testing.assert_allclose(out[..., 5:7], infl, rtol=1e-12)           # identical inflation decisions
+    assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
+    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=RTOL64)
+    _check(out, ref['cam_out'], RTOL64, f'inflation V={V}')
+
+
+def test_variance_inflation_fixed_loading_matrix():
+    from oracle import oracle
+    raw = synth_multicam(V=2, T=1500, seed=8, outlier_frac=0.04)
+    rng = np.random.default_rng(0)
+    Wm = np.linalg.qr(rng.standard_normal((4, 3)))[0] * 5.0
+    kw = dict(loading_matrix=Wm, mean=np.zeros(4))
+    res = _run(raw, torch.float64, inflate_vars=True, inflate_vars_kwargs=dict(kw), smooth_param=2.0)
+    ref = oracle.multicam(raw, dtype=np.float64, inflate_vars=True, inflate_vars_kwargs=dict(kw), smooth_param=2.0)
+    _check(_cam_out(res), ref['cam_out'], RTOL64, 'inflation with a given loading matrix')
+
+
+def test_public_entry_point_with_inflation():
+    """ensemble_kalman_smoother_multicam(inflate_vars=True) (the CLI default) runs on the device pipeline."""
+    import eks_b200
+    from eks_b200.marker_array import MarkerArray
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    from oracle import oracle
+    raw = synth_multicam(V=2, T=1200, seed=4, outlier_frac=0.03)
+    eks_b200.set_precision('float64')
+    try:
+        dfs, s, df3d = ensemble_kalman_smoother_multicam(
+            MarkerArray(raw, data_fields=['x', 'y', 'likelihood'], dtype=np.float64), ['a', 'b', 'c'], ['top', 'bot'],
+            inflate_vars=True)
+    finally:
+        eks_b200.set_precision('float32')
+    ref = oracle.multicam(raw, dtype=np.float64, inflate_vars=True)
+    np.testing.assert_allclose(s, ref['s_finals'], rtol=RTOL64)
+    for c in range(2):
+        _check(dfs[c].to_numpy().reshape(1200, 3, 9), ref['cam_out'][c], RTOL64, f'camera {c}')
