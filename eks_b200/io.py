@@ -32,12 +32,61 @@ def convert_lp_dlc(df_lp: pd.DataFrame, keypoint_names: list, model_name: str | 
     return pd.DataFrame(cols, index=df_lp.index)
 
 
+def _read_csv_fast(file_path: str):
+    """DLC / Lightning Pose CSV (3 header rows: scorer, bodyparts, coords; first column = frame index) through
+    pyarrow's multi-threaded reader -> flat '{keypoint}_{coord}' float64 DataFrame, same columns / index as
+    pd.read_csv(header=[0, 1, 2], index_col=0) + convert_lp_dlc (eks/utils.py:35-135)."""
+    import csv
+
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    with open(file_path, newline='') as f:
+        rd = csv.reader(f)
+        scorer, bodyparts, coords = next(rd), next(rd), next(rd)
+    ncol = len(scorer)
+    if not (len(bodyparts) == ncol and len(coords) == ncol and ncol >= 2):
+        raise ValueError('unexpected header')
+    names = ['__index__'] + [f'c{i}' for i in range(1, ncol)]
+    table = pacsv.read_csv(file_path, read_options=pacsv.ReadOptions(skip_rows=3, column_names=names),
+                           convert_options=pacsv.ConvertOptions(
+                               column_types={n: pa.float64() for n in names[1:]}, strings_can_be_null=True))
+    model_name = scorer[1]
+    keypoint_names = [bodyparts[i] for i in range(1, ncol) if coords[i] == 'x']
+    where = {(scorer[i], bodyparts[i], coords[i]): i for i in range(ncol - 1, 0, -1)}
+    cols = {}
+    for kp in keypoint_names:
+        for coord in ('x', 'y', 'likelihood'):
+            i = where.get((model_name, kp, coord))
+            if i is not None and not any(s.startswith('Unnamed') for s in (model_name, kp, coord)):
+                cols[f'{kp}_{coord}'] = table.column(i).to_numpy(zero_copy_only=False)
+    index = table.column(0).to_numpy(zero_copy_only=False)
+    if index.dtype.kind not in 'iu':
+        raise ValueError('non-integer frame index')
+    df = pd.DataFrame(cols, index=pd.Index(index.astype(np.int64)), copy=False)
+    return df, keypoint_names
+
+
 def _read_one(file_path: str):
     if file_path.endswith('.slp'):
         raise NotImplementedError('.slp ingest needs sleap_io, which is not available in this environment')
+    if os.environ.get('EKS_B200_PANDAS_CSV') != '1':
+        try:
+            return _read_csv_fast(file_path)
+        except Exception as e:  # unusual layouts (string index, ragged header ...): pandas handles them
+            logger.debug(f'fast CSV reader declined {file_path}: {e}')
     df = pd.read_csv(file_path, header=[0, 1, 2], index_col=0)
     kps = get_keypoint_names(df)
     return convert_lp_dlc(df, kps), kps
+
+
+def _read_many(file_paths: list) -> list:
+    """Read the seed files concurrently (pyarrow releases the GIL)."""
+    if len(file_paths) <= 1:
+        return [_read_one(fp) for fp in file_paths]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, len(file_paths))) as ex:
+        return list(ex.map(_read_one, file_paths))
 
 
 def format_data(input_source, camera_names: list | None = None) -> tuple[list, list]:
@@ -53,10 +102,7 @@ def format_data(input_source, camera_names: list | None = None) -> tuple[list, l
                          'names to list of file paths')
     dfs, keypoint_names = [], None
     if camera_names is None:
-        for fp in file_paths:
-            if not (fp.endswith('.csv') or fp.endswith('.slp')):
-                continue
-            df, keypoint_names = _read_one(fp)
+        for df, keypoint_names in _read_many([fp for fp in file_paths if fp.endswith('.csv') or fp.endswith('.slp')]):
             dfs.append(df)
     else:
         for camera in camera_names:
@@ -68,8 +114,7 @@ def format_data(input_source, camera_names: list | None = None) -> tuple[list, l
                     f"no files matching camera '{camera}' found in {input_source}. "
                     f'ensure the camera name appears as a substring of each filename.')
             per_cam = []
-            for fp in valid:
-                df, keypoint_names = _read_one(fp)
+            for df, keypoint_names in _read_many(valid):
                 per_cam.append(df)
             dfs.append(per_cam)
         counts = [len(d) for d in dfs]

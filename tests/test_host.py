@@ -241,3 +241,23 @@ def test_build_R_and_const_R_mirrors():
     np.testing.assert_allclose(compute_initial_guesses(ev[0]), oracle.compute_initial_guess(ev[0]))
     with pytest.raises(ValueError):
         compute_initial_guesses(ev[0][:1])
+
+
+def test_fast_csv_reader_equals_pandas_path(tmp_path, monkeypatch):
+    """pyarrow ingest returns the same flat DataFrames as pd.read_csv + convert_lp_dlc."""
+    import pandas as pd
+    from eks_b200 import io
+    rng = np.random.default_rng(0)
+    cols = pd.MultiIndex.from_product([['heatmap_tracker'], ['paw', 'nose', 'tail base'], ['x', 'y', 'likelihood']],
+                                      names=['scorer', 'bodyparts', 'coords'])
+    for i in range(3):
+        df = pd.DataFrame(rng.random((257, 9)).astype(np.float32) * 300, columns=cols)
+        df.iloc[5, 0] = np.nan
+        df.to_csv(tmp_path / f'pred_rng={i}.csv')
+    fast, kp_fast = io.format_data(str(tmp_path))
+    monkeypatch.setenv('EKS_B200_PANDAS_CSV', '1')
+    slow, kp_slow = io.format_data(str(tmp_path))
+    assert kp_fast == kp_slow == ['paw', 'nose', 'tail base'] and len(fast) == len(slow) == 3
+    for a, b in zip(fast, slow):
+        assert list(a.columns) == list(b.columns) and (a.index == b.index).all()
+        np.testing.assert_array_equal(a.to_numpy(), b.to_numpy())
