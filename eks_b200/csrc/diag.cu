@@ -355,6 +355,105 @@ __device__ inline void diag_warp_tile(const P (&y)[L], int nvalid, const ChanCon
     G += (double)(ga + gb);
 }
 
+#ifndef EKS_L2_PREFETCH
+#define EKS_L2_PREFETCH 0   // warp-tiles of look-ahead for an L2 prefetch of the observation stream (0 = off).
+                            // Measured on the c5 bench: 2 -> 35.4 ms, 4 -> 37.4 ms, 8 -> 45.0 ms against 32.4 ms without:
+                            // the memory system is already saturated, extra requests only add contention
+#endif
+#ifndef EKS_FFMA2
+#define EKS_FFMA2 2   // fp32: packed FFMA2 (sm_100) for the two half-chunk chains of diag_warp_tile.
+                      // 0 = scalar FFMA (33.0 ms optimiser stage on the c5 bench), 1 = 4-byte cp.async into an interleaved
+                      // SMEM layout so that pairs load directly (34.9 ms: the 4x LDGSTS count costs more than the MOVs it
+                      // saves), 2 = 16-byte ring, pairs formed in registers (32.4 ms)
+#endif
+
+// fp32 variant of diag_warp_tile on PACKED pairs: y2[i] = (y[i], y[H + i]) holds one frame of each half-chunk, so
+// the two independent dependency chains of the scalar version become the two lanes of one FFMA2 (Blackwell's
+// packed fp32 FMA: two IEEE fused multiply-adds per issue slot, bit-identical to the scalar code).  Halves the
+// floating-point instruction count of a kernel that is issue-bound (ncu: 67 % issue utilisation at 73 % of HBM peak).
+template <int L, bool FULL, bool ACC>
+__device__ inline void diag_warp_tile_f2(const float2 (&y2)[L / 2], int nvalid, const ChanConst<float>& k, float a_lane,
+                                         float b_lane, float& cm, float& cd, double& E2, double& G) {
+    constexpr int H = L / 2;
+    const int lane = threadIdx.x & 31;
+    const float alpha = k.alpha, gamma = k.gamma;
+    const float2 al2 = make_float2(alpha, alpha), ga2 = make_float2(gamma, gamma);
+    float2 U = make_float2(0.f, 0.f), W = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        W = __ffma2_rn(al2, W, U);
+        U = __ffma2_rn(al2, U, y2[i]);
+    }
+    const float2 zd2 = __ffma2_rn(ga2, W, U);      // (zad, zbd)
+    const float zam = U.x, zbm = U.y, zad = zd2.x, zbd = zd2.y;
+    const float aH = k.aH, bH = k.bH;
+    float zm = fmaf(aH, zam, zbm);
+    float zd = fmaf(aH, zad, fmaf(bH, zam, zbd));
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int d = 1 << q;
+        const float pm = __shfl_up_sync(0xffffffffu, zm, d);
+        const float pd = __shfl_up_sync(0xffffffffu, zd, d);
+        if (lane >= d) {
+            zd = fmaf(k.aL[q], pd, fmaf(k.bL[q], pm, zd));
+            zm = fmaf(k.aL[q], pm, zm);
+        }
+    }
+    float em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
+    if (lane == 0) { em = 0.f; ed = 0.f; }
+    const float tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);
+    const float cm0 = cm, cd0 = cd;
+    cm = fmaf(k.aW, cm0, tm);
+    cd = fmaf(k.aW, cd0, fmaf(k.bW, cm0, td));
+    if (!ACC) return;
+    const float m0 = fmaf(a_lane, cm0, em);
+    const float d0 = fmaf(a_lane, cd0, fmaf(b_lane, cm0, ed));
+    float2 m = make_float2(m0, fmaf(aH, m0, zam));
+    float2 dd = make_float2(d0, fmaf(aH, d0, fmaf(bH, m0, zad)));
+    float2 e2 = make_float2(0.f, 0.f), gg = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float2 e = __ffma2_rn(ga2, m, y2[i]);
+        m = __ffma2_rn(al2, m, y2[i]);
+        if (FULL) {
+            e2 = __ffma2_rn(e, e, e2);
+            gg = __ffma2_rn(e, dd, gg);
+        } else {
+            if (i < nvalid) { e2.x = fmaf(e.x, e.x, e2.x); gg.x = fmaf(e.x, dd.x, gg.x); }
+            if (H + i < nvalid) { e2.y = fmaf(e.y, e.y, e2.y); gg.y = fmaf(e.y, dd.y, gg.y); }
+        }
+        dd = __ffma2_rn(al2, dd, e);
+    }
+    E2 += (double)(e2.x + e2.y);
+    G += (double)(gg.x + gg.y);
+}
+
+// fp32 ring fill for the packed variant: 4-byte cp.async, element q of a lane's chunk lands in the interleaved slot
+// (q mod H) * 2 + q / H, so that one 16-byte shared load delivers two (y[i], y[H + i]) register pairs.
+// Instruction i moves chunk i: 32 consecutive frames = one coalesced 128-byte request, conflict-free in SMEM.
+__device__ inline void warp_issue_tile_f2(unsigned char* stage, const float* __restrict__ plane, int t0, int e_min,
+                                          int n, bool inner) {
+    constexpr int L = OPT_CHUNK_BYTES / 4, H = L / 2;
+    const int lane = threadIdx.x & 31;
+    const int pos = ((lane & (H - 1)) << 1) | (lane / H);
+    unsigned char* dst = stage + pos * 4;
+    const float* src = plane + t0 + lane;
+    if (inner) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * OPT_PAD_BYTES);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i * L) : "memory");
+        }
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int e = t0 + i * L + lane;
+            const int valid = (e < n && e >= e_min) ? 4 : 0;
+            cp_async_4(dst + i * OPT_PAD_BYTES, plane + (valid > 0 ? e : 0), valid);
+        }
+    }
+}
+
 // per-warp ring stage: 32 padded chunks
 constexpr int WRP_STAGE_BYTES = 32 * OPT_PAD_BYTES;
 
@@ -453,8 +552,23 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
         const int nt = wt_hi - first_wt;
         auto issue = [&](int stage, int wt) {
             const int t0i = t_c + wt * WT;
-            warp_issue_tile<P>(wring + stage * WRP_STAGE_BYTES, yc, t0i, e_min, a.n, vec,
-                               t0i >= e_min && t0i + WT <= a.n);
+            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 1)
+                warp_issue_tile_f2(wring + stage * WRP_STAGE_BYTES, reinterpret_cast<const float*>(yc), t0i, e_min,
+                                   a.n, t0i >= e_min && t0i + WT <= a.n);
+            else
+                warp_issue_tile<P>(wring + stage * WRP_STAGE_BYTES, yc, t0i, e_min, a.n, vec,
+                                   t0i >= e_min && t0i + WT <= a.n);
+#if EKS_L2_PREFETCH > 0
+            // pull a later warp-tile of this run into L2 so that the ring is filled at L2 latency: the SMEM ring
+            // (all of the SM's shared memory at 3 CTAs x 8 warps x 2 stages) cannot hold a DRAM latency of bytes
+            const int wtp = wt + EKS_L2_PREFETCH;
+            if (lane == 0 && vec && wtp < wt_hi) {
+                const P* pa = yc + t_c + (long long)wtp * WT;
+                const int bytes = (int)min((long long)WT, (long long)a.n - (t_c + (long long)wtp * WT)) * (int)sizeof(P) & ~15;
+                if (bytes > 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(pa), "r"(bytes) : "memory");
+            }
+#endif
         };
 #pragma unroll
         for (int st = 0; st < OPT_STAGES - 1; ++st) {
@@ -472,8 +586,44 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
             const unsigned char* mine = wring + (it % OPT_STAGES) * WRP_STAGE_BYTES + lane * OPT_PAD_BYTES;
             const int t0 = t_c + (first_wt + it) * WT;
             const int cstart = t0 + lane * L;
-            P y[L];
             const bool inner = (t0 >= e_min) && (t0 + WT <= a.n);  // warp-uniform: no masked frames
+            const bool acc = (first_wt + it) >= wt_lo;
+            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 1) {
+                constexpr int H = L / 2;
+                float2 y2[H];
+                const float2 nm2 = make_float2(-(float)mean, -(float)mean);
+                if (inner) {
+#pragma unroll
+                    for (int i = 0; i < L / 4; ++i) {
+                        const float4 v = *reinterpret_cast<const float4*>(mine + i * 16);
+                        y2[2 * i] = __fadd2_rn(make_float2(v.x, v.y), nm2);
+                        y2[2 * i + 1] = __fadd2_rn(make_float2(v.z, v.w), nm2);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < L / 4; ++i) {
+                        const float4 v = *reinterpret_cast<const float4*>(mine + i * 16);
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+                        float o[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int fr = cstart + (q & 1) * H + 2 * i + (q >> 1);
+                            o[q] = (fr >= e_min && fr < a.n) ? e[q] - (float)mean : 0.f;
+                        }
+                        y2[2 * i] = make_float2(o[0], o[1]);
+                        y2[2 * i + 1] = make_float2(o[2], o[3]);
+                    }
+                }
+                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
+                float fcm = (float)cm, fcd = (float)cd;
+                if (!acc) diag_warp_tile_f2<L, true, false>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else if (inner) diag_warp_tile_f2<L, true, true>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else diag_warp_tile_f2<L, false, true>(y2, max(0, min(L, a.n - cstart)), kk, (float)a_lane, (float)b_lane,
+                                                       fcm, fcd, E2, G);
+                cm = (P)fcm; cd = (P)fcd;
+                continue;
+            }
+            P y[L];
             if (inner) {
 #pragma unroll
                 for (int i = 0; i < L / VW; ++i) {
@@ -494,7 +644,20 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
                     }
                 }
             }
-            const bool acc = (first_wt + it) >= wt_lo;
+            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 2) {   // 16-byte ring, pairs formed in registers
+                constexpr int H = L / 2;
+                float2 y2[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) y2[i] = make_float2((float)y[i], (float)y[H + i]);
+                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
+                float fcm = (float)cm, fcd = (float)cd;
+                if (!acc) diag_warp_tile_f2<L, true, false>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else if (inner) diag_warp_tile_f2<L, true, true>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else diag_warp_tile_f2<L, false, true>(y2, max(0, min(L, a.n - cstart)), kk, (float)a_lane, (float)b_lane,
+                                                       fcm, fcd, E2, G);
+                cm = (P)fcm; cd = (P)fcd;
+                continue;
+            }
             if (!acc) diag_warp_tile<P, L, true, false>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
             else if (inner) diag_warp_tile<P, L, true, true>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
             else diag_warp_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), shk, a_lane, b_lane, cm, cd, E2, G);
