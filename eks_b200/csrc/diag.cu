@@ -49,6 +49,7 @@ struct ChanConst {
     P aL[5], bL[5];  // Phi^(L 2^k) = [[aL,0],[bL,aL]]
     P aW, bW;        // Phi^(32 L)
     P aH, bH;        // Phi^(L/2)
+    P aQ, bQ;        // Phi^(L/4)
 };
 
 // shared-memory tile ring: every thread's chunk is CHUNK_BYTES of frames, padded to PAD_BYTES so that the
@@ -249,7 +250,9 @@ __device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanS
     // Phi^(L/2) of the scaled recursion by repeated squaring of Phi = [[alpha,0],[gamma,alpha]]
     {
         P pa = k.alpha, pb = k.gamma;
-        for (int h = 1; h < L / 2; h <<= 1) { pb = P(2) * pa * pb; pa = pa * pa; }
+        for (int h = 1; h < L / 4; h <<= 1) { pb = P(2) * pa * pb; pa = pa * pa; }
+        k.aQ = pa; k.bQ = pb;
+        pb = P(2) * pa * pb; pa = pa * pa;   // Phi^(L/2) = (Phi^(L/4))^2: keeps quarter/half/full powers consistent
         k.aH = pa; k.bH = pb;
     }
     P aL = k.aH * k.aH;                 // Phi^L = (Phi^(L/2))^2: keeps the half/full powers consistent
@@ -364,7 +367,8 @@ __device__ inline void diag_warp_tile(const P (&y)[L], int nvalid, const ChanCon
 #define EKS_FFMA2 2   // fp32: packed FFMA2 (sm_100) for the two half-chunk chains of diag_warp_tile.
                       // 0 = scalar FFMA (33.0 ms optimiser stage on the c5 bench), 1 = 4-byte cp.async into an interleaved
                       // SMEM layout so that pairs load directly (34.9 ms: the 4x LDGSTS count costs more than the MOVs it
-                      // saves), 2 = 16-byte ring, pairs formed in registers (32.4 ms)
+                      // saves), 2 = 16-byte ring, pairs formed in registers (32.4 ms), 3 = same with four quarter-chunk
+                      // chains (32.4 ms: the dependent-FMA depth is not the limiter either)
 #endif
 
 // fp32 variant of diag_warp_tile on PACKED pairs: y2[i] = (y[i], y[H + i]) holds one frame of each half-chunk, so
@@ -426,6 +430,81 @@ __device__ inline void diag_warp_tile_f2(const float2 (&y2)[L / 2], int nvalid, 
     }
     E2 += (double)(e2.x + e2.y);
     G += (double)(gg.x + gg.y);
+}
+
+// Quarter-chunk version of diag_warp_tile_f2: FOUR independent chains of L/4 frames (two FFMA2 streams), which
+// halves the dependent-FMA depth of phases 1 and 3 (the kernel is latency bound: ~50 % issue utilisation with six
+// warps per scheduler).  ya[i] = (y[i], y[Q+i]), yb[i] = (y[2Q+i], y[3Q+i]).
+template <int L, bool FULL, bool ACC>
+__device__ inline void diag_warp_tile_f4(const float2 (&ya)[L / 4], const float2 (&yb)[L / 4], int nvalid,
+                                         const ChanConst<float>& k, float a_lane, float b_lane, float& cm, float& cd,
+                                         double& E2, double& G) {
+    constexpr int Q = L / 4;
+    const int lane = threadIdx.x & 31;
+    const float alpha = k.alpha, gamma = k.gamma;
+    const float2 al2 = make_float2(alpha, alpha), ga2 = make_float2(gamma, gamma);
+    float2 Ua = make_float2(0.f, 0.f), Wa = Ua, Ub = Ua, Wb = Ua;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        Wa = __ffma2_rn(al2, Wa, Ua);
+        Wb = __ffma2_rn(al2, Wb, Ub);
+        Ua = __ffma2_rn(al2, Ua, ya[i]);
+        Ub = __ffma2_rn(al2, Ub, yb[i]);
+    }
+    const float2 Da = __ffma2_rn(ga2, Wa, Ua), Db = __ffma2_rn(ga2, Wb, Ub);   // zero-state (mt, dt) of the quarters
+    const float z0m = Ua.x, z1m = Ua.y, z2m = Ub.x, z3m = Ub.y;
+    const float z0d = Da.x, z1d = Da.y, z2d = Db.x, z3d = Db.y;
+    const float aQ = k.aQ, bQ = k.bQ, aH = k.aH, bH = k.bH;
+    // halves: Phi^Q z0 + z1 and Phi^Q z2 + z3; chunk: Phi^(2Q) (first half) + second half
+    const float h0m = fmaf(aQ, z0m, z1m), h0d = fmaf(aQ, z0d, fmaf(bQ, z0m, z1d));
+    const float h1m = fmaf(aQ, z2m, z3m), h1d = fmaf(aQ, z2d, fmaf(bQ, z2m, z3d));
+    float zm = fmaf(aH, h0m, h1m);
+    float zd = fmaf(aH, h0d, fmaf(bH, h0m, h1d));
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int d = 1 << q;
+        const float pm = __shfl_up_sync(0xffffffffu, zm, d);
+        const float pd = __shfl_up_sync(0xffffffffu, zd, d);
+        if (lane >= d) {
+            zd = fmaf(k.aL[q], pd, fmaf(k.bL[q], pm, zd));
+            zm = fmaf(k.aL[q], pm, zm);
+        }
+    }
+    float em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
+    if (lane == 0) { em = 0.f; ed = 0.f; }
+    const float tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);
+    const float cm0 = cm, cd0 = cd;
+    cm = fmaf(k.aW, cm0, tm);
+    cd = fmaf(k.aW, cd0, fmaf(k.bW, cm0, td));
+    if (!ACC) return;
+    // exact states at the start of the four quarters
+    const float m0 = fmaf(a_lane, cm0, em);
+    const float d0 = fmaf(a_lane, cd0, fmaf(b_lane, cm0, ed));
+    const float m1 = fmaf(aQ, m0, z0m), d1 = fmaf(aQ, d0, fmaf(bQ, m0, z0d));
+    const float m2 = fmaf(aH, m0, h0m), d2 = fmaf(aH, d0, fmaf(bH, m0, h0d));
+    const float m3 = fmaf(aQ, m2, z2m), d3 = fmaf(aQ, d2, fmaf(bQ, m2, z2d));
+    float2 ma = make_float2(m0, m1), da = make_float2(d0, d1), mb = make_float2(m2, m3), db = make_float2(d2, d3);
+    float2 e2a = make_float2(0.f, 0.f), ga = e2a, e2b = e2a, gb = e2a;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const float2 ea = __ffma2_rn(ga2, ma, ya[i]);
+        const float2 eb = __ffma2_rn(ga2, mb, yb[i]);
+        ma = __ffma2_rn(al2, ma, ya[i]);
+        mb = __ffma2_rn(al2, mb, yb[i]);
+        if (FULL) {
+            e2a = __ffma2_rn(ea, ea, e2a); ga = __ffma2_rn(ea, da, ga);
+            e2b = __ffma2_rn(eb, eb, e2b); gb = __ffma2_rn(eb, db, gb);
+        } else {
+            if (i < nvalid) { e2a.x = fmaf(ea.x, ea.x, e2a.x); ga.x = fmaf(ea.x, da.x, ga.x); }
+            if (Q + i < nvalid) { e2a.y = fmaf(ea.y, ea.y, e2a.y); ga.y = fmaf(ea.y, da.y, ga.y); }
+            if (2 * Q + i < nvalid) { e2b.x = fmaf(eb.x, eb.x, e2b.x); gb.x = fmaf(eb.x, db.x, gb.x); }
+            if (3 * Q + i < nvalid) { e2b.y = fmaf(eb.y, eb.y, e2b.y); gb.y = fmaf(eb.y, db.y, gb.y); }
+        }
+        da = __ffma2_rn(al2, da, ea);
+        db = __ffma2_rn(al2, db, eb);
+    }
+    E2 += (double)((e2a.x + e2a.y) + (e2b.x + e2b.y));
+    G += (double)((ga.x + ga.y) + (gb.x + gb.y));
 }
 
 // fp32 ring fill for the packed variant: 4-byte cp.async, element q of a lane's chunk lands in the interleaved slot
@@ -643,6 +722,23 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
                         y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
                     }
                 }
+            }
+            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 3) {   // 16-byte ring, four quarter-chunk chains
+                constexpr int Q = L / 4;
+                float2 ya[Q], yb[Q];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    ya[i] = make_float2((float)y[i], (float)y[Q + i]);
+                    yb[i] = make_float2((float)y[2 * Q + i], (float)y[3 * Q + i]);
+                }
+                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
+                float fcm = (float)cm, fcd = (float)cd;
+                if (!acc) diag_warp_tile_f4<L, true, false>(ya, yb, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else if (inner) diag_warp_tile_f4<L, true, true>(ya, yb, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
+                else diag_warp_tile_f4<L, false, true>(ya, yb, max(0, min(L, a.n - cstart)), kk, (float)a_lane,
+                                                       (float)b_lane, fcm, fcd, E2, G);
+                cm = (P)fcm; cd = (P)fcd;
+                continue;
             }
             if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 2) {   // 16-byte ring, pairs formed in registers
                 constexpr int H = L / 2;
