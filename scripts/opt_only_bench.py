@@ -19,3 +19,11 @@ it = res.iters.double()
 gb = it.sum().item() * 1e6 * 2 * 4 / 1e9
 print(json.dumps({'tag': os.environ.get('TAG', ''), 'ms': {k: round(v, 3) for k, v in ms.items()},
                   'opt_TBps': round(gb / ms['optimize_s'], 3), 'iters_mean': it.mean().item()}))
+# distribution of the Adam iteration counts: how many sequences are still active at each evaluation launch
+import numpy as np
+itn = res.iters.cpu().numpy().ravel()
+act = np.array([(itn > k).sum() for k in range(int(itn.max()))]) / itn.size
+print(json.dumps({'iters_min': int(itn.min()), 'iters_max': int(itn.max()),
+                  'quantiles_10_50_90': [int(np.percentile(itn, q)) for q in (10, 50, 90)],
+                  'launches_with_active_fraction_below': {str(f): int((act < f).sum()) for f in (0.9, 0.5, 0.25, 0.1)},
+                  'ideal_ms_if_time_proportional_to_active': round(float(act.sum()) / len(act) * 100, 1)}))
