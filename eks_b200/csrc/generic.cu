@@ -166,6 +166,7 @@ int nll_grad_impl(int B, int D, int O, int T, const void* m0, const void* S0, co
     a.ymean = (const P*)ymean; a.Rconst = (const P*)Rconst;
     if (fill_spans(T, n_spans, s0, s1, a.sp)) return -1;
     a.s = (const P*)s; a.nll_out = (P*)nll_out; a.dnll_out = (P*)dnll_out;
+    if (a.sp.total >= GEN_RUNS_MIN_FRAMES) return generic_runs_nll_grad<P>(a, st);
     return dispatch<P>(OP_NLL, a, st);
 }
 

@@ -75,6 +75,8 @@ __device__ inline void make_seq(const GArgs<P>& a, int b, SeqModel<P>& mdl, SeqO
 template <class P>
 int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t generic_runs_optimize_workspace_bytes(int dtype, int n_blocks, int B, int D, int T);
+template <class P>
+int generic_runs_nll_grad(const GArgs<P>& a, cudaStream_t st);
 size_t linear_steady_workspace_bytes(int dtype, int B, int D, int O, int T);
 template <class P>
 int generic_runs_smooth(const GArgs<P>& a, cudaStream_t st);

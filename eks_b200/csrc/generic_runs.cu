@@ -51,6 +51,7 @@ struct RunArgs {
     P* bnd_end;               // [B][nruns][ns]
     int* flag;                // smoother: boundary mismatch flag
     P tol;                    // boundary agreement tolerance
+    int probe;                // 1: evaluate once at the given a.s[b] and write nll / dnll (eks_nll_grad), no Adam
     double* part2;            // [B][nred][4]: per-256-run sums of part + boundary mismatch flag
     int nred;                 // ceil(nruns / RUNS_RED_NT)
 };
@@ -176,10 +177,16 @@ __global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __gri
     const int n = a.sp.total;
     if (first) {
         if (tid != 0) return;
-        adam_init(bs.adam, a.s_log0[j]);
-        bs.done = (a.cap <= 0);
         bs.redo = 0;
         bs.unverified = 0;
+        if (g.probe) {   // singleton blocks: block j = sequence j, d s / d log s = 1 so that grad = d nll / d s
+            bs.done = 0;
+            bs.s = a.s[j];
+            bs.dsdlog = P(1);
+            return;
+        }
+        adam_init(bs.adam, a.s_log0[j]);
+        bs.done = (a.cap <= 0);
         if (bs.done) { a.s_log_out[j] = bs.adam.s_log; a.last_loss_out[j] = bs.adam.prev; a.iters_out[j] = 0; return; }
         P dsdlog;
         bs.s = adam_current_s(bs.adam, a.lo, a.hi, &dsdlog);
@@ -218,6 +225,12 @@ __global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __gri
     if (tid != 0) return;
     if (!verified && !last_slot) {
         bs.redo += 1;   // same s again with longer warm-ups; no Adam step on an unverified loss
+        return;
+    }
+    if (g.probe) {
+        a.nll_out[j] = loss;
+        a.dnll_out[j] = grad;
+        bs.done = 1;
         return;
     }
     if (a.trace && bs.adam.iters < a.trace_cap) {
@@ -793,6 +806,7 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
     static_assert(sizeof(RunBlockState<P>) <= 128, "workspace bound");
     RunArgs<P> g;
     g.tol = runs_tol_host<P>();
+    g.probe = a.nll_out != nullptr;
     const int n = a.sp.total;
     g.nruns = runs_geometry(n, a.B, g.run_len);
     g.ns = 2 * (a.D + a.D * a.D);
@@ -845,6 +859,38 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
 }
 template int generic_runs_optimize<float>(const GArgs<float>&, void*, size_t, cudaStream_t);
 template int generic_runs_optimize<double>(const GArgs<double>&, void*, size_t, cudaStream_t);
+
+
+// eks_nll_grad for long sequences: one verified run-parallel evaluation per sequence at the given s (the machinery of
+// generic_runs_optimize with singleton blocks and no Adam step).  The scratch is stream-ordered (cudaMallocAsync).
+__global__ void runs_iota_kernel(int B, int* __restrict__ block_off, int* __restrict__ members) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= B) block_off[i] = i;
+    if (i < B) members[i] = i;
+}
+
+template <class P>
+int generic_runs_nll_grad(const GArgs<P>& a_in, cudaStream_t st) {
+    GArgs<P> a = a_in;
+    const int dtype = sizeof(P) == 4 ? EKS_F32 : EKS_F64;
+    const size_t ws_bytes = generic_runs_optimize_workspace_bytes(dtype, a.B, a.B, a.D, a.T) +
+                            (a.ncam == 0 ? linear_steady_workspace_bytes(dtype, a.B, a.D, a.O, a.T) : 0);
+    const size_t idx_bytes = ((size_t)(2 * a.B + 1) * sizeof(int) + 255) / 256 * 256;
+    unsigned char* buf = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&buf, ws_bytes + idx_bytes, st);
+    if (e != cudaSuccess) { set_error("nll_grad: scratch allocation failed: %s", cudaGetErrorString(e)); return (int)e; }
+    int* block_off = (int*)buf;
+    int* members = block_off + a.B + 1;
+    runs_iota_kernel<<<(a.B + 128) / 128, 128, 0, st>>>(a.B, block_off, members);
+    a.n_blocks = a.B; a.block_off = block_off; a.members = members;
+    a.s_log0 = nullptr; a.cap = 1; a.trace = nullptr; a.trace_cap = 0;
+    a.lr = P(1); a.lo = P(-8); a.hi = P(8); a.tol = P(0);
+    const int rc = generic_runs_optimize<P>(a, buf + idx_bytes, ws_bytes, st);
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+template int generic_runs_nll_grad<float>(const GArgs<float>&, cudaStream_t);
+template int generic_runs_nll_grad<double>(const GArgs<double>&, cudaStream_t);
 
 // =====================================================================================================
 // IBL pupil model (eks/ibl_pupil_smoother.py:363-607): 3 states [diameter, com_x, com_y], AR(1) dynamics

@@ -83,7 +83,9 @@ int eks_const_R_median(const void* var_base, long long seq_stride, const long lo
 
 /* NLL of the EKF filter and d NLL / d s for each sequence at s[b]: the loss of
  * _vmap_optimize_singletons._optimize_one.loss (eks/core.py:640-650) incl. the non-finite -> 1e12 rule.
- * Frames restricted to the spans (n_spans == 0: all).  nll_out, dnll_ds_out: [B] real. */
+ * Frames restricted to the spans (n_spans == 0: all).  nll_out, dnll_ds_out: [B] real.
+ * Sequences of 512 frames or more are evaluated run-parallel (verified, see eks_optimize_s); the scratch for that
+ * is taken from and returned to the stream's memory pool (cudaMallocAsync / cudaFreeAsync), the call stays async. */
 int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A, const void* Q,
                  const void* C, int ncam, const void* cams, const void* y_base, long long y_seq_stride,
                  const long long* y_chan_off_host, const void* ymean, const void* Rconst, int n_spans,

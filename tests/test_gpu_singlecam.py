@@ -201,8 +201,15 @@ def test_nll_grad_entry_point_matches_oracle():
         np.testing.assert_allclose(nll.double().cpu().numpy(), n_o, rtol=rtol)
         np.testing.assert_allclose(dn.double().cpu().numpy(), g_o, rtol=rtol * 20)
     cams = fly_cams()
+    for T in (400, 3000):     # sequential kernel / verified run-parallel evaluation (T >= 512)
+        _check_pinhole_nll_grad(cams, T, dev)
+
+
+def _check_pinhole_nll_grad(cams, T, dev):
+    from eks_b200 import ops
+    from eks_b200.ops import Model, PlaneView
+    from oracle import oracle
     rng = np.random.default_rng(1)
-    T = 400
     X = np.array([-1.75, -0.30, 3.5]) + np.cumsum(rng.standard_normal((T, 3)) * 1e-3, axis=0)
     y = oracle.project(cams, X) + rng.standard_normal((T, 6)) * 0.5
     m0, S0, A, Q = X[0] + 0.01, np.eye(3) * 1e-2, np.eye(3), np.diag([1e-6, 2e-6, 1.5e-6])
