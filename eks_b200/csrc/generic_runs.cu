@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(32) gen_nll_runs_kernel(const __grid_constant_
     bool ok = true;
     P* bs = g.bnd_start + ((long long)b * g.nruns + r) * g.ns;
     P* be = g.bnd_end + ((long long)b * g.nruns + r) * g.ns;
+    // (sector-wide grouped loads as in lin_runs_kernel were measured SLOWER here -- 0.85 -> 1.07 ms per evaluation for the
+    // pinhole model: the extra registers cost occupancy and this kernel is bound by its ~3000 dependent
+    // instructions per frame, not by L2 traffic)
     for (int i = start; i < t1; ++i) {
         if (i == t0) {  // state after warm-up = predicted state of the run's first frame
             for (int q = 0; q < D; ++q) { bs[q] = m[q].v; bs[D + D * D + q] = m[q].d; }
@@ -264,9 +267,12 @@ static int runs_geometry(int n, int B, int& run_len) {
     // The per-run work is a latency-bound sequential recursion, so the runs are made as short as the 64-frame
     // warm-up makes sensible (run_len >= 64: at most 2x the frames) until ~96k threads are in flight; beyond
     // that the runs grow and the warm-up overhead shrinks.
+    // (measured on B200, pinhole 6 x 5e5 frames: minimum run length 32 / 64 / 128 -> 1.20 / 0.85 / 1.01 ms per evaluation)
+    static int min_len = 0;
+    if (min_len == 0) { const char* e = getenv("EKS_RUNS_MINLEN"); min_len = e ? atoi(e) : 64; if (min_len < 32) min_len = 32; }
     int nruns = (98304 + B - 1) / B;
     run_len = (n + nruns - 1) / nruns;
-    if (run_len < 64) run_len = 64;
+    if (run_len < min_len) run_len = min_len;
     run_len = (run_len + 31) / 32 * 32;
     return (n + run_len - 1) / run_len;
 }
@@ -704,12 +710,8 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
     const P* pinf = l.pinf + (long long)b * g.ns;
     P* bs = g.bnd_start + ((long long)b * g.nruns + r) * g.ns;
     P* be = g.bnd_end + ((long long)b * g.nruns + r) * g.ns;
-    for (int i = start; i < t1; ++i) {
-        if (i == t0) {
-            for (int k = 0; k < g.ns; ++k) bs[k] = pinf[k];
-            for (int k = 0; k < D; ++k) { bs[k] = mu[k]; bs[D + D * D + k] = dmu[k]; }
-            q = P(0); dq = P(0);
-        }
+    // one frame of the mean recursion with the observations yv (not yet centred)
+    auto frame = [&](int i, const P* yv) {
         if (i < ntr) {
             const P* e = tab + (long long)i * l.ent;
 #pragma unroll
@@ -720,11 +722,10 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
             for (int k = 0; k < ENTC; ++k) if (k < O * ES) ent[k] = e[k];
             steady_loaded = true;
         }
-        const long long f = fm(i);
 #pragma unroll
         for (int c = 0; c < OC; ++c) {
             if (c < O) {
-                P y = ob.y_base[ob.y_off[c] + f];
+                P y = yv[c];
                 if (ob.ymean) y -= ob.ymean[c];
                 P e = y, de = P(0);
 #pragma unroll
@@ -749,6 +750,64 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
         }
 #pragma unroll
         for (int j = 0; j < DC; ++j) if (j < D) { mu[j] = nm[j]; dmu[j] = ndm[j]; }
+    };
+    // Each lane walks its own run, so a per-frame scalar load touches one 32-byte sector per lane and uses 4 bytes
+    // of it: 8x the useful L2 traffic (measured: 170 us per evaluation at 4 x 1e6 frames, L2-bound).  Fixed-size
+    // models therefore fetch G = 8 consecutive frames per channel with 16-byte loads (whole sectors, once).
+    constexpr int G = FIXED ? 32 / (int)sizeof(P) : 1;   // one 32-byte sector per channel
+    constexpr int VE = 16 / (int)sizeof(P);            // elements per 16-byte load
+    const bool contiguous = (a.sp.n == 1);
+    int i = start;
+    while (i < t1) {
+        if (i == t0) {
+            for (int k = 0; k < g.ns; ++k) bs[k] = pinf[k];
+            for (int k = 0; k < D; ++k) { bs[k] = mu[k]; bs[D + D * D + k] = dmu[k]; }
+            q = P(0); dq = P(0);
+        }
+        const long long f = fm(i);
+        bool grouped = false;
+        if (G > 1 && contiguous && i + G <= t1 && (i >= t0 || i + G <= t0)) {
+            bool aligned = true;
+#pragma unroll
+            for (int c = 0; c < OC; ++c)
+                if (c < O) aligned = aligned && ((reinterpret_cast<uintptr_t>(ob.y_base + ob.y_off[c] + f) & 15) == 0);
+            if (aligned) {
+                P yb[OC][G];
+#pragma unroll
+                for (int c = 0; c < OC; ++c) {
+                    if (c < O) {
+                        const P* p = ob.y_base + ob.y_off[c] + f;
+#pragma unroll
+                        for (int v4 = 0; v4 < G / VE; ++v4) {
+                            if (sizeof(P) == 4) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(p + v4 * VE);
+                                yb[c][v4 * VE + 0] = (P)w4.x; yb[c][v4 * VE + 1] = (P)w4.y;
+                                yb[c][v4 * VE + 2] = (P)w4.z; yb[c][v4 * VE + 3] = (P)w4.w;
+                            } else {
+                                const double2 w2 = *reinterpret_cast<const double2*>(p + v4 * VE);
+                                yb[c][v4 * VE + 0] = (P)w2.x; yb[c][v4 * VE + 1] = (P)w2.y;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    P yv[OC];
+#pragma unroll
+                    for (int c = 0; c < OC; ++c) if (c < O) yv[c] = yb[c][j];
+                    frame(i + j, yv);
+                }
+                i += G;
+                grouped = true;
+            }
+        }
+        if (!grouped) {
+            P yv[OC];
+#pragma unroll
+            for (int c = 0; c < OC; ++c) if (c < O) yv[c] = ob.y_base[ob.y_off[c] + f];
+            frame(i, yv);
+            i += 1;
+        }
     }
     for (int k = 0; k < g.ns; ++k) be[k] = pinf[k];
     for (int k = 0; k < D; ++k) { be[k] = mu[k]; be[D + D * D + k] = dmu[k]; }
