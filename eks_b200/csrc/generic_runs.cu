@@ -51,6 +51,7 @@ struct RunArgs {
     P* bnd_end;               // [B][nruns][ns]
     int* flag;                // smoother: boundary mismatch flag
     P tol;                    // boundary agreement tolerance
+    const P* lin_pinf;        // linear tabulated-gain path: [B][ns] covariance template; records hold (mu, dmu) only
     int probe;                // 1: evaluate once at the given a.s[b] and write nll / dnll (eks_nll_grad), no Adam
     double* part2;            // [B][nred][4]: per-256-run sums of part + boundary mismatch flag
     int nred;                 // ceil(nruns / RUNS_RED_NT)
@@ -138,6 +139,20 @@ __device__ inline bool runs_boundary_ok(const P* e, const P* s, int D, P sval, P
     return ok;
 }
 
+// compact records of the linear tabulated-gain path: (mu, dmu) only, the covariance is the same fixed point on both
+// sides (pinf = [0, P_inf, 0, dP_inf] supplies the scales)
+template <class P>
+__device__ inline bool runs_boundary_ok_lin(const P* e, const P* s, const P* pinf, int D, P sval, P tol) {
+    bool ok = true;
+    for (int i = 0; i < D; ++i) {
+        const P sd = sqrt_(fabs(pinf[D + i * D + i]) + P(1e-30));
+        ok = ok && (fabs(e[i] - s[i]) <= tol * sd + runs_ulp<P>() * fabs(e[i]));
+        const P dsc = fabs(e[D + i]) + sd / sval;
+        ok = ok && (fabs(e[D + i] - s[D + i]) <= P(10) * tol * dsc + runs_ulp<P>() * fabs(e[i]) / sval);
+    }
+    return ok;
+}
+
 // ---- verification + reduction: one thread per run compares its start record with the previous run's end record;
 // each CTA reduces 256 runs' partial sums in a fixed order.
 template <class P>
@@ -152,9 +167,15 @@ __global__ void __launch_bounds__(RUNS_RED_NT) gen_runs_reduce_kernel(const __gr
     double v = 0, dv = 0, bad = 0;
     if (r < g.nruns) {
         const int t0 = r * g.run_len;
-        if (r >= 1 && t0 < n && t0 - g.warm[b] > 0)   // runs that started at frame 0 are exact
-            ok = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
-                                     g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, g.bstate[blk].s, g.tol);
+        if (r >= 1 && t0 < n && t0 - g.warm[b] > 0) {   // runs that started at frame 0 are exact
+            if (g.lin_pinf)
+                ok = runs_boundary_ok_lin<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * 2 * a.D,
+                                             g.bnd_start + ((long long)b * g.nruns + r) * 2 * a.D,
+                                             g.lin_pinf + (long long)b * g.ns, a.D, g.bstate[blk].s, g.tol);
+            else
+                ok = runs_boundary_ok<P>(g.bnd_end + ((long long)b * g.nruns + r - 1) * g.ns,
+                                         g.bnd_start + ((long long)b * g.nruns + r) * g.ns, a.D, g.bstate[blk].s, g.tol);
+        }
         const double* p = g.part + ((long long)b * g.nruns + r) * 3;
         v = p[0]; dv = p[1]; bad = p[2];
     }
@@ -539,7 +560,7 @@ struct LinArgs {
 // one sequential-scalar-update covariance step on the predicted covariance Pm (dual), recording the gains
 template <class P, int DC, int OC, bool FIXED>
 __device__ inline bool lin_cov_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const P* rconst, Dual<P> s,
-                                    Dual<P>* Pm, P* ent, Dual<P>& lsum) {
+                                    Dual<P>* Pm, P* ent, Dual<P>& lsum, bool a_identity) {
     using S = Dual<P>;
     const int D = dm.D(), O = dm.O();
     bool ok = true;
@@ -585,6 +606,11 @@ __device__ inline bool lin_cov_step(const Dims<DC, OC, FIXED>& dm, const SeqMode
                 const S a = S(P(0.5)) * (Pm[i * D + j] + Pm[j * D + i]);
                 Pm[i * D + j] = a; Pm[j * D + i] = a;
             }
+    if (a_identity) {   // A = I (every multi-camera model of the reference): A P A^T is P itself, bit for bit
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = Pm[i] + s * S(mdl.Q[i]);
+        return ok;
+    }
     S AP[DC * DC];
 #pragma unroll
     for (int i = 0; i < DC; ++i)
@@ -609,6 +635,14 @@ __device__ inline bool lin_cov_step(const Dims<DC, OC, FIXED>& dm, const SeqMode
     return ok;
 }
 
+template <class P>
+__device__ inline bool is_identity(const P* A, int D) {
+    bool id = true;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) id = id && (A[i * D + j] == (i == j ? P(1) : P(0)));
+    return id;
+}
+
 template <class P, int DC, int OC, bool FIXED>
 __global__ void __launch_bounds__(32) lin_prep_kernel(const __grid_constant__ GArgs<P> a,
                                                       const __grid_constant__ RunArgs<P> g,
@@ -624,6 +658,7 @@ __global__ void __launch_bounds__(32) lin_prep_kernel(const __grid_constant__ GA
     SeqObs<P> ob;
     make_seq(a, b, mdl, ob, false);
     const S s(g.bstate[blk].s, P(1));
+    const bool a_id = is_identity<P>(mdl.A, D);
     S Pm[DC * DC];
 #pragma unroll
     for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = S(mdl.S0[i]);
@@ -641,7 +676,7 @@ __global__ void __launch_bounds__(32) lin_prep_kernel(const __grid_constant__ GA
 #pragma unroll
         for (int i = 0; i < DC * DC; ++i) if (i < D * D) { old_v[i] = Pm[i].v; old_d[i] = Pm[i].d; }
         S lsum;
-        ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)t * l.ent, lsum) && ok;
+        ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)t * l.ent, lsum, a_id) && ok;
         c0 += (double)(P(O) * HALF_LOG2PI) + 0.5 * (double)lsum.v;
         c1 += 0.5 * (double)lsum.d;
         // distance to the fixed point from the last two steps (geometric convergence), or the rounding floor
@@ -665,7 +700,7 @@ __global__ void __launch_bounds__(32) lin_prep_kernel(const __grid_constant__ GA
     for (int q = 0; q < D; ++q) { pinf[q] = P(0); pinf[D + D * D + q] = P(0); }
     for (int q = 0; q < D * D; ++q) { pinf[D + q] = Pm[q].v; pinf[2 * D + D * D + q] = Pm[q].d; }
     S lsum;
-    ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)l.ncap * l.ent, lsum) && ok;
+    ok = lin_cov_step<P, DC, OC, FIXED>(dm, mdl, ob.Rconst, s, Pm, tab + (long long)l.ncap * l.ent, lsum, a_id) && ok;
     const double rest = (double)(n - ntr);
     c0 += rest * ((double)(P(O) * HALF_LOG2PI) + 0.5 * (double)lsum.v);
     c1 += rest * 0.5 * (double)lsum.d;
@@ -701,15 +736,15 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
     for (int i = 0; i < OC * DC; ++i) if (i < O * D) Cm[i] = mdl.C[i];
 #pragma unroll
     for (int i = 0; i < DC * DC; ++i) if (i < D * D) Am[i] = mdl.A[i];
+    const bool a_id = is_identity<P>(mdl.A, D);
     P ent[ENTC];
     bool steady_loaded = false;
     P mu[DC], dmu[DC];
 #pragma unroll
     for (int i = 0; i < DC; ++i) if (i < D) { mu[i] = start == 0 ? mdl.m0[i] : P(0); dmu[i] = P(0); }
     P q = P(0), dq = P(0);
-    const P* pinf = l.pinf + (long long)b * g.ns;
-    P* bs = g.bnd_start + ((long long)b * g.nruns + r) * g.ns;
-    P* be = g.bnd_end + ((long long)b * g.nruns + r) * g.ns;
+    P* bs = g.bnd_start + ((long long)b * g.nruns + r) * 2 * D;   // compact records: (mu, dmu)
+    P* be = g.bnd_end + ((long long)b * g.nruns + r) * 2 * D;
     // one frame of the mean recursion with the observations yv (not yet centred)
     auto frame = [&](int i, const P* yv) {
         if (i < ntr) {
@@ -738,6 +773,7 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
                 for (int j = 0; j < DC; ++j) if (j < D) { mu[j] += en[j] * e; dmu[j] += en[D + j] * e + en[j] * de; }
             }
         }
+        if (a_id) return;        // A = I: mu, dmu unchanged by the prediction
         P nm[DC], ndm[DC];
 #pragma unroll
         for (int j = 0; j < DC; ++j) {
@@ -760,8 +796,7 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
     int i = start;
     while (i < t1) {
         if (i == t0) {
-            for (int k = 0; k < g.ns; ++k) bs[k] = pinf[k];
-            for (int k = 0; k < D; ++k) { bs[k] = mu[k]; bs[D + D * D + k] = dmu[k]; }
+            for (int k = 0; k < D; ++k) { bs[k] = mu[k]; bs[D + k] = dmu[k]; }
             q = P(0); dq = P(0);
         }
         const long long f = fm(i);
@@ -809,8 +844,7 @@ __global__ void __launch_bounds__(64) lin_runs_kernel(const __grid_constant__ GA
             i += 1;
         }
     }
-    for (int k = 0; k < g.ns; ++k) be[k] = pinf[k];
-    for (int k = 0; k < D; ++k) { be[k] = mu[k]; be[D + D * D + k] = dmu[k]; }
+    for (int k = 0; k < D; ++k) { be[k] = mu[k]; be[D + k] = dmu[k]; }
     double v = 0.5 * (double)q, dv = 0.5 * (double)dq, bad = 0;
     if (r == 0) { v += l.cnll[3 * b]; dv += l.cnll[3 * b + 1]; bad = l.cnll[3 * b + 2]; }
     part[0] = v; part[1] = dv; part[2] = bad;
@@ -866,6 +900,7 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
     RunArgs<P> g;
     g.tol = runs_tol_host<P>();
     g.probe = a.nll_out != nullptr;
+    g.lin_pinf = nullptr;
     const int n = a.sp.total;
     g.nruns = runs_geometry(n, a.B, g.run_len);
     g.ns = 2 * (a.D + a.D * a.D);
@@ -896,6 +931,7 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
         l.ncap = lin_table_cap(dtype, a.B, D, O, n);
         l.table = (P*)take((size_t)a.B * (l.ncap + 1) * l.ent * sizeof(P));
         l.pinf = (P*)take((size_t)a.B * g.ns * sizeof(P));
+        g.lin_pinf = l.pinf;
         l.ntr = (int*)take((size_t)a.B * sizeof(int));
         l.cnll = (double*)take((size_t)a.B * 3 * sizeof(double));
         if (D == 2 && O == 2) return lin_optimize_launch<P, 2, 2, true>(a, g, l, st);
