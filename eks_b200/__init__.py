@@ -20,6 +20,11 @@ from eks_b200.ibl_pupil_smoother import (  # noqa: F401
     fit_eks_pupil,
 )
 from eks_b200.marker_array import MarkerArray, input_dfs_to_markerArray  # noqa: F401
+from eks_b200.multicam_smoother import (  # noqa: F401
+    ensemble_kalman_smoother_multicam,
+    fit_eks_mirrored_multicam,
+    fit_eks_multicam,
+)
 from eks_b200.singlecam_smoother import (  # noqa: F401
     ensemble_kalman_smoother_singlecam,
     fit_eks_singlecam,

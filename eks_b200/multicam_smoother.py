@@ -426,3 +426,39 @@ def fit_eks_multicam(input_source, save_dir: str, bodypart_list: list | None = N
     if save_3d_outputs and calibration is not None:
         df_3d.to_csv(os.path.join(save_dir, 'multicam_3d_results.csv'))
     return camera_dfs, s_finals, input_dfs_list, bodypart_list, df_3d
+
+
+def fit_eks_mirrored_multicam(input_source, save_file: str, bodypart_list: list | None = None,
+                              smooth_param: float | list | None = None, s_frames: list | None = None,
+                              camera_names: list = [], quantile_keep_pca: float = 50.0, avg_mode: str = 'median',
+                              var_mode: str = 'confidence_weighted_var', inflate_vars: bool = False,
+                              n_latent: int = 3) -> tuple:
+    """Mirrored multi-camera data: every CSV holds all views, keypoints named '{bodypart}_{camera}'
+    (eks/multicam_smoother.py:37-153).  Splits the columns per camera, runs the multi-camera smoother and writes ONE
+    CSV whose keypoints carry the camera suffix again.  Returns (final_df, s_finals, input_dfs, bodypart_list)."""
+    from eks_b200.io import format_data
+    input_dfs_list, keypoint_names = format_data(input_source)
+    if bodypart_list is None:
+        bodypart_list = list(dict.fromkeys(name.split('_')[0] for name in keypoint_names))
+    per_camera = []
+    for cam in camera_names:
+        dfs = []
+        for df in input_dfs_list:
+            rename = {c: c.replace(f'_{cam}', '') for c in df.columns if f'_{cam}_' in c}
+            dfs.append(df[list(rename)].rename(columns=rename))
+        per_camera.append(dfs)
+    marker_array = input_dfs_to_markerArray(per_camera, bodypart_list, camera_names)
+    camera_dfs, s_finals, _ = ensemble_kalman_smoother_multicam(
+        marker_array=marker_array, keypoint_names=bodypart_list, smooth_param=smooth_param,
+        quantile_keep_pca=quantile_keep_pca, camera_names=camera_names, s_frames=s_frames, avg_mode=avg_mode,
+        var_mode=var_mode, inflate_vars=inflate_vars, n_latent=n_latent)
+    parts = []
+    for cam, cdf in zip(camera_names, camera_dfs):
+        cdf = cdf.copy()
+        cdf.columns = pd.MultiIndex.from_tuples([(sc, f'{kp}_{cam}', attr) for sc, kp, attr in cdf.columns],
+                                                names=cdf.columns.names)
+        parts.append(cdf)
+    final_df = pd.concat(parts, axis=1)
+    os.makedirs(os.path.dirname(save_file), exist_ok=True)
+    final_df.to_csv(save_file)
+    return final_df, s_finals, input_dfs_list, bodypart_list

@@ -185,3 +185,25 @@ def test_public_entry_point_with_inflation():
     np.testing.assert_allclose(s, ref['s_finals'], rtol=RTOL64)
     for c in range(2):
         _check(dfs[c].to_numpy().reshape(1200, 3, 9), ref['cam_out'][c], RTOL64, f'camera {c}')
+
+
+def test_fit_eks_mirrored_multicam(tmp_path):
+    """fit_eks_mirrored_multicam (reference eks/multicam_smoother.py:37-153): CSVs with '{bodypart}_{camera}' keypoints
+    are split per camera, smoothed, and written back as one CSV with the camera suffix restored."""
+    import pandas as pd
+    from eks_b200.marker_array import MarkerArray
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam, fit_eks_mirrored_multicam
+    from eks_b200.utils import make_dlc_pandas_index
+    raw = synth_multicam(M=3, V=2, K=2, T=900, seed=31)                    # (M,V,T,K,3)
+    cams, parts = ['top', 'bot'], ['paw1', 'paw2']
+    kps = [f'{p}_{c}' for c in cams for p in parts]
+    for m in range(3):
+        cols = np.concatenate([raw[m, v, :, k, :] for v in range(2) for k in range(2)], axis=1)
+        pd.DataFrame(cols, columns=make_dlc_pandas_index(kps)).to_csv(tmp_path / f'pred_rng={m}.csv')
+    out = tmp_path / 'out' / 'mirrored.csv'
+    final_df, s, dfs, bps = fit_eks_mirrored_multicam(str(tmp_path), str(out), camera_names=cams, smooth_param=3.0)
+    assert bps == parts and out.exists() and final_df.shape == (900, 2 * 2 * 9)
+    assert [c[1] for c in final_df.columns[::9]] == ['paw1_top', 'paw2_top', 'paw1_bot', 'paw2_bot']
+    ref_dfs, _, _ = ensemble_kalman_smoother_multicam(MarkerArray(raw.astype(np.float32), data_fields=['x', 'y', 'likelihood']),
+                                                      parts, cams, smooth_param=3.0)
+    np.testing.assert_allclose(final_df.to_numpy(), np.concatenate([d.to_numpy() for d in ref_dfs], axis=1), rtol=1e-6)
