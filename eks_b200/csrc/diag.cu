@@ -18,6 +18,7 @@
 //   * NLL = n/2 log 2pi + 1/2 sum log S_t + 1/2 sum e_t^2 / S_t, its derivative likewise; partial
 //     sums are kept in fp64 so that the reference's relative-tolerance stop rule stays meaningful
 //     at 10^6 frames even in float32 mode.
+#include <cstdlib>
 #include "common.cuh"
 #include "ekf_generic.cuh"
 #include "diag.cuh"
@@ -27,6 +28,11 @@ namespace eks {
 
 constexpr int DIAG_NT = 256;
 constexpr int DIAG_NW = DIAG_NT / 32;
+#ifndef EKS_OPT_NW
+#define EKS_OPT_NW 8     // warps per CTA of diag_nll_kernel (each warp = one independent run of warp-tiles)
+#endif
+constexpr int OPT_NW = EKS_OPT_NW, OPT_NT = 32 * OPT_NW;
+constexpr int OPT_NSEG_MAX = 16 * 8 / OPT_NW;   // at most 128 runs per (sequence, channel)
 
 template <class P> struct DiagTraits;
 template <> struct DiagTraits<float> {
@@ -115,6 +121,7 @@ struct DiagOptArgs {
     double* partials;            // [B][2][nseg][2]  (sum e^2, sum e dm) per segment
     int* n_active;
     int* block_counter;          // [n_blocks] CTAs of the current evaluation that have finished
+    int blk_lo, blk_hi;          // this launch evaluates the blocks in [blk_lo, blk_hi) only
 };
 
 __device__ inline void cp_async_16(void* smem, const void* gmem, int src_bytes) {
@@ -358,6 +365,9 @@ __device__ inline void diag_warp_tile(const P (&y)[L], int nvalid, const ChanCon
     G += (double)(ga + gb);
 }
 
+#ifndef EKS_EARLY_ISSUE
+#define EKS_EARLY_ISSUE 1
+#endif
 #ifndef EKS_L2_PREFETCH
 #define EKS_L2_PREFETCH 0   // warp-tiles of look-ahead for an L2 prefetch of the observation stream (0 = off).
                             // Measured on the c5 bench: 2 -> 35.4 ms, 4 -> 37.4 ms, 8 -> 45.0 ms against 32.4 ms without:
@@ -586,9 +596,9 @@ __device__ inline void warp_issue_tile(unsigned char* stage, const P* __restrict
 // initial state geometrically (alpha^warm < 1e-14 / 1e-28).  Warps never synchronise with each other until
 // the final reduction; each streams its own 2-stage cp.async ring.
 template <class P>
-__global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
+__global__ void __launch_bounds__(OPT_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
     __shared__ ChanConst<P> shk;
-    __shared__ double red[DIAG_NW][2];
+    __shared__ double red[OPT_NW][2];
     extern __shared__ __align__(16) unsigned char ring[];
     constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
     constexpr int WT = 32 * L;  // frames per warp-tile
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
     constexpr int VW = DiagTraits<P>::VW;
     const int seg = blockIdx.x, b = blockIdx.y >> 1, c = blockIdx.y & 1;
     const int blk = a.seq_block[b];
-    if (blk < 0 || a.bstate[blk].done) return;
+    if (blk < a.blk_lo || blk >= a.blk_hi || a.bstate[blk].done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
     double* part = a.partials + (((long long)b * 2 + c) * a.nseg + seg) * 2;
@@ -605,9 +615,9 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
     __syncthreads();
     // this warp's run of warp-tiles
     const int nwt = (a.n - t_c + WT - 1) / WT;
-    const int nrun = a.nseg * DIAG_NW;
+    const int nrun = a.nseg * OPT_NW;
     const int wpr = (nwt + nrun - 1) / nrun;
-    const int run = seg * DIAG_NW + warp;
+    const int run = seg * OPT_NW + warp;
     const int wt_lo = min(nwt, run * wpr), wt_hi = min(nwt, wt_lo + wpr);
     double E2 = 0, G = 0;
     if (wt_lo < wt_hi) {
@@ -649,17 +659,23 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
             }
 #endif
         };
+        // EKS_EARLY_ISSUE: a stage is free as soon as its tile sits in registers, i.e. BEFORE the arithmetic on that
+        // tile.  Refilling it there (tile it+2) keeps two tiles outstanding per warp during the arithmetic instead of
+        // one -- twice the bytes in flight from the same shared memory (the ring already fills the SM).
+        constexpr bool EARLY = (EKS_EARLY_ISSUE != 0) && (OPT_STAGES == 2) && !(sizeof(P) == 4 && EKS_FFMA2 == 1);
 #pragma unroll
-        for (int st = 0; st < OPT_STAGES - 1; ++st) {
+        for (int st = 0; st < (EARLY ? OPT_STAGES : OPT_STAGES - 1); ++st) {
             if (st < nt) issue(st, first_wt + st);
             cp_async_commit();
         }
         for (int it = 0; it < nt; ++it) {
-            const int nx = it + OPT_STAGES - 1;
-            // the stage about to be refilled was read in iteration it-1; make sure every lane is done with it
-            __syncwarp();
-            if (nx < nt) issue(nx % OPT_STAGES, first_wt + nx);
-            cp_async_commit();
+            if (!EARLY) {
+                const int nx = it + OPT_STAGES - 1;
+                // the stage about to be refilled was read in iteration it-1; make sure every lane is done with it
+                __syncwarp();
+                if (nx < nt) issue(nx % OPT_STAGES, first_wt + nx);
+                cp_async_commit();
+            }
             cp_async_wait<OPT_STAGES - 1>();
             __syncwarp();  // tile `it` has landed for every lane of this warp
             const unsigned char* mine = wring + (it % OPT_STAGES) * WRP_STAGE_BYTES + lane * OPT_PAD_BYTES;
@@ -723,6 +739,11 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
                     }
                 }
             }
+            if (EARLY) {   // tile `it` is in registers: refill its stage with tile it+2 before the arithmetic
+                __syncwarp();
+                if (it + 2 < nt) issue(it % OPT_STAGES, first_wt + it + 2);
+                cp_async_commit();
+            }
             if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 3) {   // 16-byte ring, four quarter-chunk chains
                 constexpr int Q = L / 4;
                 float2 ya[Q], yb[Q];
@@ -767,7 +788,7 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(co
     __shared__ int is_last;
     if (threadIdx.x == 0) {
         double te = 0, tg = 0;
-        for (int w = 0; w < DIAG_NW; ++w) { te += red[w][0]; tg += red[w][1]; }
+        for (int w = 0; w < OPT_NW; ++w) { te += red[w][0]; tg += red[w][1]; }
         part[0] = te;
         part[1] = tg;
         // the CTA that completes its block's evaluation takes the Adam step and prepares the next evaluation
@@ -890,8 +911,8 @@ static int diag_nseg(int dtype, int n, int B) {
     const int nwt = (n + 32 * L - 1) / (32 * L);
     int best = 1;
     double best_eff = -1.0;
-    for (int nseg = 1; nseg <= 16; ++nseg) {
-        const int run = (nwt + nseg * DIAG_NW - 1) / (nseg * DIAG_NW);  // warp-tiles per run
+    for (int nseg = 1; nseg <= OPT_NSEG_MAX; ++nseg) {
+        const int run = (nwt + nseg * OPT_NW - 1) / (nseg * OPT_NW);  // warp-tiles per run
         if (run < 1 || (nseg > 1 && run < 2)) break;
         const double waves = (double)nseg * 2.0 * B / slots;
         const double wave_eff = waves / ceil(waves);
@@ -904,7 +925,7 @@ static int diag_nseg(int dtype, int n, int B) {
 size_t diag_optimize_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     const size_t real = dtype == EKS_F32 ? 4 : 8;
     (void)real;
-    const int nseg = 16;  // upper bound of diag_nseg
+    const int nseg = OPT_NSEG_MAX;  // upper bound of diag_nseg
     size_t bytes = 256;
     bytes += (size_t)n_blocks * 128;                   // BlockState
     bytes += (size_t)B * 2 * 1024;                     // ChanState (generous bound)
@@ -930,7 +951,7 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     a.seq_block = seq_block;
     a.block_counter = (int*)w;
     cudaMemsetAsync(a.block_counter, 0, (size_t)a.n_blocks * sizeof(int), st);
-    const int smem = DIAG_NW * OPT_STAGES * WRP_STAGE_BYTES;
+    const int smem = OPT_NW * OPT_STAGES * WRP_STAGE_BYTES;
     cudaError_t e = cudaFuncSetAttribute(diag_nll_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         set_error("diag_nll_kernel: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -943,8 +964,45 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     // runs inside the streaming kernel (last CTA of each block).  The loop is unrolled on the stream without
     // host synchronisation: finished blocks make their CTAs exit immediately.
     const dim3 grid(a.nseg, 2 * a.B);
+    a.blk_lo = 0; a.blk_hi = a.n_blocks;
     diag_adam_kernel<P><<<a.n_blocks, 32, 0, st>>>(a);
-    for (int it = 0; it < a.cap; ++it) diag_nll_kernel<P><<<grid, DIAG_NT, smem, st>>>(a);
+    // The blocks are independent optimisation problems, but launches on one stream serialise them: every evaluation
+    // would end with a drain of the whole GPU (measured: a full launch streams 5.5 TB/s on its own, the loop
+    // averaged 4.8 TB/s).  The blocks are therefore split over EKS_OPT_STREAMS internal streams whose launches
+    // overlap: while one group's evaluation drains, the other group's fills the SMs.
+    static int n_streams = -1;
+    static cudaStream_t hs[4];
+    if (n_streams < 0) {
+        const char* e2 = getenv("EKS_OPT_STREAMS");
+        n_streams = e2 ? atoi(e2) : 2;
+        if (n_streams < 1) n_streams = 1;
+        if (n_streams > 4) n_streams = 4;
+        for (int i = 0; i < n_streams; ++i)
+            if (cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking) != cudaSuccess) { n_streams = 1; break; }
+    }
+    const int ns = (a.n_blocks >= 2 * n_streams) ? n_streams : 1;
+    if (ns == 1) {
+        for (int it = 0; it < a.cap; ++it) diag_nll_kernel<P><<<grid, OPT_NT, smem, st>>>(a);
+        return check_launch("diag optimise kernels");
+    }
+    cudaEvent_t fork, join[4];
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    cudaEventRecord(fork, st);
+    DiagOptArgs<P> ai[4];
+    for (int i = 0; i < ns; ++i) {
+        cudaStreamWaitEvent(hs[i], fork, 0);
+        ai[i] = a;
+        ai[i].blk_lo = (int)((long long)a.n_blocks * i / ns);
+        ai[i].blk_hi = (int)((long long)a.n_blocks * (i + 1) / ns);
+    }
+    for (int it = 0; it < a.cap; ++it)
+        for (int i = 0; i < ns; ++i) diag_nll_kernel<P><<<grid, OPT_NT, smem, hs[i]>>>(ai[i]);
+    for (int i = 0; i < ns; ++i) {
+        cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming);
+        cudaEventRecord(join[i], hs[i]);
+    }
+    for (int i = 0; i < ns; ++i) { cudaStreamWaitEvent(st, join[i], 0); cudaEventDestroy(join[i]); }
+    cudaEventDestroy(fork);
     return check_launch("diag optimise kernels");
 }
 

@@ -6,6 +6,7 @@ stream and returns device tensors.  Nothing here computes on the CPU.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -187,7 +188,10 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
     diag = structure == STRUCT_DIAG and D == 2 and O == 2 and model.ncam == 0 and n <= 1
     runs = (not diag) and T >= 512     # verified run-parallel generic path: (NLL + Adam) per evaluation slot
     per_slot = 4 if model.ncam == 0 else 3   # (prep,) runs, verify/reduce, Adam
-    _count(2 + int(safety_cap) if diag else (2 + per_slot * (int(safety_cap) + 12) if runs else 1))
+    n_streams = max(1, min(4, int(os.environ.get('EKS_OPT_STREAMS', '2'))))   # internal streams of the decoupled path
+    if nb < 2 * n_streams:
+        n_streams = 1
+    _count(2 + n_streams * int(safety_cap) if diag else (2 + per_slot * (int(safety_cap) + 12) if runs else 1))
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
 
