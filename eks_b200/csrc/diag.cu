@@ -970,16 +970,24 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     // would end with a drain of the whole GPU (measured: a full launch streams 5.5 TB/s on its own, the loop
     // averaged 4.8 TB/s).  The blocks are therefore split over EKS_OPT_STREAMS internal streams whose launches
     // overlap: while one group's evaluation drains, the other group's fills the SMs.
-    static int n_streams = -1;
-    static cudaStream_t hs[4];
-    if (n_streams < 0) {
+    static int n_streams_dev[64];
+    static cudaStream_t hs_dev[64][4];
+    static bool hs_init[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!hs_init[dev]) {   // internal streams belong to the device that is current at first use (one table per device)
         const char* e2 = getenv("EKS_OPT_STREAMS");
-        n_streams = e2 ? atoi(e2) : 2;
-        if (n_streams < 1) n_streams = 1;
-        if (n_streams > 4) n_streams = 4;
-        for (int i = 0; i < n_streams; ++i)
-            if (cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking) != cudaSuccess) { n_streams = 1; break; }
+        int nsd = e2 ? atoi(e2) : 2;
+        if (nsd < 1) nsd = 1;
+        if (nsd > 4) nsd = 4;
+        for (int i = 0; i < nsd; ++i)
+            if (cudaStreamCreateWithFlags(&hs_dev[dev][i], cudaStreamNonBlocking) != cudaSuccess) { nsd = 1; break; }
+        n_streams_dev[dev] = nsd;
+        hs_init[dev] = true;
     }
+    const int n_streams = n_streams_dev[dev];
+    cudaStream_t* hs = hs_dev[dev];
     const int ns = (a.n_blocks >= 2 * n_streams) ? n_streams : 1;
     if (ns == 1) {
         for (int it = 0; it < a.cap; ++it) diag_nll_kernel<P><<<grid, OPT_NT, smem, st>>>(a);
