@@ -334,7 +334,7 @@ def run_b200(args):
     pipeline_frac = (kf_step * b_alg / (ms_step * 1e-3) / 1e9) / peak
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline is a rank-0, N = 1 leg (torchrun pins OMP to one thread)
         cpu = cpu_leg(M, K, min(args.cpu_frames, T), 1, 0)
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
