@@ -988,9 +988,15 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     }
     const int n_streams = n_streams_dev[dev];
     cudaStream_t* hs = hs_dev[dev];
-    const int ns = (a.n_blocks >= 2 * n_streams) ? n_streams : 1;
+    // small problems (less than two waves of CTAs per evaluation) are launch bound: a second stream only doubles
+    // the number of no-op launches after convergence
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool big = (long long)a.nseg * 2 * a.B >= 2LL * sms * EKS_OPT_MINBLOCKS;
+    const int ns = (a.n_blocks >= 2 * n_streams && big) ? n_streams : 1;
     if (ns == 1) {
         for (int it = 0; it < a.cap; ++it) diag_nll_kernel<P><<<grid, OPT_NT, smem, st>>>(a);
+        note_launches(2 + a.cap);
         return check_launch("diag optimise kernels");
     }
     cudaEvent_t fork, join[4];
@@ -1011,6 +1017,7 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     }
     for (int i = 0; i < ns; ++i) { cudaStreamWaitEvent(st, join[i], 0); cudaEventDestroy(join[i]); }
     cudaEventDestroy(fork);
+    note_launches(2 + ns * a.cap);
     return check_launch("diag optimise kernels");
 }
 

@@ -11,6 +11,8 @@
 namespace eks {
 
 static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+void note_launches(int n) { g_launches = n; }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -192,6 +194,7 @@ int optimize_impl(int B, int D, int O, int T, const void* m0, const void* S0, co
     a.trace = (P*)trace; a.trace_cap = trace_cap;
     // long sequences: verified run-parallel execution (generic_runs.cu); short ones: one thread per block
     if (a.sp.total >= GEN_RUNS_MIN_FRAMES) return generic_runs_optimize<P>(a, workspace, workspace_bytes, st);
+    note_launches(1);
     return dispatch<P>(OP_OPT, a, st);
 }
 
@@ -225,6 +228,7 @@ int smooth_impl(int B, int D, int O, int T, const void* m0, const void* S0, cons
 using namespace eks;
 
 extern "C" const char* eks_last_error(void) { return g_err; }
+extern "C" int eks_last_launch_count(void) { return g_launches; }
 extern "C" int eks_version(void) { return 100; }
 
 extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,

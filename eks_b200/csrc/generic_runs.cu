@@ -336,6 +336,7 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
         for (int b = 0; b < a.B && b < 16; ++b) fprintf(stderr, " %d", w[b]);
         fprintf(stderr, "\n");
     }
+    note_launches(1 + 3 * slots);
     return check_launch("generic run-parallel optimise kernels");
 }
 
@@ -893,6 +894,7 @@ static int lin_optimize_launch(const GArgs<P>& a, RunArgs<P> g, const LinArgs<P>
         for (int b = 0; b < a.B && b < 16; ++b) fprintf(stderr, " (%d, %d)", w[b], nt[b]);
         fprintf(stderr, "\n");
     }
+    note_launches(1 + 4 * slots);
     return check_launch("linear steady-state optimise kernels");
 }
 

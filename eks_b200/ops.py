@@ -183,15 +183,7 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                ptr(s_log0), float(lr), float(s_bounds_log[0]), float(s_bounds_log[1]), float(tol),
                                int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
                                int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
-    # decoupled path: block-table + Adam-init kernels, then one NLL launch per allowed evaluation (launches of
-    # already converged blocks exit immediately); generic path: one persistent kernel
-    diag = structure == STRUCT_DIAG and D == 2 and O == 2 and model.ncam == 0 and n <= 1
-    runs = (not diag) and T >= 512     # verified run-parallel generic path: (NLL + Adam) per evaluation slot
-    per_slot = 4 if model.ncam == 0 else 3   # (prep,) runs, verify/reduce, Adam
-    n_streams = max(1, min(4, int(os.environ.get('EKS_OPT_STREAMS', '2'))))   # internal streams of the decoupled path
-    if nb < 2 * n_streams:
-        n_streams = 1
-    _count(2 + n_streams * int(safety_cap) if diag else (2 + per_slot * (int(safety_cap) + 12) if runs else 1))
+    _count(int(lib().eks_last_launch_count()))   # the library reports what this call enqueued
     return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
 
 

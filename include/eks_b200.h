@@ -36,6 +36,8 @@ extern "C" {
 
 const char* eks_last_error(void);
 int eks_version(void);
+/* Number of kernels the most recent eks_optimize_s call of this thread enqueued (bench.py's gpu_launches). */
+int eks_last_launch_count(void);
 
 /* ---- ensemble statistics: replaces eks.core.ensemble / compute_stats (eks/core.py:25-101) --------
  * raw: [n_sessions][M][V][T][K][3] in the reference MarkerArray layout (eks/marker_array.py:15-30),
