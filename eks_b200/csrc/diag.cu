@@ -51,7 +51,7 @@ template <> struct DiagTraits<double> {
 template <class P>
 struct ChanConst {
     P alpha, beta, a, cc, dalpha, dbeta, iS, diS, logS, dlogS;
-    P gamma;         // -c beta: coupling of the scaled recursion (see diag_tile)
+    P gamma;         // -c beta: coupling of the scaled recursion (see diag_warp_tile)
     P aL[5], bL[5];  // Phi^(L 2^k) = [[aL,0],[bL,aL]]
     P aW, bW;        // Phi^(32 L)
     P aH, bH;        // Phi^(L/2)
@@ -72,7 +72,6 @@ constexpr int OPT_PAD_BYTES = 144;
 #define EKS_OPT_RELOAD 0
 #endif
 constexpr int OPT_STAGES = EKS_OPT_STAGES;
-constexpr int OPT_STAGE_BYTES = DIAG_NT * OPT_PAD_BYTES;
 
 // ---- device-resident optimiser state -----------------------------------------------------------------
 template <class P>
@@ -90,14 +89,6 @@ struct ChanState {           // one per (sequence, channel): produced by diag_ad
     double tsum[5];          // transient sums: logS, dlogS, e2 iS, e2 diS, cc e dm iS
     int t_c;                 // first steady-state frame (multiple of 4)
     int warm;                // frames after which a zero carry-in is forgotten below rounding
-};
-
-template <class P>
-struct OptShared {
-    ChanConst<P> ch;
-    P z_tile[2][2];        // [buf][m,dm]
-    P agg[2][DIAG_NW][2];  // [buf][warp][m,dm]
-    double red[DIAG_NW][2];
 };
 
 template <class P>
@@ -140,52 +131,6 @@ __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\
 template <int N>
 __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Issue the asynchronous copy of frames [t0, t0 + DIAG_NT*L) of one plane into a ring stage; frames
-// outside [e_min, n) are zero-filled without touching memory.  Consecutive lanes fetch consecutive
-// 16-byte granules (fully coalesced 512-byte requests); the destination is the padded per-thread chunk
-// layout (conflict-free 16-byte reads at stride 144 B).
-template <class P>
-__device__ inline void opt_issue_tile(unsigned char* stage, const P* __restrict__ plane, int t0, int e_min, int n,
-                                      bool vec) {
-    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    if (vec) {
-        constexpr int EPG = 16 / (int)sizeof(P);       // elements per 16-byte granule
-        constexpr int GPC = OPT_CHUNK_BYTES / 16;      // granules per chunk
-#pragma unroll
-        for (int i = 0; i < GPC; ++i) {
-            const int v = i * DIAG_NT + threadIdx.x;
-            const int j = v / GPC, q = v - j * GPC;
-            const int e = t0 + j * L + q * EPG;
-            int valid = max(0, min(EPG, n - e)) * (int)sizeof(P);
-            if (e < e_min) valid = 0;                  // e_min is chunk aligned: whole granules
-            cp_async_16(stage + j * OPT_PAD_BYTES + q * 16, plane + (valid > 0 ? e : 0), valid);
-        }
-    } else {
-#pragma unroll 4
-        for (int i = 0; i < L; ++i) {
-            const int v = i * DIAG_NT + threadIdx.x;
-            const int j = v / L, q = v - j * L;
-            const int e = t0 + j * L + q;
-            const int valid = (e < n && e >= e_min) ? (int)sizeof(P) : 0;
-            if (sizeof(P) == 4) cp_async_4(stage + j * OPT_PAD_BYTES + q * 4, plane + (valid > 0 ? e : 0), valid);
-            else cp_async_8(stage + j * OPT_PAD_BYTES + q * 8, plane + (valid > 0 ? e : 0), valid);
-        }
-    }
-}
-
-// Fast path of opt_issue_tile for a tile that lies completely inside [e_min, n) and is 16-byte aligned:
-// granule i of this thread sits at constant offsets from two per-thread bases (no masks, no index math).
-template <class P>
-__device__ inline void opt_issue_tile_fast(unsigned char* stage_thread, const P* __restrict__ tile_thread) {
-    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    constexpr int GPC = OPT_CHUNK_BYTES / 16;
-    constexpr int CPI = DIAG_NT / GPC;  // chunks covered by one round of DIAG_NT granules
-#pragma unroll
-    for (int i = 0; i < GPC; ++i) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(stage_thread + i * CPI * OPT_PAD_BYTES);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(tile_thread + i * CPI * L) : "memory");
-    }
-}
 
 // ---- transient: sequential scalar filter with s-sensitivities until the variance recursion has reached
 // its floating-point fixed point (or the sequence ends).  One thread per (sequence, channel).
