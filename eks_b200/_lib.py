@@ -55,6 +55,7 @@ _SIGS = {
                                   c_void_p]),
 }
 _OPTIONAL_SIGS = {
+    'eks_triangulate_mean': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'eks_last_launch_count': (c_int, []),
     'eks_mc_valid_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_double, c_double,

@@ -336,10 +336,15 @@ def ensemble_kalman_smoother_multicam(
 
     nonlinear = camgroup is not None
     if nonlinear:
-        tri = triangulate_3d_models(marker_array, camgroup)
-        ys_3d = tri.mean(axis=0)
-        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_geometric(ys_3d)
         h_fn, _ = make_projection_from_camgroup(camgroup)
+        # triangulate_3d_models(...).mean(axis=0) on the device (eks_triangulate_mean): one thread per
+        # (keypoint, frame) instead of M*K host calls into OpenCV
+        raw_dev = torch.as_tensor(np.ascontiguousarray(marker_array.slice_fields('x', 'y', 'likelihood').array
+                                                       if list(marker_array.data_fields) != ['x', 'y', 'likelihood']
+                                                       else marker_array.array)).to(dev)
+        ys_3d = ops.triangulate_mean(raw_dev, torch.as_tensor(np.asarray(h_fn.cams, dtype=np.float64))).cpu().numpy()
+        del raw_dev
+        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_geometric(ys_3d)
         ys = np.stack([mA_to_stacked_array(emA_unsm, k) for k in range(K)])          # un-centred (:392-405)
         ens_vars = np.stack([mA_to_stacked_array(emA_inflated, k) for k in range(K)])
         D = 3

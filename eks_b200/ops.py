@@ -332,3 +332,16 @@ def mc_inflate_step(y: PlaneView, ymean: torch.Tensor, var: PlaneView, T: int, l
                                     stream_ptr()), 'eks_mc_inflate_step')
     _count(1)
     return flags
+
+
+def triangulate_mean(raw: torch.Tensor, cams: torch.Tensor) -> torch.Tensor:
+    """raw (M,V,T,K,3) device tensor (pixels), cams (V,29) float64 -> (K,T,3) float64: mean over the ensemble of
+    the triangulated points (triangulate_3d_models(...).mean(axis=0))."""
+    assert raw.is_cuda and raw.is_contiguous() and raw.dim() == 5 and raw.shape[-1] == 3
+    M, V, T, K, _ = raw.shape
+    cams = cams.to(device=raw.device, dtype=torch.float64).contiguous()
+    out = torch.empty((K, T, 3), dtype=torch.float64, device=raw.device)
+    check(lib().eks_triangulate_mean(ptr(raw), dt_code(raw.dtype), M, V, T, K, ptr(cams), ptr(out), stream_ptr()),
+          'eks_triangulate_mean')
+    _count(1)
+    return out

@@ -217,6 +217,15 @@ int eks_mc_inflate_step(int dtype, int B, int V, int L, int T, const void* y_bas
                         const long long* var_chan_off_host, const double* loading, const double* mean, double epsilon,
                         double threshold, double scalar, const int* active, int* flags_out, void* stream);
 
+/* Triangulation of the calibrated multi-camera path: triangulate_3d_models(...).mean(axis=0)
+ * (eks/multicam_smoother.py:888-911, :385-386; aniposelib CameraGroup.triangulate(fast=True) restated as
+ * cv2.undistortPoints + pairwise cv2.triangulatePoints + nan-median over the camera pairs).
+ * raw: the (M, V, T, K, 3) seed predictions (pixels; float or double), cams [V][EKS_CAM_STRIDE] DOUBLE camera
+ * parameters (same packing as the pinhole emission), out [K][T][3] double = mean over the M ensemble members of the
+ * triangulated points.  fp64 arithmetic. */
+int eks_triangulate_mean(const void* raw, int raw_dtype, int M, int V, int T, int K, const double* cams, double* out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,12 @@ static void adam_any(int n, const P* loss, const P* g, P s_log0, P lr, P tol, in
 
 HOSTCHECK_API(f32, float)
 HOSTCHECK_API(f64, double)
+
+// ---- triangulation templates (triangulate.cuh) on the host: compared with cv2 in tests/test_host.py
+#include "../../eks_b200/csrc/triangulate.cuh"
+extern "C" void hc_undistort(const double* cam, int n, const double* uv, double* out) {
+    for (int i = 0; i < n; ++i) undistort_point(cam, uv[2 * i], uv[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+extern "C" void hc_triangulate_points(const double* cams, int V, int n, const double* uv /*[n][2V]*/, double* X /*[n][3]*/) {
+    for (int i = 0; i < n; ++i) triangulate_point(cams, V, uv + (size_t)i * 2 * V, X + (size_t)i * 3);
+}

@@ -261,3 +261,39 @@ def test_fast_csv_reader_equals_pandas_path(tmp_path, monkeypatch):
     for a, b in zip(fast, slow):
         assert list(a.columns) == list(b.columns) and (a.index == b.index).all()
         np.testing.assert_array_equal(a.to_numpy(), b.to_numpy())
+
+
+def test_triangulation_templates_match_opencv():
+    """The device triangulation (triangulate.cuh, compiled for the host) against the OpenCV primitives of the host
+    mirror: cv2.undistortPoints, and CameraGroup.triangulate = pairwise cv2.triangulatePoints + nan-median."""
+    import ctypes
+    import cv2
+    from eks_b200.multicam_smoother import CameraGroup, make_projection_from_camgroup
+    from oracle import oracle
+    hc = ctypes.CDLL(os.path.join(ROOT, 'tests', 'hostcheck', 'libhostcheck.so'))
+    cg = CameraGroup.load(os.path.join(ROOT, 'tests', 'golden', 'fly_calibration.toml'))
+    cams = np.ascontiguousarray(make_projection_from_camgroup(cg)[0].cams, dtype=np.float64)     # (V,29)
+    V = cams.shape[0]
+    rng = np.random.default_rng(0)
+    n = 400
+    X = np.array([-1.75, -0.30, 3.5]) + rng.normal(0, 0.05, (n, 3))
+    uv = oracle.project(cams, X) + rng.normal(0, 0.7, (n, 2 * V))                                 # noisy pixels
+    uv[5, 2:4] = np.nan                                                                           # one view missing
+    # undistortion, camera by camera
+    for c, cam in enumerate(cg.cameras):
+        pts = np.ascontiguousarray(uv[:, 2 * c:2 * c + 2])
+        ok = np.isfinite(pts).all(axis=1)
+        got = np.empty_like(pts)
+        hc.hc_undistort(cams[c].ctypes.data_as(ctypes.c_void_p), n, pts.ctypes.data_as(ctypes.c_void_p),
+                        got.ctypes.data_as(ctypes.c_void_p))
+        ref = cv2.undistortPoints(pts[ok].reshape(-1, 1, 2), cam.matrix, cam.dist).reshape(-1, 2)
+        np.testing.assert_allclose(got[ok], ref, rtol=1e-12, atol=1e-14)
+    # full triangulation
+    got = np.empty((n, 3))
+    uvc = np.ascontiguousarray(uv)
+    hc.hc_triangulate_points(cams.ctypes.data_as(ctypes.c_void_p), V, n, uvc.ctypes.data_as(ctypes.c_void_p),
+                             got.ctypes.data_as(ctypes.c_void_p))
+    ref = cg.triangulate(np.stack([uv[:, 2 * c:2 * c + 2] for c in range(V)]), fast=True)
+    assert np.isfinite(got).all() and np.isfinite(ref).all()
+    np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9)
+    assert np.abs(got - X).max() < 0.05                                                            # and it is the point
