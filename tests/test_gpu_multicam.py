@@ -203,6 +203,7 @@ def test_device_triangulation_matches_host_mirror():
     the host mirror (cv2.undistortPoints + pairwise cv2.triangulatePoints + nan-median) on the fly fixture, with a
     missing view injected."""
     import os
+    import torch
     from conftest import GOLDEN
     from eks_b200 import ops
     from eks_b200.marker_array import MarkerArray
