@@ -253,7 +253,7 @@ def project_3d_covariance_to_2d(ms_k, Vs_k, h_cam: PinholeProjection, inflated_v
 
 
 def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames, avg_mode,
-                            var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None) -> tuple:
+                            var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None, cams=None) -> tuple:
     """Linear PCA-latent model without variance inflation: every per-frame stage runs on the device
     (eks_b200.pipeline.multicam_smooth_sessions); the host only packs the DataFrames."""
     from eks_b200.pipeline import multicam_smooth_sessions
@@ -269,7 +269,7 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
     res = multicam_smooth_sessions(raw[None], smooth_param=sp, spans=normalize_spans(T, s_frames),
                                    quantile_keep_pca=quantile_keep_pca, n_latent=n_latent, avg_mode=avg_mode,
                                    var_mode=var_mode, dtype=dtype, inflate_vars=inflate_vars,
-                                   inflate_vars_kwargs=inflate_vars_kwargs)
+                                   inflate_vars_kwargs=inflate_vars_kwargs, cams=cams)
     out = res.out[0].permute(1, 3, 0, 2).contiguous().double().cpu().numpy()        # (V,T,K,9)
     ms = res.ms.double().cpu().numpy()                                              # (K,T,L)
     Vd = torch.diagonal(res.Vs, dim1=2, dim2=3).double().cpu().numpy()              # (K,T,L)
@@ -315,6 +315,10 @@ def ensemble_kalman_smoother_multicam(
             inflate_vars_kwargs['mean'] = np.zeros_like(inflate_vars_kwargs['mean'])
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
                                        avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs)
+    if camgroup is not None and not inflate_vars and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
+        h_all, _ = make_projection_from_camgroup(camgroup)          # calibrated model, device-resident pipeline
+        return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
+                                       avg_mode, var_mode, 3, cams=h_all.cams)
 
     t0 = time.perf_counter()
     ema = ensemble(marker_array, avg_mode=avg_mode, var_mode=var_mode)

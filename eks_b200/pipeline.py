@@ -235,9 +235,12 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
                              n_latent: int = 3, avg_mode='median', var_mode='confidence_weighted_var',
                              dtype=torch.float32, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
                              min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None,
-                             inflate_vars: bool = False, inflate_vars_kwargs: dict | None = None) -> MulticamResult:
-    """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551; linear model, inflate_vars=False) for S
-    sessions at once, every per-frame stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.
+                             inflate_vars: bool = False, inflate_vars_kwargs: dict | None = None,
+                             cams=None) -> MulticamResult:
+    """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551) for S sessions at once, every per-frame
+    stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.  cams = None: linear PCA-latent model; cams = (V, 29)
+    packed camera parameters: calibrated pinhole EKF (triangulation on the device, geometric initialisation of the
+    3-D state on the host from the (K, T, 3) triangulated means; no variance inflation on this branch).
 
     The only host work is the O x O eigen-decomposition per keypoint (O = 2V <= 16) on the moments the device
     reduced -- one small device->host copy and one host->device copy of the components."""
@@ -269,6 +272,9 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
                            avg_mode=avg_mode, var_mode=var_mode)
     yv = PlaneView(out, V * 9 * T, [v * 9 * T + (3 + j) * T for v in range(V) for j in range(2)])
     vv = PlaneView(out, V * 9 * T, [v * 9 * T + (5 + j) * T for v in range(V) for j in range(2)])
+    if cams is not None:
+        return _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap,
+                                 min_R_var, stage)
     with stage('center'):
         ymean, n_good, ws = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
     with stage('pca'):
@@ -306,3 +312,43 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
     with stage('reproject'):
         ops.reproject(ms, Vs, V, out, V * 9 * T, 9 * T, [0, T, 7 * T, 8 * T], C=C, ymean=ymean, var=vv)
     return MulticamResult(out, ms, Vs, s_finals, iters, loss, ymean, C, S0, Q, n_good)
+
+
+def _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap, min_R_var,
+                      stage) -> MulticamResult:
+    """Calibrated branch of multicam_smooth_sessions (eks/multicam_smoother.py:380-405, 446-480): un-centred
+    observations, 3-D state initialised from the triangulated ensemble mean, pinhole emission."""
+    import numpy as np
+    from eks_b200.multicam_smoother import initialize_kalman_filter_geometric
+    S, M, V, T, K, _ = raw.shape
+    dev, B = raw.device, S * K
+    cams64 = torch.as_tensor(np.asarray(cams, dtype=np.float64))
+    assert cams64.shape == (V, 29), 'cams must be (n_cameras, 29) packed camera parameters'
+    with stage('triangulate'):
+        tri = torch.stack([ops.triangulate_mean(raw[s_], cams64) for s_ in range(S)])       # (S,K,T,3) float64
+    with stage('geometric_init'):
+        m0s, S0s, As, Qs, _ = initialize_kalman_filter_geometric(tri.reshape(B, T, 3).cpu().numpy())
+    f = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dtype).contiguous()
+    d_cams = cams64.to(device=dev, dtype=dtype).contiguous()
+    model = Model(f(m0s), f(S0s), f(As), f(Qs), None, d_cams)
+    iters = loss = None
+    if smooth_param is not None:
+        s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)
+        s_finals = (s.expand(K) if s.dim() == 0 or s.numel() == 1 else s).expand(S, K).contiguous()
+    else:
+        with stage('initial_guess'):
+            _, s_log0 = ops.initial_guess(vv, B, T)
+        with stage('const_R_median'):
+            Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
+        with stage('optimize_s'):
+            opt = ops.optimize_s(model, yv, T, Rconst, s_log0, spans=spans, lr=lr, s_bounds_log=s_bounds_log, tol=tol,
+                                 safety_cap=safety_cap)
+        s_finals = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1])).view(S, K)
+        iters, loss = opt['iters'].view(S, K), opt['loss'].view(S, K)
+    with stage('filter_smooth'):
+        ms, Vs = ops.filter_smooth(model, yv, vv, T, s_finals.reshape(B).to(dtype))
+    with stage('reproject'):
+        ops.reproject(ms, Vs, V, out, V * 9 * T, 9 * T, [0, T, 7 * T, 8 * T], cams=d_cams, var=vv,
+                      pinhole_var_quirk=True)
+    zeros = torch.zeros((B, 2 * V), dtype=dtype, device=dev)
+    return MulticamResult(out, ms, Vs, s_finals, iters, loss, zeros, None, model.S0, model.Q, None)
