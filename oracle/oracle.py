@@ -341,8 +341,9 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
     """ensemble_kalman_smoother_multicam restated (eks/multicam_smoother.py:279-551), inflate_vars=False.
 
     raw: (M,V,T,K,3).  Linear model: centring and PCA initialisation are the oracle's own restatement
-    (mc_center_predictions / mc_pca_init, NumPy + scikit-learn's PCA).  Nonlinear model: triangulation and the
-    geometric initialisation are one-off host steps shared with the product's host utilities.
+    (mc_center_predictions / mc_pca_init, NumPy + scikit-learn's PCA).  Nonlinear model (camgroup = path of an
+    Anipose calibration TOML, or the list load_calibration returns): triangulation and the geometric initialisation
+    are the oracle's own NumPy restatement (load_calibration / triangulate_3d_models / geometric_init below).
     Returns dict(cam_out (V,T,K,9), out3d (T,K,2*D), s_finals, info)."""
     raw = np.asarray(raw)
     M, V, T, K, _ = raw.shape
@@ -350,13 +351,12 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
     stacked = lambda lo, hi: np.transpose(ens[..., lo:hi], (2, 1, 0, 3)).reshape(K, T, 2 * V)   # channel o = 2 v + xy
     cams = None
     if camgroup is not None:
-        # triangulation + geometric init are one-off host pre-stages shared with the product
-        from eks_b200.marker_array import MarkerArray
-        from eks_b200.multicam_smoother import (initialize_kalman_filter_geometric, make_projection_from_camgroup,
-                                                triangulate_3d_models)
-        tri = triangulate_3d_models(MarkerArray(raw, data_fields=['x', 'y', 'likelihood']), camgroup)
-        m0s, S0s, As, Qs, Cs = initialize_kalman_filter_geometric(tri.mean(axis=0))
-        cams = make_projection_from_camgroup(camgroup)[0].cams
+        # triangulation + geometric initialisation: the oracle's OWN restatement (NumPy only; see the
+        # "calibration" section below) -- nothing here comes from the product package
+        calib = load_calibration(camgroup) if isinstance(camgroup, (str, os.PathLike)) else camgroup
+        tri = triangulate_3d_models(raw, calib)                                # (M,K,T,3)
+        m0s, S0s, As, Qs, Cs = geometric_init(tri.mean(axis=0))
+        cams = pack_calibration(calib)
         ys = stacked(0, 2)
         D = 3
     else:
@@ -407,6 +407,124 @@ def multicam(raw, quantile_keep_pca=50.0, n_latent=3, camgroup=None, smooth_para
         out3d[:, k, 5] = Vs64[k][:, 2, 2]
     return dict(cam_out=cam_out, out3d=out3d, s_finals=s_finals, info=info, ms=ms, Vs=Vs)
 
+
+
+
+# ----------------------------------------------------------------------------- calibration, triangulation, 3-D init
+# Independent NumPy restatement (no OpenCV, no product code) of the calibrated pre-stage:
+#   * aniposelib.cameras.CameraGroup.load / Camera.undistort_points / CameraGroup.triangulate(fast=True)
+#     (third-party, aniposelib>=0.8.0, pyproject.toml:35; call sites eks/multicam_smoother.py:233, 902): per camera
+#     cv2.undistortPoints with its default criteria (five fixed-point iterations of the inverse distortion), then for
+#     every camera PAIR the homogeneous DLT of cv2.triangulatePoints (null vector of the 4x4 system by SVD), and the
+#     nan-median over the pairs;
+#   * triangulate_3d_models (eks/multicam_smoother.py:888-911) and initialize_kalman_filter_geometric (:600-650).
+# Pinned against OpenCV itself in tests/test_oracle.py (cv2.undistortPoints, cv2.triangulatePoints).
+def load_calibration(path) -> list:
+    """Anipose calibration TOML -> list of dicts(name, matrix (3,3), dist (n,), rvec (3,), tvec (3,)), sorted by
+    section name (cam_0, cam_1, ...), which is the order CameraGroup.load keeps."""
+    import tomllib
+    with open(path, 'rb') as f:
+        cfg = tomllib.load(f)
+    cams = []
+    for key in sorted(k for k in cfg if k.startswith('cam_')):
+        c = cfg[key]
+        cams.append(dict(name=c['name'], matrix=np.asarray(c['matrix'], dtype=np.float64),
+                         dist=np.asarray(c['distortions'], dtype=np.float64).ravel(),
+                         rvec=np.asarray(c['rotation'], dtype=np.float64).ravel(),
+                         tvec=np.asarray(c['translation'], dtype=np.float64).ravel()))
+    return cams
+
+
+def pack_calibration(calib) -> np.ndarray:
+    """(V, 29) packed cameras (make_projection_from_camgroup, eks/multicam_smoother.py:862-885)."""
+    return np.stack([pack_camera(c['rvec'], c['tvec'], c['matrix'], c['dist']) for c in calib])
+
+
+def undistort_points(pts, Kmat, dist, iters: int = 5) -> np.ndarray:
+    """cv2.undistortPoints(pts, K, dist) with the default criteria restated: normalise with the camera matrix, then
+    `iters` fixed-point iterations x <- (x0 - tangential(x) - prism(x)) / radial(x).  pts (N,2) pixels -> (N,2)."""
+    k = np.zeros(14)
+    d = np.asarray(dist, dtype=np.float64).ravel()
+    k[:min(14, d.size)] = d[:14]
+    Kmat = np.asarray(Kmat, dtype=np.float64)
+    fx, fy, cx, cy = Kmat[0, 0], Kmat[1, 1], Kmat[0, 2], Kmat[1, 2]
+    pts = np.asarray(pts, dtype=np.float64)
+    x0 = (pts[:, 0] - cx) / fx
+    y0 = (pts[:, 1] - cy) / fy
+    x, y = x0.copy(), y0.copy()
+    for _ in range(iters):
+        r2 = x * x + y * y
+        icd = (1.0 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1.0 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+        icd = np.where(icd < 0, 1.0, icd)            # OpenCV: a negative ratio leaves the point at x0 (never hit here)
+        dx = 2.0 * k[2] * x * y + k[3] * (r2 + 2.0 * x * x) + k[8] * r2 + k[9] * r2 * r2
+        dy = k[2] * (r2 + 2.0 * y * y) + 2.0 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2
+        x = (x0 - dx) * icd
+        y = (y0 - dy) * icd
+    return np.stack([x, y], axis=1)
+
+
+def triangulate_pair(P1, P2, x1, x2) -> np.ndarray:
+    """cv2.triangulatePoints restated: rows x*P[2]-P[0], y*P[2]-P[1] of both views, right singular vector of the
+    smallest singular value, de-homogenised.  P1, P2 (3,4); x1, x2 (N,2) normalised coordinates -> (N,3)."""
+    N = x1.shape[0]
+    A = np.empty((N, 4, 4))
+    A[:, 0] = x1[:, 0:1] * P1[2] - P1[0]
+    A[:, 1] = x1[:, 1:2] * P1[2] - P1[1]
+    A[:, 2] = x2[:, 0:1] * P2[2] - P2[0]
+    A[:, 3] = x2[:, 1:2] * P2[2] - P2[1]
+    X = np.full((N, 3), np.nan)
+    ok = np.isfinite(A).all(axis=(1, 2))
+    if ok.any():
+        vh = np.linalg.svd(A[ok])[2][:, 3, :]
+        with np.errstate(all='ignore'):
+            X[ok] = vh[:, :3] / vh[:, 3:4]
+    return X
+
+
+def triangulate_fast(points, calib) -> np.ndarray:
+    """CameraGroup.triangulate(points, fast=True): points (V,N,2) pixels -> (N,3)."""
+    import itertools
+    V = len(calib)
+    und = [undistort_points(points[c], calib[c]['matrix'], calib[c]['dist']) for c in range(V)]
+    Rt = []
+    for c in calib:
+        E = np.empty((3, 4))
+        E[:, :3] = rodrigues(c['rvec'])
+        E[:, 3] = c['tvec']
+        Rt.append(E)
+    tris = [triangulate_pair(Rt[a], Rt[b], und[a], und[b]) for a, b in itertools.combinations(range(V), 2)]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', category=RuntimeWarning)
+        return np.nanmedian(np.stack(tris), axis=0)
+
+
+def triangulate_3d_models(raw, calib) -> np.ndarray:
+    """eks/multicam_smoother.py:888-911: raw (M,V,T,K,>=2) -> (M,K,T,3), one triangulate(fast=True) per (m, k)."""
+    raw = np.asarray(raw, dtype=np.float64)
+    M, V, T, K, _ = raw.shape
+    tri = np.zeros((M, K, T, 3))
+    for m in range(M):
+        for k in range(K):
+            tri[m, k] = triangulate_fast(raw[m, :, :, k, :2], calib)
+    return tri
+
+
+def geometric_init(ys3d):
+    """initialize_kalman_filter_geometric (eks/multicam_smoother.py:600-650): ys3d (K,T,3) ->
+    m0 = mean of the first 10 frames, S0 = diag(nanvar + 1e-4), A = C = I, Q = diag(max((1.4826 MAD(diff))^2, 1e-8))."""
+    ys3d = np.asarray(ys3d, dtype=np.float64)
+    K, T, D = ys3d.shape
+    m0s = ys3d[:, :10].mean(axis=1)
+    S0s = np.stack([np.diag(np.nanvar(ys3d[k], axis=0) + 1e-4) for k in range(K)])
+    eye = np.tile(np.eye(D), (K, 1, 1))
+    Qs = np.empty((K, D, D))
+    for k in range(K):
+        dx = np.diff(ys3d[k], axis=0)
+        med = np.median(dx, axis=0)
+        mad = np.median(np.abs(dx - med), axis=0) + 1e-12
+        Qs[k] = np.diag(np.maximum((1.4826 * mad) ** 2, 1e-8))
+    return m0s, S0s, eye, Qs, eye.copy()
 
 
 # ----------------------------------------------------------------------------- multi-camera pre-stage (linear model)

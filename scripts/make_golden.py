@@ -58,14 +58,13 @@ def singlecam_case(name, files, keypoints=None, raw_from=None, **kw):
 
 def multicam_case(name, cam_files, camera_names, keypoints=None, calibration=None, **kw):
     """cam_files: {camera: [csv per seed]}.  Stores raw (M,V,T,K,3) float32 + oracle outputs."""
-    from eks_b200.multicam_smoother import CameraGroup
     raws = []
     kps = keypoints
     for cam in camera_names:
         r, kps = load_csvs(cam_files[cam], kps)
         raws.append(r)
     raw = np.stack(raws, axis=1).astype(np.float32).astype(np.float64)   # (M,V,T,K,3)
-    camgroup = CameraGroup.load(calibration) if calibration else None
+    camgroup = calibration   # path of the Anipose TOML: the oracle has its own loader / triangulation
     res = {'raw': raw.astype(np.float32), 'keypoints': np.array(kps), 'cameras': np.array(camera_names)}
     for tag, dt in (('f64', np.float64), ('f32', np.float32)):
         r = oracle.multicam(raw, camgroup=camgroup, dtype=dt, **kw)

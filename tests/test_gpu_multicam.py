@@ -198,22 +198,21 @@ def test_run_parallel_generic_pinhole_matches_oracle():
     np.testing.assert_allclose(Vs, Vs_o, rtol=1e-3, atol=1e-6 * np.abs(Vs_o).max())
 
 
-def test_device_triangulation_matches_host_mirror():
-    """eks_triangulate_mean (one thread per keypoint-frame, fp64) against triangulate_3d_models(...).mean(axis=0) of
-    the host mirror (cv2.undistortPoints + pairwise cv2.triangulatePoints + nan-median) on the fly fixture, with a
-    missing view injected."""
+def test_device_triangulation_matches_oracle():
+    """eks_triangulate_mean (one thread per keypoint-frame, fp64) against the ORACLE's independent NumPy restatement of
+    triangulate_3d_models(...).mean(axis=0) (oracle.triangulate_3d_models: undistortion iterations + pairwise SVD DLT +
+    nan-median; itself pinned to OpenCV in tests/test_oracle.py) on the fly fixture, with a missing view injected."""
     import os
     import torch
     from conftest import GOLDEN
     from eks_b200 import ops
-    from eks_b200.marker_array import MarkerArray
-    from eks_b200.multicam_smoother import CameraGroup, make_projection_from_camgroup, triangulate_3d_models
+    from oracle import oracle
     g = load_golden('multicam_fly_nonlinear')
     raw = g['raw'].astype(np.float64)[:, :, :200].copy()          # (M,V,T,K,3)
     raw[1, 2, 17, 0, :2] = np.nan
-    cg = CameraGroup.load(os.path.join(GOLDEN, 'fly_calibration.toml'))
-    ref = triangulate_3d_models(MarkerArray(raw, data_fields=['x', 'y', 'likelihood'], dtype=np.float64), cg).mean(axis=0)
-    cams = torch.as_tensor(np.asarray(make_projection_from_camgroup(cg)[0].cams, dtype=np.float64))
+    calib = oracle.load_calibration(os.path.join(GOLDEN, 'fly_calibration.toml'))
+    ref = oracle.triangulate_3d_models(raw, calib).mean(axis=0)
+    cams = torch.as_tensor(oracle.pack_calibration(calib))
     for dt in (torch.float64, torch.float32):
         got = ops.triangulate_mean(torch.as_tensor(raw).to('cuda', dt).contiguous(), cams).cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=1e-6 if dt == torch.float64 else 1e-4, atol=1e-8)

@@ -145,6 +145,15 @@ def test_product_never_imports_oracle():
                 assert 'oracle' not in src.replace('# oracle', ''), f'{f} references oracle/'
 
 
+def test_oracle_never_imports_product():
+    """The checker must be independent of what it checks: nothing under oracle/ imports or loads eks_b200."""
+    import re
+    for f in os.listdir(os.path.join(ROOT, 'oracle')):
+        if f.endswith(('.py', '.cpp', '.h', 'Makefile')):
+            src = open(os.path.join(ROOT, 'oracle', f)).read()
+            assert not re.search(r'(import|from)\s+eks_b200|libeks_b200', src), f'oracle/{f} depends on the product'
+
+
 # ------------------------------------------------------------------ host logic (reference tests mirrored)
 def test_crop_frames_semantics():
     """reference tests/test_utils.py:28-98."""
