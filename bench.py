@@ -78,6 +78,75 @@ def synth_session_host(M, K, T, seed):
     return np.concatenate([pred, lik[..., None]], axis=-1)[:, None].astype(np.float32)
 
 
+def synth_multicam_host(M, V, K, T, seed):
+    """Config-3 family: 3-D random-walk latent -> 2V pixel coordinates through a random orthonormal
+    W (2V x 3) + per-camera offsets of 100-300 px; seeds = truth + N(0, .5^2), x8 noise and low likelihood on a 2 %
+    occlusion mask shared by seeds and cameras.  Returns (M,V,T,K,3) float32."""
+    rng = np.random.default_rng(4321 + seed)
+    raw = np.empty((M, V, T, K, 3), dtype=np.float32)
+    for k in range(K):
+        lat = np.cumsum(rng.normal(0, 0.3, size=(T, 3)), axis=0)
+        W = np.linalg.qr(rng.standard_normal((2 * V, 3)))[0]                       # orthonormal columns
+        truth = lat @ W.T * 1.5 + rng.uniform(100, 300, size=(1, 2 * V))              # (T, 2V)
+        occ = rng.random(T) < 0.02
+        sigma = np.where(occ, 4.0, 0.5)[:, None]
+        for m in range(M):
+            noisy = truth + rng.standard_normal((T, 2 * V)) * sigma
+            raw[m, :, :, k, 0:2] = noisy.reshape(T, V, 2).transpose(1, 0, 2)
+            u = rng.random((V, T))
+            raw[m, :, :, k, 2] = np.where(occ[None], 0.05 + 0.45 * u, 0.9 + 0.1 * u)
+    return raw
+
+
+def fly_cameras():
+    """(V, 29) packed cameras of the bundled fly rig (tests/golden/fly_calibration.toml = the reference's
+    data/fly/calibration.toml) + the product's CameraGroup."""
+    from eks_b200.multicam_smoother import CameraGroup, make_projection_from_camgroup
+    cg = CameraGroup.load(os.path.join(ROOT, 'tests', 'golden', 'fly_calibration.toml'))
+    return np.asarray(make_projection_from_camgroup(cg)[0].cams, dtype=np.float64), cg
+
+
+def project_pinhole_np(cams, X):
+    """The reference's pinhole model (eks/multicam_smoother.py:806-859) in NumPy, for data synthesis only:
+    X (N,3) world -> (N, 2V) pixels.  cams: (V,29) = R(9) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1..s4."""
+    out = np.empty((X.shape[0], 2 * cams.shape[0]))
+    for v, c in enumerate(cams):
+        Rm, t = c[0:9].reshape(3, 3), c[9:12]
+        fx, fy, cx, cy, skew = c[12:17]
+        k1, k2, p1, p2, k3, k4, k5, k6, s1, s2, s3, s4 = c[17:29]
+        Xc = X @ Rm.T + t
+        x, y = Xc[:, 0] / Xc[:, 2], Xc[:, 1] / Xc[:, 2]
+        r2 = x * x + y * y
+        radial = 1 + k1 * r2 + k2 * r2 ** 2 + k3 * r2 ** 3 + k4 * r2 ** 4 + k5 * r2 ** 5 + k6 * r2 ** 6
+        xd = x * radial + 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + s1 * r2 + s2 * r2 * r2
+        yd = y * radial + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + s3 * r2 + s4 * r2 * r2
+        out[:, 2 * v] = fx * xd + skew * yd + cx
+        out[:, 2 * v + 1] = fy * yd + cy
+    return out
+
+
+def synth_fly_host(M, K, T, seed, cams):
+    """Config-4 family: 3-D random walk (step sigma 1e-3 world units, reflected into a +-0.1 box around the
+    rig centre (-1.75, -0.30, 3.50)) projected through the calibrated cameras, + N(0, .5^2) px noise per seed, x8 on a
+    2 % occlusion mask.  Returns (M,V,T,K,3) float32."""
+    rng = np.random.default_rng(8765 + seed)
+    V = cams.shape[0]
+    raw = np.empty((M, V, T, K, 3), dtype=np.float32)
+    centre = np.array([-1.75, -0.30, 3.50])
+    for k in range(K):
+        w = np.cumsum(rng.normal(0, 1e-3, size=(T, 3)), axis=0) + rng.uniform(-0.05, 0.05, size=(1, 3))
+        w = np.abs((w + 0.1) % 0.4 - 0.2) - 0.1                                       # reflect into [-0.1, 0.1]
+        uv = project_pinhole_np(cams, centre + w)                                     # (T, 2V)
+        occ = rng.random(T) < 0.02
+        sigma = np.where(occ, 4.0, 0.5)[:, None]
+        for m in range(M):
+            noisy = uv + rng.standard_normal((T, 2 * V)) * sigma
+            raw[m, :, :, k, 0:2] = noisy.reshape(T, V, 2).transpose(1, 0, 2)
+            u = rng.random((V, T))
+            raw[m, :, :, k, 2] = np.where(occ[None], 0.05 + 0.45 * u, 0.9 + 0.1 * u)
+    return raw
+
+
 # ----------------------------------------------------------------------------- CPU oracle leg
 def cpu_leg(M, K, T_sample, steps, warmup):
     """Time the CPU oracle (oracle/liboracle.so, OpenMP over sequences) on one session of T_sample frames."""

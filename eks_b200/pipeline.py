@@ -236,7 +236,7 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
                              dtype=torch.float32, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
                              min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None,
                              inflate_vars: bool = False, inflate_vars_kwargs: dict | None = None,
-                             cams=None) -> MulticamResult:
+                             cams=None, trace_cap: int = 0) -> MulticamResult:
     """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551) for S sessions at once, every per-frame
     stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.  cams = None: linear PCA-latent model; cams = (V, 29)
     packed camera parameters: calibrated pinhole EKF (triangulation on the device, geometric initialisation of the
@@ -274,7 +274,7 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
     vv = PlaneView(out, V * 9 * T, [v * 9 * T + (5 + j) * T for v in range(V) for j in range(2)])
     if cams is not None:
         return _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap,
-                                 min_R_var, stage)
+                                 min_R_var, stage, trace_cap)
     with stage('center'):
         ymean, n_good, ws = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
     with stage('pca'):
@@ -304,7 +304,8 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
             Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
         with stage('optimize_s'):
             opt = ops.optimize_s(model, yv, T, Rconst, s_log0, ymean=ymean, spans=spans, lr=lr,
-                                 s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap)
+                                 s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap)
+        multicam_smooth_sessions.last_opt = opt
         s_finals = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1])).view(S, K)
         iters, loss = opt['iters'].view(S, K), opt['loss'].view(S, K)
     with stage('filter_smooth'):
@@ -315,7 +316,7 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
 
 
 def _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap, min_R_var,
-                      stage) -> MulticamResult:
+                      stage, trace_cap=0) -> MulticamResult:
     """Calibrated branch of multicam_smooth_sessions (eks/multicam_smoother.py:380-405, 446-480): un-centred
     observations, 3-D state initialised from the triangulated ensemble mean, pinhole emission."""
     import numpy as np
@@ -342,7 +343,8 @@ def _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_
             Rconst = ops.const_R_median(vv, B, T, spans=spans, min_var=min_R_var)
         with stage('optimize_s'):
             opt = ops.optimize_s(model, yv, T, Rconst, s_log0, spans=spans, lr=lr, s_bounds_log=s_bounds_log, tol=tol,
-                                 safety_cap=safety_cap)
+                                 safety_cap=safety_cap, trace_cap=trace_cap)
+        multicam_smooth_sessions.last_opt = opt
         s_finals = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1])).view(S, K)
         iters, loss = opt['iters'].view(S, K), opt['loss'].view(S, K)
     with stage('filter_smooth'):

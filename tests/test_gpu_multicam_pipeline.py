@@ -96,9 +96,16 @@ def test_mirror_mouse_separate_fp64_matches_golden():
 
 def test_mirror_mouse_separate_fp32():
     g = load_golden('multicam_mirror_mouse_separate')
-    res = _run(g['raw'], torch.float32, quantile_keep_pca=95.0)
-    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), g['s_f64'], rtol=2e-2)   # fp32 stop rule is a knife edge
+    from eks_b200.pipeline import multicam_smooth_sessions
     from oracle import oracle
+    from parity import fp32_stop_protocol
+    res = _run(g['raw'], torch.float32, quantile_keep_pca=95.0, trace_cap=300)
+    ref_t = oracle.multicam(g['raw'].astype(np.float64), quantile_keep_pca=95.0, dtype=np.float64, trace_cap=300)
+    trace = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
+    it = res.iters[0].cpu().numpy()
+    for k in range(trace.shape[0]):   # float32 stop protocol (tests/parity.py) instead of a loose tolerance on s
+        fp32_stop_protocol(f'mirror-mouse-separate kp{k}', trace[k], it[k], ref_t['info']['trace'][k],
+                           ref_t['info']['iters'][k])
     ref = oracle.multicam(g['raw'].astype(np.float64), quantile_keep_pca=95.0, dtype=np.float64,
                           smooth_param=res.s_finals[0].cpu().numpy())
     _check(_cam_out(res), ref['cam_out'], RTOL32, 'mirror-mouse-separate fp32')
