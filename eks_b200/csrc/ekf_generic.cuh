@@ -93,10 +93,22 @@ struct Dims {
 // accumulating nll += 0.5 * (log 2pi + log s_i + e_i^2 / s_i); then (optionally) the filtered
 // moments are exported and the state is predicted forward with A, s*Q.
 // Returns false if an innovation variance is not positive/finite.
-template <class S, class P, int DC, int OC, bool FIXED, bool NL>
+//
+// BOOST (final smoother pass): dynamax computes the gain with psd_solve's 1e-9 diagonal boost,
+// K = P H^T (S + eps I)^-1, and the filtered covariance as P - K S K^T with the UN-boosted S.  That is
+// represented exactly here: the sequential scalar updates run with R' = R + eps, which gives exactly that K (hence
+// the filtered mean) and P' = P - K (S + eps I) K^T; then P_f = P' + eps K K^T with K = P' H^T R'^-1, i.e.
+// P_f = P' + eps P' (H^T R'^-2 H) P'.  It matters on frames where an ensemble variance is tiny (eps / R up to 1e-6
+// relative); the loss path (constant R >= 1e-4) keeps BOOST = false: its effect there is O(eps / S) on the NLL.
+template <class S, class P, int DC, int OC, bool FIXED, bool NL, bool BOOST = false>
 EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const P* yv, const P* rv, S s, S* m,
                      S* Pm, S& nll, S* mf_out, S* Pf_out, const S* Adiag = nullptr, const S* Qdiag = nullptr) {
     const int D = dm.D(), O = dm.O();
+    S Mb[BOOST ? DC * DC : 1];   // H^T R'^-2 H
+    if (BOOST) {
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) Mb[BOOST ? i : 0] = S(P(0));
+    }
     const P HALF_LOG2PI = P(0.91893853320467274178032973640562);
     S delta[DC];  // m_cur - m_pred
 #pragma unroll
@@ -138,7 +150,17 @@ EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, cons
                     Ph[i] = acc;
                 }
             }
-            S si = S(rv[ch]);
+            S si = S(BOOST ? rv[ch] + P(1e-9) : rv[ch]);
+            if (BOOST) {
+                const S ir2 = S(P(1)) / (si * si);   // si == R' here
+#pragma unroll
+                for (int i = 0; i < DC; ++i)
+                    if (i < D) {
+#pragma unroll
+                        for (int j = 0; j < DC; ++j)
+                            if (j < D) Mb[BOOST ? i * D + j : 0] += h[i] * h[j] * ir2;
+                    }
+            }
 #pragma unroll
             for (int j = 0; j < DC; ++j)
                 if (j < D) { si += h[j] * Ph[j]; e -= h[j] * delta[j]; }
@@ -156,6 +178,36 @@ EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, cons
                 }
             }
         }
+    }
+    if (BOOST) {   // P_f = P' + eps P' (H^T R'^-2 H) P'
+        S PM[DC * DC];
+#pragma unroll
+        for (int i = 0; i < DC; ++i)
+            if (i < D) {
+#pragma unroll
+                for (int j = 0; j < DC; ++j)
+                    if (j < D) {
+                        S acc = S(P(0));
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) if (k < D) acc += Pm[i * D + k] * Mb[BOOST ? k * D + j : 0];
+                        PM[i * D + j] = acc;
+                    }
+            }
+        S add[DC * DC];
+#pragma unroll
+        for (int i = 0; i < DC; ++i)
+            if (i < D) {
+#pragma unroll
+                for (int j = 0; j < DC; ++j)
+                    if (j < D) {
+                        S acc = S(P(0));
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) if (k < D) acc += PM[i * D + k] * Pm[k * D + j];
+                        add[i * D + j] = acc;
+                    }
+            }
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] += S(P(1e-9)) * add[i];
     }
     // symmetrise the filtered covariance (dynamax symmetrize) and form the filtered mean
     S mf[DC];
@@ -481,8 +533,8 @@ EKS_HD void seq_smooth(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, co
     for (int t = 0; t < T; ++t) {
         P yv[OC], rv[OC];
         load_obs<P, OC>(ob, O, t, yv, rv);
-        ekf_step<P, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, s, m, Pm, nll, mf + (long long)t * D,
-                                          Pf + (long long)t * D * D);
+        ekf_step<P, P, DC, OC, FIXED, NL, true>(dm, mdl, yv, rv, s, m, Pm, nll, mf + (long long)t * D,
+                                                Pf + (long long)t * D * D);
     }
     // backward pass: G = psd_solve(A P_f A^T + sQ, A P_f)^T, boost 1e-9
     P msn[DC], Vsn[DC * DC];

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(32) gen_filter_runs_kernel(const __grid_consta
         P yv[OC], rv[OC];
         load_obs<P, OC>(ob, O, t, yv, rv);
         P mf[DC], Pf[DC * DC];
-        ekf_step<P, P, DC, OC, FIXED, NL>(dm, mdl, yv, rv, s, m, Pm, nll, mf, Pf);
+        ekf_step<P, P, DC, OC, FIXED, NL, true>(dm, mdl, yv, rv, s, m, Pm, nll, mf, Pf);
         if (t >= t0) {
             for (int q = 0; q < D; ++q) mfb[(long long)t * D + q] = mf[q];
             for (int q = 0; q < D * D; ++q) Pfb[(long long)t * D * D + q] = Pf[q];
