@@ -2,738 +2,42 @@
 // single-camera EKS model, eks/singlecam_smoother.py:246-284).  With a diagonal R the 2-D filter is
 // two independent scalar filters that share the smoothing parameter s.
 //
-// diag_optimize_kernel: the whole Adam loop of _vmap_optimize_singletons / the block path
-// (eks/core.py:562-699, 403-559) for one block per CTA, persistent over all iterations:
-//   * loss path has CONSTANT R (core.py:702-709) => the variance recursion is data independent.
-//     Lane c of warp 0 runs it sequentially (with its s-sensitivity) until it reaches its floating
-//     point fixed point ("transient", a few tens of frames), accumulating the NLL there exactly as
-//     the sequential filter does;
-//   * for the remaining frames the gain is constant and the predicted mean m_t and its sensitivity
-//     dm_t/ds obey a constant-coefficient linear recurrence
-//         z_{t+1} = Phi z_t + b y_t,  z = (m, dm),  Phi = [[alpha,0],[dalpha,alpha]], b = (beta,dbeta)
-//     which is evaluated EXACTLY in parallel: each thread owns L consecutive frames in registers,
-//     computes its zero-state response (2 FMAs / frame), a block-wide scan with the closed-form
-//     powers Phi^(L 2^k) hands every thread its carry-in, and a second register pass accumulates
-//     sum e^2 and sum e dm (7 FMAs / frame).  y is read from HBM/L2 once per Adam iteration.
-//   * NLL = n/2 log 2pi + 1/2 sum log S_t + 1/2 sum e_t^2 / S_t, its derivative likewise; partial
-//     sums are kept in fp64 so that the reference's relative-tolerance stop rule stays meaningful
-//     at 10^6 frames even in float32 mode.
+// (1) diag_optimize, "stream" mode: the Adam loop of _vmap_optimize_singletons / the block path
+//     (eks/core.py:562-699, 403-559) as ONE streaming launch per evaluation (diag_nll_kernel; the evaluation itself is
+//     diag_stream_cta in diag_stream.cuh) with the Adam step taken by the last CTA of each block.  The default
+//     optimiser is the lag-statistics one of diag_lag.cu, which reads the observations once; this mode is kept for
+//     EKS_OPT_MODE=stream and as its cross-check.
+// (2) the final filter + RTS smoother pass with time-varying R_t (below).
 #include <cstdlib>
 #include "common.cuh"
 #include "ekf_generic.cuh"
 #include "diag.cuh"
+#include "diag_stream.cuh"
 #include "../../include/eks_b200.h"
 
 namespace eks {
 
 constexpr int DIAG_NT = 256;
 constexpr int DIAG_NW = DIAG_NT / 32;
-#ifndef EKS_OPT_NW
-#define EKS_OPT_NW 8     // warps per CTA of diag_nll_kernel (each warp = one independent run of warp-tiles)
-#endif
-constexpr int OPT_NW = EKS_OPT_NW, OPT_NT = 32 * OPT_NW;
-constexpr int OPT_NSEG_MAX = 16 * 8 / OPT_NW;   // at most 128 runs per (sequence, channel)
-
-template <class P> struct DiagTraits;
-template <> struct DiagTraits<float> {
-    static constexpr int L = 16;
-    using vec_t = float4;
-    static constexpr int VW = 4;
-    __device__ static float eps() { return 1.1920929e-7f; }
-};
-template <> struct DiagTraits<double> {
-    static constexpr int L = 8;
-    using vec_t = double2;
-    static constexpr int VW = 2;
-    __device__ static double eps() { return 2.220446049250313e-16; }
-};
-
-template <class P>
-struct ChanConst {
-    P alpha, beta, a, cc, dalpha, dbeta, iS, diS, logS, dlogS;
-    P gamma;         // -c beta: coupling of the scaled recursion (see diag_warp_tile)
-    P aL[5], bL[5];  // Phi^(L 2^k) = [[aL,0],[bL,aL]]
-    P aW, bW;        // Phi^(32 L)
-    P aH, bH;        // Phi^(L/2)
-    P aQ, bQ;        // Phi^(L/4)
-};
-
-// shared-memory tile ring: every thread's chunk is CHUNK_BYTES of frames, padded to PAD_BYTES so that the
-// per-thread 16-byte reads are bank-conflict free (stride 144 B = 9 x 16 B)
-constexpr int OPT_CHUNK_BYTES = 128;
-constexpr int OPT_PAD_BYTES = 144;
-#ifndef EKS_OPT_STAGES
-#define EKS_OPT_STAGES 2
-#endif
-#ifndef EKS_OPT_MINBLOCKS
-#define EKS_OPT_MINBLOCKS 3
-#endif
-#ifndef EKS_OPT_RELOAD
-#define EKS_OPT_RELOAD 0
-#endif
-constexpr int OPT_STAGES = EKS_OPT_STAGES;
-
-// ---- device-resident optimiser state -----------------------------------------------------------------
-template <class P>
-struct BlockState {          // one per block (group of sequences sharing one s)
-    AdamState<P> adam;
-    P s, dsdlog;
-    int done;
-    int pad;
-};
-template <class P>
-struct ChanState {           // one per (sequence, channel): produced by diag_adam_kernel for the current s
-    ChanConst<P> k;
-    P z0[2];                 // (m, dm) at frame t_c
-    P a_lane[32], b_lane[32];// Phi^(L lane) = [[a_lane,0],[b_lane,a_lane]] for folding a warp carry
-    double tsum[5];          // transient sums: logS, dlogS, e2 iS, e2 diS, cc e dm iS
-    int t_c;                 // first steady-state frame (multiple of 4)
-    int warm;                // frames after which a zero carry-in is forgotten below rounding
-};
-
-template <class P>
-struct DiagOptArgs {
-    int B, t_begin, n, nseg;
-    const P *m0, *S0, *A, *Q, *C;
-    PlaneView y;
-    const P *ymean, *Rconst;
-    int n_blocks;
-    const int *block_off, *members;
-    const int* seq_block;        // [B] block index of every sequence
-    const P* s_log0;
-    P lr, lo, hi, tol;
-    int cap;
-    P *s_log_out, *last_loss_out;
-    int* iters_out;
-    P* trace;
-    int trace_cap;
-    BlockState<P>* bstate;       // [n_blocks]
-    ChanState<P>* cstate;        // [B][2]
-    double* partials;            // [B][2][nseg][2]  (sum e^2, sum e dm) per segment
-    int* n_active;
-    int* block_counter;          // [n_blocks] CTAs of the current evaluation that have finished
-    int blk_lo, blk_hi;          // this launch evaluates the blocks in [blk_lo, blk_hi) only
-};
-
-__device__ inline void cp_async_16(void* smem, const void* gmem, int src_bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ inline void cp_async_8(void* smem, const void* gmem, int src_bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ inline void cp_async_4(void* smem, const void* gmem, int src_bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
-}
-__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-
-// ---- transient: sequential scalar filter with s-sensitivities until the variance recursion has reached
-// its floating-point fixed point (or the sequence ends).  One thread per (sequence, channel).
-template <class P>
-__device__ void diag_transient(const DiagOptArgs<P>& a, int b, int c, P s, ChanState<P>& out) {
-    const P av = a.A[(long long)b * 4 + c * 3], cc = a.C[(long long)b * 4 + c * 3], Qc = a.Q[(long long)b * 4 + c * 3];
-    const P r = a.Rconst[(long long)b * 2 + c];
-    const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
-    const P* yp = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.y.chan_off[c] + a.t_begin;
-    P Pv = a.S0[(long long)b * 4 + c * 3], dP = P(0), m = a.m0[(long long)b * 2 + c], dm = P(0);
-    double sl = 0, sdl = 0, se = 0, sde = 0, sg = 0;
-    const P tol = P(8) * DiagTraits<P>::eps();
-    const P BOOST = P(1e-9);
-    P prevdP_chg = P(INFINITY), prevP_chg = P(INFINITY);
-    int stall = 0;
-    int t = 0;
-    const int n = a.n;
-    P S, iS, dS, diS, K, dK, alpha;
-    while (true) {
-        S = cc * cc * Pv + r;
-        iS = P(1) / S;
-        const P iSb = P(1) / (S + BOOST);       // psd_solve boosts the gain solve only
-        dS = cc * cc * dP;
-        diS = -dS * iS * iS;
-        K = Pv * cc * iSb;
-        dK = cc * (dP * iSb - Pv * dS * iSb * iSb);
-        // P_f = P - K S K and alpha = a (1 - K c), written without cancellation (identical algebra)
-        const P Pf = Pv * iSb * (r + BOOST * (P(1) + cc * K));
-        const P dPf = r * (dP * iS + Pv * diS);
-        const P Pn = av * av * Pf + s * Qc;
-        const P dPn = av * av * dPf + Qc;
-        alpha = av * iSb * (r + BOOST);
-        // convergence of (P, dP): relative step below tol * (1 - rho), rho = alpha^2 the contraction
-        // factor, or the iteration has hit its rounding floor (steps no longer shrinking)
-        const P gap = P(1) - alpha * alpha;
-        const P chgP = fabs(Pn - Pv), chgd = fabs(dPn - dP);
-        bool conv = (chgP <= tol * gap * fabs(Pn)) && (chgd <= tol * gap * fabs(dPn));
-        if (chgP >= prevP_chg && chgd >= prevdP_chg) ++stall;
-        if (stall >= 24) conv = true;
-        prevP_chg = chgP;
-        prevdP_chg = chgd;
-        if ((conv && (t & 3) == 0) || t >= n) break;
-        const P y = yp[t] - mean;
-        const P e = y - cc * m;
-        sl += (double)log_(S);
-        sdl += (double)(dS * iS);
-        se += (double)(e * e * iS);
-        sde += (double)(e * e * diS);
-        sg += (double)(cc * e * dm * iS);
-        const P mf = m + K * e;
-        const P dmf = dm + dK * e - K * cc * dm;
-        m = av * mf;
-        dm = av * dmf;
-        Pv = Pn;
-        dP = dPn;
-        ++t;
-    }
-    ChanConst<P>& k = out.k;
-    k.a = av; k.cc = cc;
-    k.alpha = alpha;
-    k.beta = av * K;
-    k.dalpha = -av * cc * dK;
-    k.dbeta = av * dK;
-    k.iS = iS; k.diS = diS;
-    k.logS = log_(S);
-    k.dlogS = dS * iS;
-    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    k.gamma = -cc * k.beta;
-    // Phi^(L/2) of the scaled recursion by repeated squaring of Phi = [[alpha,0],[gamma,alpha]]
-    {
-        P pa = k.alpha, pb = k.gamma;
-        for (int h = 1; h < L / 4; h <<= 1) { pb = P(2) * pa * pb; pa = pa * pa; }
-        k.aQ = pa; k.bQ = pb;
-        pb = P(2) * pa * pb; pa = pa * pa;   // Phi^(L/2) = (Phi^(L/4))^2: keeps quarter/half/full powers consistent
-        k.aH = pa; k.bH = pb;
-    }
-    P aL = k.aH * k.aH;                 // Phi^L = (Phi^(L/2))^2: keeps the half/full powers consistent
-    P bL = P(2) * k.aH * k.bH;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        k.aL[i] = aL; k.bL[i] = bL;
-        bL = P(2) * aL * bL;
-        aL = aL * aL;
-    }
-    k.aW = aL; k.bW = bL;
-    out.a_lane[0] = P(1);
-    out.b_lane[0] = P(0);
-    for (int l = 1; l < 32; ++l) {  // Phi^(L l) = Phi^L Phi^(L (l-1))
-        out.a_lane[l] = k.aL[0] * out.a_lane[l - 1];
-        out.b_lane[l] = k.aL[0] * out.b_lane[l - 1] + k.bL[0] * out.a_lane[l - 1];
-    }
-    // scaled state: mt = m / beta, dt = dm / dbeta  (dm' = alpha dm + dbeta e  =>  dt' = alpha dt + e)
-    out.z0[0] = m / k.beta;
-    out.z0[1] = (k.dbeta != P(0)) ? dm / k.dbeta : P(0);
-    out.tsum[0] = sl; out.tsum[1] = sdl; out.tsum[2] = se; out.tsum[3] = sde; out.tsum[4] = sg;
-    out.t_c = t;
-    // frames after which the response to the state at their start has decayed below rounding:
-    // alpha^W (and W alpha^(W-1)) negligible against 1 -> W = ln(eps_w) / ln(alpha), eps_w far below eps
-    const double la = log((double)fmin(fmax(alpha, P(1e-30)), P(1)));
-    const double lw = (sizeof(P) == 4) ? -32.0 : -64.0;  // ln(1.3e-14) / ln(1.6e-28)
-    double w = (la < -1e-12) ? lw / la : 2.0e9;
-    w = fmin(w + 64.0, 2.0e9);
-    out.warm = (int)w;
-}
 
 template <class P> __device__ void diag_adam_body(const DiagOptArgs<P>& a, int j, bool first);
 
-// One WARP-tile: 32 lanes x L frames of one channel, y[] = the lane's register-resident chunk (already
-// centred).  Every warp owns a contiguous run of warp-tiles, so the whole evaluation needs no block-wide
-// barrier: the only cross-lane traffic is the 5-step shuffle scan below.
-//
-// The recursion runs in SCALED variables mt = m / beta, dt = (dm/ds) / dbeta, which removes every
-// multiply that is not fused:   mt' = alpha mt + y,   e = y + gamma mt  (gamma = -c beta),   dt' = alpha dt + e,
-// i.e. z' = Phi z + (y, y) with Phi = [[alpha, 0], [gamma, alpha]]  (5 FMA per frame in phase 3).
-// sum e^2 is unchanged and sum e dm = dbeta * sum e dt (applied once, in diag_adam_kernel).
-// The chunk is processed as two independent half-chunks (two dependency chains in flight per lane):
-// the zero-state responses of the halves are combined with Phi^(L/2), and the second half of phase 3
-// starts from the exact mid-chunk state Phi^(L/2) z_in + z_a.
-// (cm, cd) is the warp's carry: state at the first frame of this warp-tile on entry, of the next on exit.
-template <class P, int L, bool FULL, bool ACC>
-__device__ inline void diag_warp_tile(const P (&y)[L], int nvalid, const ChanConst<P>& k, P a_lane, P b_lane,
-                                      P& cm, P& cd, double& E2, double& G) {
-    constexpr int H = L / 2;
-    const int lane = threadIdx.x & 31;
-    const P alpha = k.alpha, gamma = k.gamma;
-    // phase 1: zero-state responses.  U = sum alpha^(H-1-i) y_i (= mt),  W = sum alpha^(H-1-i) U_i
-    P Ua = P(0), Wa = P(0), Ub = P(0), Wb = P(0);
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        Wa = fma(alpha, Wa, Ua);
-        Wb = fma(alpha, Wb, Ub);
-        Ua = fma(alpha, Ua, y[i]);
-        Ub = fma(alpha, Ub, y[H + i]);
-    }
-    const P zam = Ua, zad = fma(gamma, Wa, Ua);   // first half from a zero state: (mt, dt)
-    const P zbm = Ub, zbd = fma(gamma, Wb, Ub);   // second half from a zero state
-    const P aH = k.aH, bH = k.bH;                 // Phi^(L/2)
-    P zm = fma(aH, zam, zbm);
-    P zd = fma(aH, zad, fma(bH, zam, zbd));
-    // warp inclusive scan with the closed-form powers of Phi
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int d = 1 << q;
-        const P pm = __shfl_up_sync(0xffffffffu, zm, d);
-        const P pd = __shfl_up_sync(0xffffffffu, zd, d);
-        if (lane >= d) {
-            zd = fma(k.aL[q], pd, fma(k.bL[q], pm, zd));
-            zm = fma(k.aL[q], pm, zm);
-        }
-    }
-    P em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
-    if (lane == 0) { em = P(0); ed = P(0); }
-    const P tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);  // warp aggregate
-    const P cm0 = cm, cd0 = cd;
-    cm = fma(k.aW, cm0, tm);                       // carry for the next warp-tile: Phi^(32 L) c + aggregate
-    cd = fma(k.aW, cd0, fma(k.bW, cm0, td));
-    if (!ACC) return;
-    // exact states at the start of the two half-chunks
-    P m0 = fma(a_lane, cm0, em);
-    P d0 = fma(a_lane, cd0, fma(b_lane, cm0, ed));
-    P m1 = fma(aH, m0, zam);
-    P d1 = fma(aH, d0, fma(bH, m0, zad));
-    // phase 3 (5 FMA per frame)
-    P e2a = P(0), ga = P(0), e2b = P(0), gb = P(0);
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        const P ea = fma(gamma, m0, y[i]);
-        const P eb = fma(gamma, m1, y[H + i]);
-        m0 = fma(alpha, m0, y[i]);
-        m1 = fma(alpha, m1, y[H + i]);
-        if (FULL || i < nvalid) { e2a = fma(ea, ea, e2a); ga = fma(ea, d0, ga); }
-        if (FULL || H + i < nvalid) { e2b = fma(eb, eb, e2b); gb = fma(eb, d1, gb); }
-        d0 = fma(alpha, d0, ea);
-        d1 = fma(alpha, d1, eb);
-    }
-    E2 += (double)(e2a + e2b);
-    G += (double)(ga + gb);
-}
-
-#ifndef EKS_EARLY_ISSUE
-#define EKS_EARLY_ISSUE 1
-#endif
-#ifndef EKS_L2_PREFETCH
-#define EKS_L2_PREFETCH 0   // warp-tiles of look-ahead for an L2 prefetch of the observation stream (0 = off).
-                            // Measured on the c5 bench: 2 -> 35.4 ms, 4 -> 37.4 ms, 8 -> 45.0 ms against 32.4 ms without:
-                            // the memory system is already saturated, extra requests only add contention
-#endif
-#ifndef EKS_FFMA2
-#define EKS_FFMA2 2   // fp32: packed FFMA2 (sm_100) for the two half-chunk chains of diag_warp_tile.
-                      // 0 = scalar FFMA (33.0 ms optimiser stage on the c5 bench), 1 = 4-byte cp.async into an interleaved
-                      // SMEM layout so that pairs load directly (34.9 ms: the 4x LDGSTS count costs more than the MOVs it
-                      // saves), 2 = 16-byte ring, pairs formed in registers (32.4 ms), 3 = same with four quarter-chunk
-                      // chains (32.4 ms: the dependent-FMA depth is not the limiter either)
-#endif
-
-// fp32 variant of diag_warp_tile on PACKED pairs: y2[i] = (y[i], y[H + i]) holds one frame of each half-chunk, so
-// the two independent dependency chains of the scalar version become the two lanes of one FFMA2 (Blackwell's
-// packed fp32 FMA: two IEEE fused multiply-adds per issue slot, bit-identical to the scalar code).  Halves the
-// floating-point instruction count of a kernel that is issue-bound (ncu: 67 % issue utilisation at 73 % of HBM peak).
-template <int L, bool FULL, bool ACC>
-__device__ inline void diag_warp_tile_f2(const float2 (&y2)[L / 2], int nvalid, const ChanConst<float>& k, float a_lane,
-                                         float b_lane, float& cm, float& cd, double& E2, double& G) {
-    constexpr int H = L / 2;
-    const int lane = threadIdx.x & 31;
-    const float alpha = k.alpha, gamma = k.gamma;
-    const float2 al2 = make_float2(alpha, alpha), ga2 = make_float2(gamma, gamma);
-    float2 U = make_float2(0.f, 0.f), W = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        W = __ffma2_rn(al2, W, U);
-        U = __ffma2_rn(al2, U, y2[i]);
-    }
-    const float2 zd2 = __ffma2_rn(ga2, W, U);      // (zad, zbd)
-    const float zam = U.x, zbm = U.y, zad = zd2.x, zbd = zd2.y;
-    const float aH = k.aH, bH = k.bH;
-    float zm = fmaf(aH, zam, zbm);
-    float zd = fmaf(aH, zad, fmaf(bH, zam, zbd));
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int d = 1 << q;
-        const float pm = __shfl_up_sync(0xffffffffu, zm, d);
-        const float pd = __shfl_up_sync(0xffffffffu, zd, d);
-        if (lane >= d) {
-            zd = fmaf(k.aL[q], pd, fmaf(k.bL[q], pm, zd));
-            zm = fmaf(k.aL[q], pm, zm);
-        }
-    }
-    float em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
-    if (lane == 0) { em = 0.f; ed = 0.f; }
-    const float tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);
-    const float cm0 = cm, cd0 = cd;
-    cm = fmaf(k.aW, cm0, tm);
-    cd = fmaf(k.aW, cd0, fmaf(k.bW, cm0, td));
-    if (!ACC) return;
-    const float m0 = fmaf(a_lane, cm0, em);
-    const float d0 = fmaf(a_lane, cd0, fmaf(b_lane, cm0, ed));
-    float2 m = make_float2(m0, fmaf(aH, m0, zam));
-    float2 dd = make_float2(d0, fmaf(aH, d0, fmaf(bH, m0, zad)));
-    float2 e2 = make_float2(0.f, 0.f), gg = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        const float2 e = __ffma2_rn(ga2, m, y2[i]);
-        m = __ffma2_rn(al2, m, y2[i]);
-        if (FULL) {
-            e2 = __ffma2_rn(e, e, e2);
-            gg = __ffma2_rn(e, dd, gg);
-        } else {
-            if (i < nvalid) { e2.x = fmaf(e.x, e.x, e2.x); gg.x = fmaf(e.x, dd.x, gg.x); }
-            if (H + i < nvalid) { e2.y = fmaf(e.y, e.y, e2.y); gg.y = fmaf(e.y, dd.y, gg.y); }
-        }
-        dd = __ffma2_rn(al2, dd, e);
-    }
-    E2 += (double)(e2.x + e2.y);
-    G += (double)(gg.x + gg.y);
-}
-
-// Quarter-chunk version of diag_warp_tile_f2: FOUR independent chains of L/4 frames (two FFMA2 streams), which
-// halves the dependent-FMA depth of phases 1 and 3 (the kernel is latency bound: ~50 % issue utilisation with six
-// warps per scheduler).  ya[i] = (y[i], y[Q+i]), yb[i] = (y[2Q+i], y[3Q+i]).
-template <int L, bool FULL, bool ACC>
-__device__ inline void diag_warp_tile_f4(const float2 (&ya)[L / 4], const float2 (&yb)[L / 4], int nvalid,
-                                         const ChanConst<float>& k, float a_lane, float b_lane, float& cm, float& cd,
-                                         double& E2, double& G) {
-    constexpr int Q = L / 4;
-    const int lane = threadIdx.x & 31;
-    const float alpha = k.alpha, gamma = k.gamma;
-    const float2 al2 = make_float2(alpha, alpha), ga2 = make_float2(gamma, gamma);
-    float2 Ua = make_float2(0.f, 0.f), Wa = Ua, Ub = Ua, Wb = Ua;
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        Wa = __ffma2_rn(al2, Wa, Ua);
-        Wb = __ffma2_rn(al2, Wb, Ub);
-        Ua = __ffma2_rn(al2, Ua, ya[i]);
-        Ub = __ffma2_rn(al2, Ub, yb[i]);
-    }
-    const float2 Da = __ffma2_rn(ga2, Wa, Ua), Db = __ffma2_rn(ga2, Wb, Ub);   // zero-state (mt, dt) of the quarters
-    const float z0m = Ua.x, z1m = Ua.y, z2m = Ub.x, z3m = Ub.y;
-    const float z0d = Da.x, z1d = Da.y, z2d = Db.x, z3d = Db.y;
-    const float aQ = k.aQ, bQ = k.bQ, aH = k.aH, bH = k.bH;
-    // halves: Phi^Q z0 + z1 and Phi^Q z2 + z3; chunk: Phi^(2Q) (first half) + second half
-    const float h0m = fmaf(aQ, z0m, z1m), h0d = fmaf(aQ, z0d, fmaf(bQ, z0m, z1d));
-    const float h1m = fmaf(aQ, z2m, z3m), h1d = fmaf(aQ, z2d, fmaf(bQ, z2m, z3d));
-    float zm = fmaf(aH, h0m, h1m);
-    float zd = fmaf(aH, h0d, fmaf(bH, h0m, h1d));
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int d = 1 << q;
-        const float pm = __shfl_up_sync(0xffffffffu, zm, d);
-        const float pd = __shfl_up_sync(0xffffffffu, zd, d);
-        if (lane >= d) {
-            zd = fmaf(k.aL[q], pd, fmaf(k.bL[q], pm, zd));
-            zm = fmaf(k.aL[q], pm, zm);
-        }
-    }
-    float em = __shfl_up_sync(0xffffffffu, zm, 1), ed = __shfl_up_sync(0xffffffffu, zd, 1);
-    if (lane == 0) { em = 0.f; ed = 0.f; }
-    const float tm = __shfl_sync(0xffffffffu, zm, 31), td = __shfl_sync(0xffffffffu, zd, 31);
-    const float cm0 = cm, cd0 = cd;
-    cm = fmaf(k.aW, cm0, tm);
-    cd = fmaf(k.aW, cd0, fmaf(k.bW, cm0, td));
-    if (!ACC) return;
-    // exact states at the start of the four quarters
-    const float m0 = fmaf(a_lane, cm0, em);
-    const float d0 = fmaf(a_lane, cd0, fmaf(b_lane, cm0, ed));
-    const float m1 = fmaf(aQ, m0, z0m), d1 = fmaf(aQ, d0, fmaf(bQ, m0, z0d));
-    const float m2 = fmaf(aH, m0, h0m), d2 = fmaf(aH, d0, fmaf(bH, m0, h0d));
-    const float m3 = fmaf(aQ, m2, z2m), d3 = fmaf(aQ, d2, fmaf(bQ, m2, z2d));
-    float2 ma = make_float2(m0, m1), da = make_float2(d0, d1), mb = make_float2(m2, m3), db = make_float2(d2, d3);
-    float2 e2a = make_float2(0.f, 0.f), ga = e2a, e2b = e2a, gb = e2a;
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const float2 ea = __ffma2_rn(ga2, ma, ya[i]);
-        const float2 eb = __ffma2_rn(ga2, mb, yb[i]);
-        ma = __ffma2_rn(al2, ma, ya[i]);
-        mb = __ffma2_rn(al2, mb, yb[i]);
-        if (FULL) {
-            e2a = __ffma2_rn(ea, ea, e2a); ga = __ffma2_rn(ea, da, ga);
-            e2b = __ffma2_rn(eb, eb, e2b); gb = __ffma2_rn(eb, db, gb);
-        } else {
-            if (i < nvalid) { e2a.x = fmaf(ea.x, ea.x, e2a.x); ga.x = fmaf(ea.x, da.x, ga.x); }
-            if (Q + i < nvalid) { e2a.y = fmaf(ea.y, ea.y, e2a.y); ga.y = fmaf(ea.y, da.y, ga.y); }
-            if (2 * Q + i < nvalid) { e2b.x = fmaf(eb.x, eb.x, e2b.x); gb.x = fmaf(eb.x, db.x, gb.x); }
-            if (3 * Q + i < nvalid) { e2b.y = fmaf(eb.y, eb.y, e2b.y); gb.y = fmaf(eb.y, db.y, gb.y); }
-        }
-        da = __ffma2_rn(al2, da, ea);
-        db = __ffma2_rn(al2, db, eb);
-    }
-    E2 += (double)((e2a.x + e2a.y) + (e2b.x + e2b.y));
-    G += (double)((ga.x + ga.y) + (gb.x + gb.y));
-}
-
-// fp32 ring fill for the packed variant: 4-byte cp.async, element q of a lane's chunk lands in the interleaved slot
-// (q mod H) * 2 + q / H, so that one 16-byte shared load delivers two (y[i], y[H + i]) register pairs.
-// Instruction i moves chunk i: 32 consecutive frames = one coalesced 128-byte request, conflict-free in SMEM.
-__device__ inline void warp_issue_tile_f2(unsigned char* stage, const float* __restrict__ plane, int t0, int e_min,
-                                          int n, bool inner) {
-    constexpr int L = OPT_CHUNK_BYTES / 4, H = L / 2;
-    const int lane = threadIdx.x & 31;
-    const int pos = ((lane & (H - 1)) << 1) | (lane / H);
-    unsigned char* dst = stage + pos * 4;
-    const float* src = plane + t0 + lane;
-    if (inner) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * OPT_PAD_BYTES);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i * L) : "memory");
-        }
-    } else {
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int e = t0 + i * L + lane;
-            const int valid = (e < n && e >= e_min) ? 4 : 0;
-            cp_async_4(dst + i * OPT_PAD_BYTES, plane + (valid > 0 ? e : 0), valid);
-        }
-    }
-}
-
-// per-warp ring stage: 32 padded chunks
-constexpr int WRP_STAGE_BYTES = 32 * OPT_PAD_BYTES;
-
-// Asynchronous copy of one warp-tile (32 x L frames starting at frame t0) into a warp's ring stage; frames
-// outside [e_min, n) are zero-filled without touching memory.  Lane l fetches granules l, l+32, ...:
-// every instruction is one fully coalesced 512-byte request.
-template <class P>
-__device__ inline void warp_issue_tile(unsigned char* stage, const P* __restrict__ plane, int t0, int e_min, int n,
-                                       bool vec, bool inner) {
-    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    constexpr int EPG = 16 / (int)sizeof(P);
-    constexpr int GPC = OPT_CHUNK_BYTES / 16;
-    const int lane = threadIdx.x & 31;
-    if (vec && inner) {
-        const int j0 = lane / GPC, q = lane % GPC;
-        const P* src = plane + t0 + j0 * L + q * EPG;
-        unsigned char* dst = stage + j0 * OPT_PAD_BYTES + q * 16;
-        constexpr int CPI = 32 / GPC;  // chunks covered per instruction
-#pragma unroll
-        for (int i = 0; i < GPC; ++i) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i * CPI * OPT_PAD_BYTES);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i * CPI * L) : "memory");
-        }
-    } else if (vec) {
-#pragma unroll
-        for (int i = 0; i < GPC; ++i) {
-            const int v = i * 32 + lane;
-            const int j = v / GPC, q = v - j * GPC;
-            const int e = t0 + j * L + q * EPG;
-            int valid = max(0, min(EPG, n - e)) * (int)sizeof(P);
-            if (e < e_min) valid = 0;  // e_min is chunk aligned: whole granules
-            cp_async_16(stage + j * OPT_PAD_BYTES + q * 16, plane + (valid > 0 ? e : 0), valid);
-        }
-    } else {
-#pragma unroll 4
-        for (int i = 0; i < L; ++i) {
-            const int v = i * 32 + lane;
-            const int j = v / L, q = v - j * L;
-            const int e = t0 + j * L + q;
-            const int valid = (e < n && e >= e_min) ? (int)sizeof(P) : 0;
-            if (sizeof(P) == 4) cp_async_4(stage + j * OPT_PAD_BYTES + q * 4, plane + (valid > 0 ? e : 0), valid);
-            else cp_async_8(stage + j * OPT_PAD_BYTES + q * 8, plane + (valid > 0 ? e : 0), valid);
-        }
-    }
-}
-
 // ---- kernel A: one NLL(+d/ds) evaluation.  grid = (nseg, 2 * B): CTA (k, 2b+c) handles segment k of
-// channel c of sequence b, and each of its 8 warps an independent contiguous run of warp-tiles (32 lanes x
-// L frames) inside it.  A run starts from the exact state at t_c (first run, or slow forgetting) or from a
-// zero state `warm` frames earlier, which is exact to rounding because the steady-state filter forgets its
-// initial state geometrically (alpha^warm < 1e-14 / 1e-28).  Warps never synchronise with each other until
-// the final reduction; each streams its own 2-stage cp.async ring.
+// channel c of sequence b (diag_stream_cta).
 template <class P>
 __global__ void __launch_bounds__(OPT_NT, EKS_OPT_MINBLOCKS) diag_nll_kernel(const __grid_constant__ DiagOptArgs<P> a) {
     __shared__ ChanConst<P> shk;
     __shared__ double red[OPT_NW][2];
     extern __shared__ __align__(16) unsigned char ring[];
-    constexpr int L = OPT_CHUNK_BYTES / (int)sizeof(P);
-    constexpr int WT = 32 * L;  // frames per warp-tile
-    using V = typename DiagTraits<P>::vec_t;
-    constexpr int VW = DiagTraits<P>::VW;
     const int seg = blockIdx.x, b = blockIdx.y >> 1, c = blockIdx.y & 1;
     const int blk = a.seq_block[b];
     if (blk < a.blk_lo || blk >= a.blk_hi || a.bstate[blk].done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const ChanState<P>& cs = a.cstate[(long long)b * 2 + c];
+    const int warp = threadIdx.x >> 5;
     double* part = a.partials + (((long long)b * 2 + c) * a.nseg + seg) * 2;
-    const int t_c = cs.t_c;
-    if (threadIdx.x == 0) shk = cs.k;
-    __syncthreads();
-    // this warp's run of warp-tiles
-    const int nwt = (a.n - t_c + WT - 1) / WT;
-    const int nrun = a.nseg * OPT_NW;
-    const int wpr = (nwt + nrun - 1) / nrun;
-    const int run = seg * OPT_NW + warp;
-    const int wt_lo = min(nwt, run * wpr), wt_hi = min(nwt, wt_lo + wpr);
-    double E2 = 0, G = 0;
-    if (wt_lo < wt_hi) {
-        // warm-up: whole chunks, starting `warm` frames before the run
-        const int warm_chunks = (cs.warm + L - 1) / L;
-        const long long e_min_ll = (long long)t_c + (long long)wt_lo * WT - (long long)warm_chunks * L;
-        int first_wt, e_min;
-        P cm, cd;
-        if (wt_lo == 0 || e_min_ll <= (long long)t_c) {
-            first_wt = 0; e_min = 0; cm = cs.z0[0]; cd = cs.z0[1];
-        } else {
-            e_min = (int)e_min_ll;
-            first_wt = (e_min - t_c) / WT;
-            cm = P(0); cd = P(0);
-        }
-        const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
-        const P mean = a.ymean ? a.ymean[(long long)b * 2 + c] : P(0);
-        const bool vec = (reinterpret_cast<uintptr_t>(yc + t_c) & 15) == 0;
-        const P a_lane = cs.a_lane[lane], b_lane = cs.b_lane[lane];
-        unsigned char* wring = ring + warp * (OPT_STAGES * WRP_STAGE_BYTES);
-        const int nt = wt_hi - first_wt;
-        auto issue = [&](int stage, int wt) {
-            const int t0i = t_c + wt * WT;
-            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 1)
-                warp_issue_tile_f2(wring + stage * WRP_STAGE_BYTES, reinterpret_cast<const float*>(yc), t0i, e_min,
-                                   a.n, t0i >= e_min && t0i + WT <= a.n);
-            else
-                warp_issue_tile<P>(wring + stage * WRP_STAGE_BYTES, yc, t0i, e_min, a.n, vec,
-                                   t0i >= e_min && t0i + WT <= a.n);
-#if EKS_L2_PREFETCH > 0
-            // pull a later warp-tile of this run into L2 so that the ring is filled at L2 latency: the SMEM ring
-            // (all of the SM's shared memory at 3 CTAs x 8 warps x 2 stages) cannot hold a DRAM latency of bytes
-            const int wtp = wt + EKS_L2_PREFETCH;
-            if (lane == 0 && vec && wtp < wt_hi) {
-                const P* pa = yc + t_c + (long long)wtp * WT;
-                const int bytes = (int)min((long long)WT, (long long)a.n - (t_c + (long long)wtp * WT)) * (int)sizeof(P) & ~15;
-                if (bytes > 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(pa), "r"(bytes) : "memory");
-            }
-#endif
-        };
-        // EKS_EARLY_ISSUE: a stage is free as soon as its tile sits in registers, i.e. BEFORE the arithmetic on that
-        // tile.  Refilling it there (tile it+2) keeps two tiles outstanding per warp during the arithmetic instead of
-        // one -- twice the bytes in flight from the same shared memory (the ring already fills the SM).
-        constexpr bool EARLY = (EKS_EARLY_ISSUE != 0) && (OPT_STAGES == 2) && !(sizeof(P) == 4 && EKS_FFMA2 == 1);
-#pragma unroll
-        for (int st = 0; st < (EARLY ? OPT_STAGES : OPT_STAGES - 1); ++st) {
-            if (st < nt) issue(st, first_wt + st);
-            cp_async_commit();
-        }
-        for (int it = 0; it < nt; ++it) {
-            if (!EARLY) {
-                const int nx = it + OPT_STAGES - 1;
-                // the stage about to be refilled was read in iteration it-1; make sure every lane is done with it
-                __syncwarp();
-                if (nx < nt) issue(nx % OPT_STAGES, first_wt + nx);
-                cp_async_commit();
-            }
-            cp_async_wait<OPT_STAGES - 1>();
-            __syncwarp();  // tile `it` has landed for every lane of this warp
-            const unsigned char* mine = wring + (it % OPT_STAGES) * WRP_STAGE_BYTES + lane * OPT_PAD_BYTES;
-            const int t0 = t_c + (first_wt + it) * WT;
-            const int cstart = t0 + lane * L;
-            const bool inner = (t0 >= e_min) && (t0 + WT <= a.n);  // warp-uniform: no masked frames
-            const bool acc = (first_wt + it) >= wt_lo;
-            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 1) {
-                constexpr int H = L / 2;
-                float2 y2[H];
-                const float2 nm2 = make_float2(-(float)mean, -(float)mean);
-                if (inner) {
-#pragma unroll
-                    for (int i = 0; i < L / 4; ++i) {
-                        const float4 v = *reinterpret_cast<const float4*>(mine + i * 16);
-                        y2[2 * i] = __fadd2_rn(make_float2(v.x, v.y), nm2);
-                        y2[2 * i + 1] = __fadd2_rn(make_float2(v.z, v.w), nm2);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < L / 4; ++i) {
-                        const float4 v = *reinterpret_cast<const float4*>(mine + i * 16);
-                        const float e[4] = {v.x, v.y, v.z, v.w};
-                        float o[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int fr = cstart + (q & 1) * H + 2 * i + (q >> 1);
-                            o[q] = (fr >= e_min && fr < a.n) ? e[q] - (float)mean : 0.f;
-                        }
-                        y2[2 * i] = make_float2(o[0], o[1]);
-                        y2[2 * i + 1] = make_float2(o[2], o[3]);
-                    }
-                }
-                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
-                float fcm = (float)cm, fcd = (float)cd;
-                if (!acc) diag_warp_tile_f2<L, true, false>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else if (inner) diag_warp_tile_f2<L, true, true>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else diag_warp_tile_f2<L, false, true>(y2, max(0, min(L, a.n - cstart)), kk, (float)a_lane, (float)b_lane,
-                                                       fcm, fcd, E2, G);
-                cm = (P)fcm; cd = (P)fcd;
-                continue;
-            }
-            P y[L];
-            if (inner) {
-#pragma unroll
-                for (int i = 0; i < L / VW; ++i) {
-                    const V v = *reinterpret_cast<const V*>(mine + i * 16);
-                    const P* e = reinterpret_cast<const P*>(&v);
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) y[i * VW + q] = e[q] - mean;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < L / VW; ++i) {
-                    const V v = *reinterpret_cast<const V*>(mine + i * 16);
-                    const P* e = reinterpret_cast<const P*>(&v);
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) {
-                        const int fr = cstart + i * VW + q;
-                        y[i * VW + q] = (fr >= e_min && fr < a.n) ? e[q] - mean : P(0);
-                    }
-                }
-            }
-            if (EARLY) {   // tile `it` is in registers: refill its stage with tile it+2 before the arithmetic
-                __syncwarp();
-                if (it + 2 < nt) issue(it % OPT_STAGES, first_wt + it + 2);
-                cp_async_commit();
-            }
-            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 3) {   // 16-byte ring, four quarter-chunk chains
-                constexpr int Q = L / 4;
-                float2 ya[Q], yb[Q];
-#pragma unroll
-                for (int i = 0; i < Q; ++i) {
-                    ya[i] = make_float2((float)y[i], (float)y[Q + i]);
-                    yb[i] = make_float2((float)y[2 * Q + i], (float)y[3 * Q + i]);
-                }
-                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
-                float fcm = (float)cm, fcd = (float)cd;
-                if (!acc) diag_warp_tile_f4<L, true, false>(ya, yb, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else if (inner) diag_warp_tile_f4<L, true, true>(ya, yb, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else diag_warp_tile_f4<L, false, true>(ya, yb, max(0, min(L, a.n - cstart)), kk, (float)a_lane,
-                                                       (float)b_lane, fcm, fcd, E2, G);
-                cm = (P)fcm; cd = (P)fcd;
-                continue;
-            }
-            if constexpr (sizeof(P) == 4 && EKS_FFMA2 == 2) {   // 16-byte ring, pairs formed in registers
-                constexpr int H = L / 2;
-                float2 y2[H];
-#pragma unroll
-                for (int i = 0; i < H; ++i) y2[i] = make_float2((float)y[i], (float)y[H + i]);
-                const ChanConst<float>& kk = reinterpret_cast<const ChanConst<float>&>(shk);
-                float fcm = (float)cm, fcd = (float)cd;
-                if (!acc) diag_warp_tile_f2<L, true, false>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else if (inner) diag_warp_tile_f2<L, true, true>(y2, L, kk, (float)a_lane, (float)b_lane, fcm, fcd, E2, G);
-                else diag_warp_tile_f2<L, false, true>(y2, max(0, min(L, a.n - cstart)), kk, (float)a_lane, (float)b_lane,
-                                                       fcm, fcd, E2, G);
-                cm = (P)fcm; cd = (P)fcd;
-                continue;
-            }
-            if (!acc) diag_warp_tile<P, L, true, false>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
-            else if (inner) diag_warp_tile<P, L, true, true>(y, L, shk, a_lane, b_lane, cm, cd, E2, G);
-            else diag_warp_tile<P, L, false, true>(y, max(0, min(L, a.n - cstart)), shk, a_lane, b_lane, cm, cd, E2, G);
-        }
-        cp_async_wait<0>();
-    }
-    E2 = warp_sum(E2);
-    G = warp_sum(G);
-    if (lane == 0) { red[warp][0] = E2; red[warp][1] = G; }
-    __syncthreads();
+    double te, tg;
+    diag_stream_cta<P>(a, b, c, seg, a.nseg, ring, shk, red, te, tg);
     __shared__ int is_last;
     if (threadIdx.x == 0) {
-        double te = 0, tg = 0;
-        for (int w = 0; w < OPT_NW; ++w) { te += red[w][0]; tg += red[w][1]; }
         part[0] = te;
         part[1] = tg;
         // the CTA that completes its block's evaluation takes the Adam step and prepares the next evaluation

@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include "common.cuh"
 #include "ekf_generic.cuh"
+#include <cstring>
+#include <cstdlib>
 #include "generic.cuh"
 #include "diag.cuh"
 #include "../../include/eks_b200.h"
@@ -245,7 +247,7 @@ extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m
 }
 
 extern "C" size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T) {
-    const size_t a1 = diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
+    const size_t a1 = diag_lag_workspace_bytes(dtype, n_blocks, B, T);   // >= diag_optimize_workspace_bytes
     const size_t a2 = T >= GEN_RUNS_MIN_FRAMES ? generic_runs_optimize_workspace_bytes(dtype, n_blocks, B, D, T) +
                                                      linear_steady_workspace_bytes(dtype, B, D, O, T) : 0;
     return a1 > a2 ? a1 : a2;
@@ -262,7 +264,8 @@ extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void*
     cudaStream_t st = (cudaStream_t)stream;
     // model_structure == EKS_STRUCT_DIAG: the caller asserts D == O == 2 with diagonal A, C, Q, S0
     // (single-camera model) -> time-parallel persistent kernel (diag.cu); one contiguous span only
-    if (model_structure == EKS_STRUCT_DIAG && D == 2 && O == 2 && ncam == 0 && n_spans <= 1) {
+    if ((model_structure == EKS_STRUCT_DIAG || model_structure == EKS_STRUCT_DIAG_STREAM) && D == 2 && O == 2 &&
+        ncam == 0 && n_spans <= 1) {
         EKS_REQUIRE(y_base && y_off && Rconst && block_off && members && s_log0 && s_log_out && last_loss_out &&
                         iters_out && m0 && S0 && A && Q && C, "optimize_s: null pointer");
         int t_begin = 0, n = T;
@@ -270,9 +273,16 @@ extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void*
             EKS_REQUIRE(s0[0] >= 0 && s1[0] <= T && s0[0] < s1[0], "bad span 0");
             t_begin = s0[0]; n = s1[0] - s0[0];
         }
-        return diag_optimize(dtype, B, T, m0, S0, A, Q, C, y_base, y_seq_stride, y_off, ymean, Rconst, t_begin, n,
-                             n_blocks, block_off, members, s_log0, lr, lo, hi, tol, cap, s_log_out, last_loss_out,
-                             iters_out, trace, trace_cap, workspace, workspace_bytes, st);
+        // default: lag-statistics optimiser (one pass over the observations, one persistent launch; diag_lag.cu).
+        // EKS_OPT_MODE=stream selects the one-streaming-launch-per-evaluation loop of diag.cu (cross-check).
+        static const bool stream_mode = [] { const char* e = getenv("EKS_OPT_MODE"); return e && !strcmp(e, "stream"); }();
+        if (stream_mode || model_structure == EKS_STRUCT_DIAG_STREAM)
+            return diag_optimize(dtype, B, T, m0, S0, A, Q, C, y_base, y_seq_stride, y_off, ymean, Rconst, t_begin, n,
+                                 n_blocks, block_off, members, s_log0, lr, lo, hi, tol, cap, s_log_out, last_loss_out,
+                                 iters_out, trace, trace_cap, workspace, workspace_bytes, st);
+        return diag_lag_optimize(dtype, B, T, m0, S0, A, Q, C, y_base, y_seq_stride, y_off, ymean, Rconst, t_begin, n,
+                                 n_blocks, block_off, members, s_log0, lr, lo, hi, tol, cap, s_log_out, last_loss_out,
+                                 iters_out, trace, trace_cap, workspace, workspace_bytes, st);
     }
     if (dtype == EKS_F32)
         return optimize_impl<float>(B, D, O, T, m0, S0, A, Q, C, ncam, cams, y_base, y_seq_stride, y_off, ymean,

@@ -21,7 +21,7 @@ OUT_COLS = ['x', 'y', 'likelihood', 'x_ens_median', 'y_ens_median', 'x_ens_var',
             'x_posterior_var', 'y_posterior_var']
 # where the ensemble kernel's (x_avg, y_avg, var_x, var_y, likelihood) land inside that block
 ENS_TO_OUT = [3, 4, 5, 6, 2]
-STRUCT_GENERAL, STRUCT_DIAG = 0, 1
+STRUCT_GENERAL, STRUCT_DIAG, STRUCT_DIAG_STREAM = 0, 1, 2
 # number of kernels of libeks_b200.so launched through this module (bench.py reports it)
 LAUNCH_COUNT = 0
 

@@ -35,10 +35,13 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
                               avg_mode='median', var_mode='confidence_weighted_var', dtype=torch.float32,
                               lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300, min_R_var=1e-4,
                               out: torch.Tensor | None = None, force_generic: bool = False,
-                              trace_cap: int = 0, timers: dict | None = None) -> SinglecamResult:
+                              trace_cap: int = 0, timers: dict | None = None,
+                              opt_mode: str = 'lag') -> SinglecamResult:
     """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
 
-    spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks."""
+    spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks.
+    opt_mode: 'lag' (one pass over the observations, closed-form NLL from lag statistics -- the default) or 'stream'
+    (one streaming pass per Adam evaluation); both are the same optimisation (tests compare them)."""
     assert raw.is_cuda and raw.dim() == 6 and raw.shape[2] == 1 and raw.shape[-1] == 3
 
     class _Stage:  # optional CUDA-event bracket per stage on the launching stream (bench.py)
@@ -94,7 +97,8 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
         with _Stage('optimize_s'):
             opt = ops.optimize_s(model, yv, T, Rconst, s_log0, blocks=all_blocks, ymean=ymean, spans=spans, lr=lr,
                                  s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
-                                 structure=ops.STRUCT_GENERAL if force_generic else ops.STRUCT_DIAG)
+                                 structure=ops.STRUCT_GENERAL if force_generic else (
+                                     ops.STRUCT_DIAG_STREAM if opt_mode == 'stream' else ops.STRUCT_DIAG))
         s_blk = torch.exp(opt['s_log'].double().clamp(s_bounds_log[0], s_bounds_log[1]))
         if all_blocks is None:
             s_finals = s_blk.view(S, K)

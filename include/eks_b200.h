@@ -32,6 +32,7 @@ extern "C" {
 #define EKS_MAX_STATE 6    /* max latent dimension */
 #define EKS_STRUCT_GENERAL 0 /* model_structure: no assumption */
 #define EKS_STRUCT_DIAG 1    /* caller asserts D == O == 2 and diagonal A, C, Q, S0 (singlecam model) */
+#define EKS_STRUCT_DIAG_STREAM 2 /* same model; force one streaming pass over the observations per evaluation */
 #define EKS_CAM_STRIDE 29  /* R(9 row-major) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 */
 
 const char* eks_last_error(void);
@@ -101,7 +102,11 @@ int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const vo
  * s_log_out (real, the value AFTER the last update, core.py:675), last_loss_out (real), iters_out (int).
  * The caller forms s = exp(clip(s_log, lo, hi)) (core.py:694).  trace (nullable): [n_blocks][trace_cap][3]
  * real rows (s_log, loss, lr*grad) per iteration.  model_structure: EKS_STRUCT_GENERAL (one block per thread,
- * sequential in time) or EKS_STRUCT_DIAG (persistent CTA per block, exact time-parallel scan; needs <= 1 span). */
+ * sequential in time), EKS_STRUCT_DIAG (needs <= 1 span: lag statistics of the increments in ONE pass over the
+ * observations, then the whole Adam loop of a block in one persistent CTA evaluating the NLL in closed form from them,
+ * streaming an evaluation only where the closed form is not exact to rounding -- eks_b200/csrc/diag_lag.cu) or
+ * EKS_STRUCT_DIAG_STREAM (the exact time-parallel streaming evaluation once per Adam iteration, one launch each --
+ * eks_b200/csrc/diag.cu; also selected by the environment variable EKS_OPT_MODE=stream). */
 size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T);
 int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
                    const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
