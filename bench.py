@@ -1,18 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the full s-optimised single-camera EKS hot path on B200.
+"""bench.py -- throughput of the full s-optimised EKS hot path on B200 (BASELINE.json metric: keypoint-frames/s
+smoothed incl. s-optimisation; % of the HBM roofline).
 
-One "step" = one pass of the whole path (ensemble statistics -> s-optimisation -> filter + RTS smoother
--> nine output columns) over one batch of `--sessions` synthetic sessions per GPU.  The default workload
-is BASELINE.json config 5's per-GPU shard: sessions of 10 seeds x 20 keypoints x 1M frames; with
-`--gpus 8 --sessions 8` the job is exactly config 5 (64 sessions sharded over 8 B200, no collective on
-the data path: `scaling: weak`).  `--workload c2` runs config 2 (5 seeds x 17 keypoints x 100k frames).
+One "step" = one pass of the whole path (ensemble statistics -> initial guess / median R -> Adam on log s with the
+reference's stop rule -> filter + RTS smoother -> output columns) over one batch of synthetic sessions per GPU.
 
-Output: ONE JSON line (rank 0).  `value` = keypoint-frames/s with inputs resident in HBM; `e2e` = the
-same metric through the public API with HOST (pinned) inputs and outputs, copies inside the timed
-region; `roofline` = dominant kernel vs measured HBM peak; `cpu_baseline` = the CPU oracle (a port of
-the reference path, oracle/) timed on a bounded sample on this box's host cores.
-`--impl reference` times that CPU implementation only (the reference's own JAX path cannot be installed
-in this environment: jax/dynamax/optax are absent and there is no network).
+  --workload c5 (default)  BASELINE config 5's per-GPU shard: 8 sessions x (10 seeds x 20 keypoints x 10^6 frames),
+                           singlecam; `--gpus 8` = the whole 64-session job (sessions shard over the ranks with no
+                           collective on the data path: `scaling: weak`).  Config 5 does not fit ONE GPU resident
+                           (153.6 GB in + 46 GB out), so N = 1 runs 8 of its 64 sessions.
+  --workload c2            singlecam 5 seeds x 17 keypoints x 10^5 frames
+  --workload c3            multicam linear (PCA latent), 2 cameras x 4 keypoints x 10 seeds x 10^6 frames
+  --workload c4            calibrated pinhole EKF (fly rig), 3 cameras x 6 keypoints x 5 seeds x 5 10^5 frames
+
+Output: ONE JSON line (rank 0).
+  value        kf/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e          kf/s with HOST (pinned) inputs and outputs through the batched device pipeline, copies in the timed region
+  e2e_public   kf/s through the reference-facing call (ensemble_kalman_smoother_singlecam / _multicam: MarkerArray of
+               host arrays in, pandas DataFrames out), one session per call
+  roofline     the dominant kernel of the step (largest device time) against the measured HBM peak; `kernels` lists
+               every stage the same way; `pipeline_one_touch` the whole step against SURVEY 8(d)'s one-touch bytes
+  cpu_baseline the CPU oracle (oracle/, a port of the reference path) on a bounded sample on this box's host cores,
+               plus `shared_sequence`: Adam evaluation counts of the GPU and of the fp32 / fp64 oracle on the SAME data
+`--impl reference` times that CPU implementation only, on the same `config` (the reference's own JAX path cannot be
+installed here: jax / dynamax / optax are absent and there is no network).
 """
 import argparse
 import json
@@ -28,26 +39,55 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (seeds M, keypoints K, frames T, default sessions per GPU)
-    'c5': (10, 20, 1_000_000, 8),
-    'c2': (5, 17, 100_000, 1),
+    # name: kind, seeds M, cameras V, keypoints K, frames T, default sessions per GPU
+    'c5': dict(kind='singlecam', M=10, V=1, K=20, T=1_000_000, S=8),
+    'c2': dict(kind='singlecam', M=5, V=1, K=17, T=100_000, S=1),
+    'c3': dict(kind='multicam', M=10, V=2, K=4, T=1_000_000, S=1),
+    'c4': dict(kind='pinhole', M=5, V=3, K=6, T=500_000, S=1),
 }
+METRIC = 'keypoint-frames/sec smoothed incl. s-optimisation'
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
     ap.add_argument('--sessions', type=int, default=None, help='sessions per GPU per step')
     ap.add_argument('--frames', type=int, default=None)
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
+    ap.add_argument('--opt-mode', default='lag', choices=['lag', 'stream'], help='singlecam optimiser (pipeline.py)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-public', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--cpu-frames', type=int, default=20_000, help='frames per sequence of the CPU sample')
+    ap.add_argument('--cpu-frames', type=int, default=None, help='frames per sequence of the CPU sample')
+    ap.add_argument('--cpu-budget', type=float, default=150.0, help='seconds the reference arm may spend in total')
     return ap.parse_args()
+
+
+def workload_of(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.sessions:
+        w['S'] = args.sessions
+    if args.frames:
+        w['T'] = args.frames
+    return w
+
+
+def config_of(args, w):
+    """The SAME dict for both arms (--impl b200 / reference): names the workload, nothing measured."""
+    kind = {'singlecam': 'singlecam, per-keypoint Adam s-optimisation (reference stop rule)',
+            'multicam': 'multicam linear PCA latent (D=3), per-keypoint Adam s-optimisation',
+            'pinhole': 'multicam calibrated pinhole EKF (fly rig, D=3), per-keypoint Adam s-optimisation'}[w['kind']]
+    return {'workload': f"{args.workload}: {w['S']} sessions/GPU x {w['M']} seeds x {w['V']} cameras x {w['K']} keypoints x "
+                        f"{w['T']} frames, {kind}",
+            'sessions_per_gpu': w['S'], 'seeds': w['M'], 'cameras': w['V'], 'keypoints': w['K'], 'frames': w['T'],
+            'l2': ('inputs larger than L2 (resident raw tensor %.2f GB per GPU)' if
+                   w['S'] * w['M'] * w['V'] * w['T'] * w['K'] * 3 * (4 if args.dtype == 'f32' else 8) >= (1 << 30) else
+                   'L2 flushed between timed steps by an untimed 512 MB write (resident raw tensor %.2f GB per GPU)') % (
+                w['S'] * w['M'] * w['V'] * w['T'] * w['K'] * 3 * (4 if args.dtype == 'f32' else 8) / 1e9)}
 
 
 # ----------------------------------------------------------------------------- synthetic data (SURVEY 8d)
@@ -148,49 +188,78 @@ def synth_fly_host(M, K, T, seed, cams):
 
 
 # ----------------------------------------------------------------------------- CPU oracle leg
-def cpu_leg(M, K, T_sample, steps, warmup):
-    """Time the CPU oracle (oracle/liboracle.so, OpenMP over sequences) on one session of T_sample frames."""
+def synth_host(w, T, seed):
+    """one session of workload w with T frames: (M,V,T,K,3) float32"""
+    if w['kind'] == 'singlecam':
+        return synth_session_host(w['M'], w['K'], T, seed)
+    if w['kind'] == 'multicam':
+        return synth_multicam_host(w['M'], w['V'], w['K'], T, seed)
+    return synth_fly_host(w['M'], w['K'], T, seed, fly_cameras()[0])
+
+
+def oracle_run(w, raw, dtype):
     from oracle import oracle
-    raw = synth_session_host(M, K, T_sample, seed=0)
+    if w['kind'] == 'singlecam':
+        return oracle.singlecam(raw, dtype=dtype)
+    if w['kind'] == 'multicam':
+        return oracle.multicam(raw.astype(np.float64), dtype=dtype, quantile_keep_pca=50.0)
+    return oracle.multicam(raw.astype(np.float64), dtype=dtype,
+                           camgroup=os.path.join(ROOT, 'tests', 'golden', 'fly_calibration.toml'))
+
+
+def cpu_leg(w, T_sample, steps, warmup, raw=None):
+    """Time the CPU oracle (oracle/liboracle.so, OpenMP over sequences; fp32 like the reference's production path) on
+    ONE session of T_sample frames."""
+    if raw is None:
+        raw = synth_host(w, T_sample, seed=0)
     cores = os.cpu_count() or 1
     os.environ['OMP_NUM_THREADS'] = str(cores)   # torchrun exports OMP_NUM_THREADS=1: use every host core
     times, iters = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        r = oracle.singlecam(raw, dtype=np.float32)
+        r = oracle_run(w, raw, np.float32)
         dt = time.perf_counter() - t0
         iters = r['info']['iters']
         if i >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
-    return dict(value=K * T_sample / sec, unit='keypoint-frames/s', cores=cores, kind='port',
-                sample=f'1 session x {M} seeds x {K} keypoints x {T_sample} frames, fp32, oracle/liboracle.so '
-                       f'(C++/OpenMP restatement of the reference path; mean Adam iterations '
-                       f'{float(np.mean(iters)):.1f})',
-                sec_per_step=sec)
+    return dict(value=w['K'] * T_sample / sec, unit='keypoint-frames/s', cores=cores, kind='port',
+                sample=f"1 session x {w['M']} seeds x {w['V']} cameras x {w['K']} keypoints x {T_sample} frames, fp32, "
+                       f"oracle/liboracle.so (C++/OpenMP restatement of the reference path; mean Adam iterations "
+                       f"{float(np.mean(iters)):.1f}); the path is O(frames), kf/s does not depend on the frame count",
+                sec_per_step=sec, iters=[int(x) for x in iters])
+
+
+def cpu_rate_probe(w):
+    """kf/s of the oracle on a small probe (sizes the bounded sample)."""
+    T = min(w['T'], 20_000 if w['kind'] == 'singlecam' else 5_000)
+    return cpu_leg(w, T, 1, 0)['value']
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    M, K, T, S = WORKLOADS[args.workload]
-    Tc = min(args.cpu_frames, T)
-    res = cpu_leg(M, K, Tc, max(1, args.steps), min(args.warmup, 1))
+    w = workload_of(args)
+    if args.cpu_frames:
+        Tc = min(args.cpu_frames, w['T'])
+    else:   # the whole --steps/--warmup run must end within a few minutes: bound the frames per step
+        rate = cpu_rate_probe(w)
+        n_runs = max(1, args.steps) + min(args.warmup, 1)
+        Tc = int(min(w['T'], max(10_000, rate * args.cpu_budget / (n_runs * w['K']))))
+        Tc = (Tc // 1000) * 1000
+    res = cpu_leg(w, Tc, max(1, args.steps), min(args.warmup, 1))
     line = {
-        'impl': 'reference', 'metric': 'keypoint-frames/sec smoothed incl. s-optimisation', 'value': res['value'],
-        'unit': 'keypoint-frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': res['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: sessions of {M} seeds x {K} keypoints x {T} frames, '
-                               f'singlecam, per-keypoint s-optimisation (CPU sample: {Tc} frames/sequence, '
-                               'O(T) path => kf/s is frame-count independent)'},
+        'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'keypoint-frames/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['sec_per_step'] * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_of(args, w),
         'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-        'e2e': {'value': res['value'], 'unit': 'keypoint-frames/s', 'h2d_bytes_per_step': 0,
-                'd2h_bytes_per_step': 0},
+        'e2e': {'value': res['value'], 'unit': 'keypoint-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-        'note': 'the reference JAX/dynamax path is not installable here; this arm times oracle/, the CPU '
-                'restatement of the same algorithm, on all host cores',
+        'note': 'the reference JAX/dynamax path is not installable here; this arm times oracle/, the CPU restatement of '
+                'the same algorithm, on all host cores; each step = one session of the workload truncated to '
+                f'{Tc} frames (of {w["T"]}) so that the run ends within minutes',
     }
     print(json.dumps(line))
 
@@ -206,7 +275,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -244,11 +313,37 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def stage_bytes_per_kf(w, wbytes, stage, n_eval_mean, opt_mode):
+    """ALGORITHMIC bytes per keypoint-frame of one stage (SURVEY 8d "per-kernel" figures)."""
+    M, V = w['M'], w['V']
+    obs = 2 * V
+    D = 2 if w['kind'] == 'singlecam' else 3
+    if stage == 'ensemble':
+        return wbytes * (3 * M * V + 5 * V)                 # raw x, y, likelihood in; 5 planes per camera out
+    if stage == 'const_R_median':
+        return wbytes * obs                                 # one read of the variance planes
+    if stage == 'optimize_s':
+        if w['kind'] == 'singlecam' and opt_mode == 'lag':
+            return wbytes * obs                             # the observations are read ONCE (lag statistics)
+        return wbytes * obs * n_eval_mean                   # one read of the observations per evaluation
+    if stage == 'filter_smooth':
+        if w['kind'] == 'singlecam':
+            return wbytes * 4 * obs                         # y, var in; x, posterior var out (fused epilogue)
+        return wbytes * (2 * obs + D + D * D)               # y, var in; smoothed mean + covariance out
+    if stage == 'reproject':
+        return wbytes * (D + D * D + obs + 2 * obs)         # latent moments + var in; x, y, 2 posterior vars per camera
+    if stage == 'triangulate':
+        return wbytes * 3 * M * V + 24
+    if stage in ('center', 'pca', 'latent_init'):
+        return wbytes * (obs + 1)
+    return 0.0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from eks_b200 import ops
-    from eks_b200.pipeline import singlecam_smooth_sessions
+    from eks_b200.pipeline import multicam_smooth_sessions, singlecam_smooth_sessions
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -257,20 +352,27 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    M, K, T, S = WORKLOADS[args.workload]
-    if args.sessions:
-        S = args.sessions
-    if args.frames:
-        T = args.frames
+    w = workload_of(args)
+    kind, M, V, K, T, S = w['kind'], w['M'], w['V'], w['K'], w['T'], w['S']
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
-    w = 4 if args.dtype == 'f32' else 8
+    wb = 4 if args.dtype == 'f32' else 8
+    cams = fly_cameras()[0] if kind == 'pinhole' else None
 
     # resident inputs: S sessions on this GPU (distinct seeds per rank and session)
-    raw = torch.empty((S, M, 1, T, K, 3), device=dev, dtype=dtype)
+    raw = torch.empty((S, M, V, T, K, 3), device=dev, dtype=dtype)
     for s_ in range(S):
-        raw[s_] = synth_session_device(torch, M, K, T, seed=rank * 1000 + s_, device=dev, dtype=dtype)
-    out = torch.empty((S, K, 9, T), device=dev, dtype=dtype)
+        if kind == 'singlecam':
+            raw[s_] = synth_session_device(torch, M, K, T, seed=rank * 1000 + s_, device=dev, dtype=dtype)
+        else:
+            raw[s_] = torch.as_tensor(synth_host(w, T, seed=rank * 1000 + s_)).to(dev, dtype)
+    out_shape = (S, K, 9, T) if kind == 'singlecam' else (S, K, V, 9, T)
+    out = torch.empty(out_shape, device=dev, dtype=dtype)
     torch.cuda.synchronize()
+
+    def step(raw_, out_, timers=None):
+        if kind == 'singlecam':
+            return singlecam_smooth_sessions(raw_, dtype=dtype, out=out_, timers=timers, opt_mode=args.opt_mode)
+        return multicam_smooth_sessions(raw_, dtype=dtype, out=out_, timers=timers, quantile_keep_pca=50.0, cams=cams)
 
     def barrier():
         if world > 1:
@@ -280,49 +382,53 @@ def run_b200(args):
     timers = {}
     res = None
     for _ in range(args.warmup):
-        res = singlecam_smooth_sessions(raw, dtype=dtype, out=out)
+        res = step(raw, out)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ops.LAUNCH_COUNT = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    # inputs larger than L2 need no flush; small workloads (c2) get an untimed 512 MB write between the timed steps
+    resident = raw.numel() * wb
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if resident < (1 << 30) else None
+    evs = []
     for _ in range(args.steps):
-        res = singlecam_smooth_sessions(raw, dtype=dtype, out=out, timers=timers)
-    ev1.record()
+        if flush is not None:
+            flush.fill_(1)
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        res = step(raw, out, timers)
+        e1_.record()
+        evs.append((e0_, e1_))
     barrier()
     launches = ops.LAUNCH_COUNT
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = float(sum(a_.elapsed_time(b_) for a_, b_ in evs))
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    clocks = sampler.stop() if sampler else None
     kf_step = S * K * T                      # per GPU
     value = world * kf_step / (ms_step * 1e-3)
     iters = res.iters.double()
     n_eval_mean = float(iters.mean().item())
     n_eval_max = int(iters.max().item())
-
     # per-stage device times (CUDA events recorded on the launching stream inside the timed region)
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
 
-    # ---- e2e through the public API: host (pinned) inputs and outputs, copies inside the timed region
+    # ---- e2e, batched device pipeline: host (pinned) inputs and outputs, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         n_pin = min(S, 2)
-        h_in = [torch.empty((1, M, 1, T, K, 3), dtype=dtype).pin_memory() for _ in range(n_pin)]
+        sess_in, sess_out = (1, M, V, T, K, 3), (1,) + out_shape[1:]
+        h_in = [torch.empty(sess_in, dtype=dtype).pin_memory() for _ in range(n_pin)]
         for i in range(n_pin):
             h_in[i].copy_(raw[i:i + 1])
-        h_out = [torch.empty((1, K, 9, T), dtype=dtype).pin_memory() for _ in range(n_pin)]
+        h_out = [torch.empty(sess_out, dtype=dtype).pin_memory() for _ in range(n_pin)]
         torch.cuda.synchronize()
         s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        d_in = [torch.empty((1, M, 1, T, K, 3), device=dev, dtype=dtype) for _ in range(2)]
-        d_out = [torch.empty((1, K, 9, T), device=dev, dtype=dtype) for _ in range(2)]
+        d_in = [torch.empty(sess_in, device=dev, dtype=dtype) for _ in range(2)]
+        d_out = [torch.empty(sess_out, device=dev, dtype=dtype) for _ in range(2)]
 
         def e2e_step():
-            ev_in = [None, None]
-            ev_cmp = [None, None]
-            ev_out = [None, None]
+            ev_in, ev_cmp, ev_out = [None, None], [None, None], [None, None]
             for i in range(S):
                 b = i & 1
                 with torch.cuda.stream(s_in):
@@ -335,7 +441,7 @@ def run_b200(args):
                     s_cmp.wait_event(ev_in[b])
                     if ev_out[b] is not None:
                         s_cmp.wait_event(ev_out[b])
-                    singlecam_smooth_sessions(d_in[b], dtype=dtype, out=d_out[b])
+                    step(d_in[b], d_out[b])
                     ev_cmp[b] = torch.cuda.Event()
                     ev_cmp[b].record(s_cmp)
                 with torch.cuda.stream(s_out):
@@ -359,67 +465,132 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ms_e2e = float(te.item()) / n_e2e
+        h2d = int(S * M * V * T * K * 3 * wb)
+        d2h = int(np.prod(out_shape) * wb)
         e2e = {'value': world * kf_step / (ms_e2e * 1e-3), 'unit': 'keypoint-frames/s',
-               'h2d_bytes_per_step': int(S * M * T * K * 3 * w), 'd2h_bytes_per_step': int(S * K * 9 * T * w),
-               'ms_per_step': ms_e2e,
-               'how': 'per session: pinned H2D -> eks_b200.pipeline.singlecam_smooth_sessions -> pinned D2H, '
-                      'double-buffered on three streams'}
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e,
+               'h2d_gbs_per_rank': (h2d + d2h) / (ms_e2e * 1e-3) / 1e9,
+               'how': 'per session: pinned H2D -> eks_b200.pipeline.*_smooth_sessions -> pinned D2H, double-buffered on '
+                      'three streams; h2d_gbs_per_rank = (H2D + D2H bytes) / time on this rank'}
         del h_in, h_out, d_in, d_out
+
+    # ---- e2e through the reference-facing call: MarkerArray of host arrays in, pandas DataFrames out
+    e2e_public = None
+    if not args.no_public:
+        from eks_b200.marker_array import MarkerArray
+        host = raw[0].float().cpu().numpy() if dtype == torch.float32 else raw[0].cpu().numpy()
+        kps = [f'kp{k}' for k in range(K)]
+        if kind == 'singlecam':
+            from eks_b200.singlecam_smoother import ensemble_kalman_smoother_singlecam
+
+            def public():
+                return ensemble_kalman_smoother_singlecam(MarkerArray(host, data_fields=['x', 'y', 'likelihood']), kps)
+        else:
+            from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+            cg = fly_cameras()[1] if kind == 'pinhole' else None
+            names = [c.name for c in cg.cameras] if cg else [f'cam{v}' for v in range(V)]
+
+            def public():
+                return ensemble_kalman_smoother_multicam(MarkerArray(host, data_fields=['x', 'y', 'likelihood']), kps, names,
+                                                         quantile_keep_pca=50.0, camgroup=cg)
+        public()                                        # warm-up (allocator, pinned staging)
+        barrier()
+        n_pub = 2
+        t0 = time.perf_counter()
+        for _ in range(n_pub):
+            r_pub = public()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / n_pub
+        tp = torch.tensor([sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        sec = float(tp.item())
+        out_bytes = int(sum(df.to_numpy().nbytes for df in (r_pub[0] if isinstance(r_pub[0], list) else [r_pub[0]])))
+        e2e_public = {'value': world * K * T / sec, 'unit': 'keypoint-frames/s', 'sec_per_call': sec,
+                      'h2d_bytes_per_call': int(host.nbytes), 'd2h_bytes_per_call': out_bytes,
+                      'how': 'wall clock of one call of the reference-facing entry point on host arrays (MarkerArray in, '
+                             'DataFrames out), one session per call, every rank concurrently (max over ranks)'}
+        del host
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the persistent Adam / NLL kernel)
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (of measured)'
     else:
         peak, peak_src = 6650.0, 'fallback 6.65 TB/s (of fallback)'
-    opt_ms = stage_ms.get('optimize_s')
-    # dominant kernel: diag_nll_kernel, launched once per Adam evaluation.  Algorithmic bytes of one launch:
-    # every evaluation reads the observation planes of each still-active sequence once (SURVEY 8d:
-    # w * obs bytes per keypoint-frame per evaluation).  Launch duration = CUDA-event time of the optimiser
-    # stage / number of launches that had work (the interleaved one-warp Adam kernels, ~2% of the stage per
-    # the ncu launch list, are included => the fraction is slightly pessimistic).
-    n_launch = max(1, n_eval_max)
-    alg_bytes = float(iters.sum().item()) * T * 2 * w / n_launch
+    # ---- every stage against the HBM roofline: algorithmic bytes of the stage / its CUDA-event time
+    kernel_names = {'ensemble': 'ensemble_staged_kernel', 'const_R_median': 'select_hist_kernel + select_scan_kernel',
+                    'optimize_s': ('lag_stats_kernel + diag_lag_opt_kernel' if kind == 'singlecam' and args.opt_mode == 'lag'
+                                   else 'diag_nll_kernel' if kind == 'singlecam' else
+                                   'lin_prep_kernel + lin_runs_kernel + gen_runs_reduce_kernel' if kind == 'multicam' else
+                                   'gen_nll_runs_kernel + gen_runs_reduce_kernel'),
+                    'filter_smooth': 'diag_filter_kernel + diag_rts_kernel' if kind == 'singlecam' else
+                                     'gen_filter_runs_kernel + gen_rts_runs_kernel',
+                    'reproject': 'reproject_kernel', 'triangulate': 'triangulate_mean_kernel'}
+    tj = {}
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):   # dram bytes per algorithmic byte from the committed ncu --set full captures
+        tj = json.load(open(tpath))
+    kernels = {}
+    for st, ms in stage_ms.items():
+        bpk = stage_bytes_per_kf(w, wb, st, n_eval_mean, args.opt_mode)
+        if bpk <= 0 or ms <= 0:
+            continue
+        alg = bpk * kf_step
+        ach = alg / (ms * 1e-3) / 1e9
+        ratio = tj.get(kernel_names.get(st, st), {}).get('dram_per_algorithmic')
+        kernels[st] = {'kernel': kernel_names.get(st, st), 'ms': ms, 'algorithmic_bytes': alg, 'achieved': ach,
+                       'frac': ach / peak, 'share_of_step': ms / ms_step,
+                       'traffic': (alg * ratio) if ratio else None}
+    dom = max(kernels, key=lambda k: kernels[k]['ms']) if kernels else None
     roofline = None
-    if opt_ms:
-        launch_ms = opt_ms / n_launch
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):   # dram bytes per algorithmic byte from the committed ncu --set full capture
-            tj = json.load(open(tpath)).get('diag_nll_kernel')
-            if tj:
-                traffic = alg_bytes * tj['dram_bytes'] / tj['algorithmic_bytes']
-        roofline = {'bound': 'hbm', 'kernel': 'diag_nll_kernel', 'achieved': achieved, 'peak': peak,
-                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_launch': alg_bytes, 'launches': n_launch, 'launch_ms': launch_ms,
-                    'share_of_step': opt_ms / ms_step}
-    b_alg = w * (3 * M + 9)
+    if dom:
+        kd = kernels[dom]
+        roofline = {'bound': 'hbm', 'kernel': kd['kernel'], 'stage': dom, 'achieved': kd['achieved'], 'peak': peak,
+                    'unit': 'GB/s', 'frac': kd['frac'], 'traffic': kd['traffic'], 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': kd['algorithmic_bytes'], 'launch_ms': kd['ms'],
+                    'share_of_step': kd['share_of_step'],
+                    'how': 'dominant stage of the step = largest CUDA-event time on the launching stream inside the '
+                           'timed region; achieved = algorithmic bytes of that stage / that time'}
+    D3 = 0 if kind == 'singlecam' else 3
+    b_alg = wb * (3 * M * V + 9 * V + 2 * D3)
     pipeline_frac = (kf_step * b_alg / (ms_step * 1e-3) / 1e9) / peak
 
-    cpu = None
+    cpu = shared = None
     if not args.no_cpu and world == 1:   # the CPU baseline is a rank-0, N = 1 leg (torchrun pins OMP to one thread)
-        cpu = cpu_leg(M, K, min(args.cpu_frames, T), 1, 0)
-        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        Tc = min(args.cpu_frames or (100_000 if kind == 'singlecam' else 20_000), T)
+        sample = synth_host(w, Tc, seed=0)
+        c = cpu_leg(w, Tc, 1, 0, raw=sample)
+        cpu = {k: c[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        # Adam evaluation counts on the SAME sequences: GPU (this arm's precision), fp32 oracle, fp64 oracle
+        g = step(torch.as_tensor(sample).to(dev, dtype)[None], None)
+        torch.cuda.synchronize()
+        kk = min(K, 4)
+        r64 = oracle_run(w, sample[:, :, :, :kk], np.float64)
+        shared = {'frames': Tc, 'keypoints_compared': kk,
+                  'n_eval_gpu': [int(x) for x in g.iters[0].cpu().numpy()[:kk]],
+                  'n_eval_oracle_f64': [int(x) for x in r64['info']['iters']],
+                  'n_eval_oracle_f32': c['iters'][:kk],
+                  's_gpu': [float(x) for x in g.s_finals[0].cpu().numpy()[:kk]],
+                  's_oracle_f64': [float(x) for x in r64['s_finals']]}
 
+    cfg = config_of(args, w)
     line = {
-        'metric': 'keypoint-frames/sec smoothed incl. s-optimisation', 'value': value, 'unit': 'keypoint-frames/s',
+        'metric': METRIC, 'value': value, 'unit': 'keypoint-frames/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {S} sessions/GPU x {M} seeds x {K} keypoints x {T} frames, '
-                               'singlecam, per-keypoint Adam s-optimisation (reference stop rule)',
-                   'sessions_per_gpu': S, 'seeds': M, 'keypoints': K, 'frames': T,
-                   'l2': 'inputs larger than L2 (resident raw tensor %.1f GB per GPU)' % (raw.numel() * w / 1e9),
-                   'n_eval_mean': n_eval_mean, 'n_eval_max': n_eval_max},
-        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        'config': cfg,
+        'e2e': e2e, 'e2e_public': e2e_public, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        'kernels': kernels,
         'pipeline_one_touch': {'bytes_per_kf': b_alg, 'frac_of_hbm_peak': pipeline_frac,
                                'achieved_gbs': kf_step * b_alg / (ms_step * 1e-3) / 1e9},
-        'stage_ms': stage_ms, 'cpu_baseline': cpu,
+        'n_eval': {'mean': n_eval_mean, 'max': n_eval_max, 'optimiser': args.opt_mode if kind == 'singlecam' else 'runs'},
+        'stage_ms': stage_ms, 'cpu_baseline': cpu, 'shared_sequence': shared,
     }
     print(json.dumps(line))
     if world > 1:
