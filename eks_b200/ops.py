@@ -205,7 +205,7 @@ def filter_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.T
 
 
 def diag_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Tensor, ymean, out: torch.Tensor,
-                out_seq_stride: int, out_off, latent_out: bool = False):
+                out_seq_stride: int, out_off, latent_out: bool = False, exact_scan: bool = False):
     """Decoupled (singlecam) final pass: filter + RTS + reprojection straight into the output planes.
 
     out_off: element offsets (within a sequence's block) of [x plane, y plane, x post-var plane,
@@ -217,9 +217,10 @@ def diag_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Ten
     yo, vo, oo = i64_host(y.chan_off), i64_host(var.chan_off), i64_host(out_off)
     check(lib().eks_diag_smooth(dt_code(dtype), B, T, ptr(model.m0), ptr(model.S0), ptr(model.A), ptr(model.Q),
                                 ptr(model.C), ptr(y.base), y.seq_stride, ptr(yo), ptr(ymean), ptr(var.base),
-                                var.seq_stride, ptr(vo), ptr(s), ptr(out), out_seq_stride, ptr(oo), int(latent_out),
-                                ptr(ws), nbytes, stream_ptr()), 'eks_diag_smooth')
-    _count(2)
+                                var.seq_stride, ptr(vo), ptr(s), ptr(out), out_seq_stride, ptr(oo),
+                                int(latent_out) | (2 if exact_scan else 0), ptr(ws), nbytes, stream_ptr()),
+          'eks_diag_smooth')
+    _count(int(lib().eks_last_launch_count()))
     return ws
 
 

@@ -36,7 +36,7 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
                               lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300, min_R_var=1e-4,
                               out: torch.Tensor | None = None, force_generic: bool = False,
                               trace_cap: int = 0, timers: dict | None = None,
-                              opt_mode: str = 'lag') -> SinglecamResult:
+                              opt_mode: str = 'lag', exact_scan: bool = False) -> SinglecamResult:
     """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
 
     spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks.
@@ -118,7 +118,7 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
     s_dev = s_finals.reshape(B).to(dtype)
     if not force_generic and hasattr(lib(), 'eks_diag_smooth'):
         with _Stage('filter_smooth'):
-            ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T])
+            ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T], exact_scan=exact_scan)
     else:
         ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev, ymean=ymean)
         o = out.view(B, 9, T)

@@ -130,15 +130,22 @@ int eks_filter_smooth(int dtype, int B, int D, int O, int T, const void* m0, con
 
 /* Decoupled (single-camera) final pass: EKS_STRUCT_DIAG form of eks_filter_smooth fused with the
  * reprojection epilogue of eks/singlecam_smoother.py:189-217 (x = C m + mean, posterior variance =
- * diag(C V C^T)).  Time-parallel (Moebius / affine block scans).  Writes, per sequence b, the planes
- * out[b*out_seq_stride + out_off[j] + t], j = 0..3: smoothed x, smoothed y, posterior var x, posterior var y.
- * latent_out = 1 writes the latent smoothed means / variances themselves (the ms, diag Vs of eks_filter_smooth). */
+ * diag(C V C^T)).  Writes, per sequence b, the planes out[b*out_seq_stride + out_off[j] + t], j = 0..3: smoothed x,
+ * smoothed y, posterior var x, posterior var y.
+ * flags: bit 0 (EKS_SMOOTH_LATENT) writes the latent smoothed means / variances themselves (the ms, diag Vs of
+ * eks_filter_smooth); bit 1 (EKS_SMOOTH_EXACT_SCAN) skips the fused pass.
+ * Default execution: ONE fused, time-segmented kernel (forward filter and RTS recursion of a segment in registers, halo
+ * frames on both sides absorb the unknown boundary states; the contraction of both recursions over the halos is
+ * bounded from the data and VERIFIED per segment), then the exact scan kernels (Moebius / affine block scans over the
+ * whole sequence, filtered moments through the workspace) redo only the sequences the fused kernel flagged. */
+#define EKS_SMOOTH_LATENT 1
+#define EKS_SMOOTH_EXACT_SCAN 2
 size_t eks_diag_smooth_workspace_bytes(int dtype, int B, int T);
 int eks_diag_smooth(int dtype, int B, int T, const void* m0, const void* S0, const void* A, const void* Q,
                     const void* C, const void* y_base, long long y_seq_stride, const long long* y_chan_off_host,
                     const void* ymean, const void* var_base, long long var_seq_stride,
                     const long long* var_chan_off_host, const void* s, void* out, long long out_seq_stride,
-                    const long long* out_off_host, int latent_out, void* workspace, size_t workspace_bytes,
+                    const long long* out_off_host, int flags, void* workspace, size_t workspace_bytes,
                     void* stream);
 
 /* Reprojection epilogue for generic models: replaces the loops of eks/multicam_smoother.py:450-511 and

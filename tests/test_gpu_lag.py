@@ -114,3 +114,52 @@ def test_diagonal_dynamics_other_than_identity_stream():
         np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-7)
     finally:
         eks_b200.set_precision('float32')
+
+
+# ----------------------------------------------------------------------------------------------- fused final pass
+def _out(res):
+    return res.out[0].permute(2, 0, 1).double().cpu().numpy()
+
+
+@pytest.mark.parametrize('dtype,rtol', [(torch.float64, 1e-11), (torch.float32, 2e-5)])
+def test_fused_smoother_equals_exact_scan(dtype, rtol):
+    """the fused time-segmented final pass (halo frames absorb the boundary states, verified) against the exact
+    Moebius / affine scan kernels over the whole sequence, at the same s"""
+    raw = synth_singlecam(M=6, K=3, T=50_001, seed=13)
+    s = [0.05, 0.2, 1.5]
+    from eks_b200.pipeline import singlecam_smooth_sessions
+    t = torch.as_tensor(raw).cuda().to(dtype)
+    fused = singlecam_smooth_sessions(t[None], dtype=dtype, smooth_param=s)
+    exact = singlecam_smooth_sessions(t[None], dtype=dtype, smooth_param=s, exact_scan=True)
+    torch.cuda.synchronize()
+    check_columns(_out(fused), _out(exact), rtol, f'fused vs exact {dtype}')
+
+
+def test_fused_smoother_slow_forgetting_falls_back():
+    """s / r tiny: the halos cannot absorb the boundary states, the verification flags every sequence and the exact
+    kernels redo them -- the result is still the oracle's"""
+    from oracle import oracle
+    raw = _smooth_walk(M=4, K=2, T=30_000, seed=3, step=0.002, noise=0.8)
+    s = [1e-5, 3e-5]
+    ref = oracle.singlecam(raw, dtype=np.float64, smooth_param=s)
+    from eks_b200.pipeline import singlecam_smooth_sessions
+    res = singlecam_smooth_sessions(torch.as_tensor(raw).cuda()[None], dtype=torch.float64, smooth_param=s)
+    torch.cuda.synchronize()
+    check_columns(_out(res), ref['out'], 1e-5, 'slow forgetting')
+
+
+def test_fused_smoother_nan_observation_propagates_like_the_oracle():
+    """a frame where every seed is NaN makes the ensemble median NaN: the reference's filter turns everything after it
+    (and, through the RTS pass, everything before it) into NaN; the fused pass must not confine that to one segment"""
+    from oracle import oracle
+    raw = synth_singlecam(M=3, K=2, T=20_000, seed=5)
+    raw[:, 0, 7777, 1, 0:2] = np.nan     # both coordinates (the reference's dense 2-D filter couples them through NaN)
+    ref = oracle.singlecam(raw, dtype=np.float64, smooth_param=[0.1, 0.1])
+    from eks_b200.pipeline import singlecam_smooth_sessions
+    res = singlecam_smooth_sessions(torch.as_tensor(raw).cuda()[None], dtype=torch.float64, smooth_param=[0.1, 0.1])
+    torch.cuda.synchronize()
+    out = _out(res)
+    for c in (0, 1, 7, 8):
+        np.testing.assert_array_equal(np.isnan(out[..., c]), np.isnan(ref['out'][..., c]))
+    ok = ~np.isnan(ref['out'])
+    np.testing.assert_allclose(out[ok], ref['out'][ok], rtol=1e-5, atol=1e-7)
