@@ -32,7 +32,8 @@
 
 namespace eks {
 
-constexpr int LAG_T0 = 256;     // frames [0, T0) are filtered sequentially in every evaluation; statistics start after
+constexpr int LAG_T0 = 256;     // frames [0, T0) are filtered sequentially in an evaluation; statistics start after
+constexpr int LAG_NT0 = 3;      // statistics are kept for T0 = 256, 128, 64 (lag_reduce_kernel); the evaluation picks
 constexpr int LAG_CH = 4096;    // increments per shared-memory tile of lag_stats_kernel
 constexpr int LAG_RM = 16;      // lags per thread (register tile)
 constexpr int LAG_RP = 16;      // frames per thread and step (register tile)
@@ -44,7 +45,7 @@ struct LagStatArgs {
     PlaneView y;
     int B, t_begin, n, nchunk, nx;   // nx = gridDim.x
     double* partial;                 // [2B][nx][W]
-    double* R;                       // [2B][W]
+    double* R;                       // [LAG_NT0][2B][W]
 };
 
 template <class P> struct LagVec;
@@ -62,7 +63,7 @@ __device__ __forceinline__ int lag_phys(int x) { return x + (x >> 4) * (16 / (in
 // from 12 16-byte shared loads.  float32 mode: products and the <= 128-term partial sums per tile in float32, promoted
 // to float64 per tile (error of a partial ~1e-6 relative, of the 10^6-frame sum ~1e-8; the data are float32 anyway).
 template <class P, int W>
-__global__ void __launch_bounds__(LAG_NT) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
+__global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 2 : 1) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
     constexpr int PADE = 16 / (int)sizeof(P);
     constexpr int NLOG = LAG_CH + W;
     constexpr int NPHYS = NLOG + (NLOG / 16) * PADE + PADE;
@@ -96,8 +97,9 @@ __global__ void __launch_bounds__(LAG_NT) lag_stats_kernel(const __grid_constant
             if (g >= NG) break;
             const int m0 = g * LAG_RM;
             P acc[LAG_RM];
+            float2 acc2[LAG_RM];
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) acc[j] = P(0);
+            for (int j = 0; j < LAG_RM; ++j) { acc[j] = P(0); acc2[j] = make_float2(0.f, 0.f); }
             for (int step = 0; step < LAG_CH / (32 * LAG_RP); ++step) {
                 const int p = (step * 32 + lane) * LAG_RP;
                 if (step * 32 * LAG_RP >= nvalid) break;      // warp-uniform: nothing left in this tile
@@ -120,13 +122,35 @@ __global__ void __launch_bounds__(LAG_NT) lag_stats_kernel(const __grid_constant
                         bv[16 + i * VW + k] = e1[k];
                     }
                 }
+                if constexpr (sizeof(P) == 4) {
+                    // packed FFMA2 (sm_100): the even and the odd frames of the 16-frame tile are the two lanes of one
+                    // instruction, acc2[j] = (sum over even i, sum over odd i) of a_i b_{i+j}.  Odd lags need the b pairs
+                    // at odd offsets: a second, shifted copy of the window (register moves, 30 per 128 FFMA2).
+                    float2 a2[LAG_RP / 2], be[(LAG_RP + LAG_RM) / 2], bo[(LAG_RP + LAG_RM) / 2 - 1];
 #pragma unroll
-                for (int i = 0; i < LAG_RP; ++i)
+                    for (int k = 0; k < LAG_RP / 2; ++k) a2[k] = make_float2((float)av[2 * k], (float)av[2 * k + 1]);
 #pragma unroll
-                    for (int j = 0; j < LAG_RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
+                    for (int k = 0; k < (LAG_RP + LAG_RM) / 2; ++k) be[k] = make_float2((float)bv[2 * k], (float)bv[2 * k + 1]);
+#pragma unroll
+                    for (int k = 0; k < (LAG_RP + LAG_RM) / 2 - 1; ++k)
+                        bo[k] = make_float2((float)bv[2 * k + 1], (float)bv[2 * k + 2]);
+#pragma unroll
+                    for (int j = 0; j < LAG_RM; ++j)
+#pragma unroll
+                        for (int k = 0; k < LAG_RP / 2; ++k)
+                            acc2[j] = __ffma2_rn(a2[k], (j & 1) ? bo[k + (j >> 1)] : be[k + (j >> 1)], acc2[j]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < LAG_RP; ++i)
+#pragma unroll
+                        for (int j = 0; j < LAG_RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) accd[q][j] += (double)acc[j];
+            for (int j = 0; j < LAG_RM; ++j) {
+                if constexpr (sizeof(P) == 4) accd[q][j] += (double)acc2[j].x + (double)acc2[j].y;
+                else accd[q][j] += (double)acc[j];
+            }
         }
     }
 #pragma unroll
@@ -141,16 +165,30 @@ __global__ void __launch_bounds__(LAG_NT) lag_stats_kernel(const __grid_constant
     }
 }
 
-// fixed-order sum of the per-CTA partials: one thread per (sequence, channel, lag)
+// fixed-order sum of the per-CTA partials: one thread per (sequence, channel, lag).  R[0] = statistics of the increments
+// after frame T0 = 256 (what lag_stats_kernel summed); R[1], R[2] = the same from frame 128 / 64 on (the few extra
+// products are added here), so that an evaluation whose variance transient ends early need not walk to frame 256.
 template <class P, int W>
 __global__ void lag_reduce_kernel(const __grid_constant__ LagStatArgs<P> a) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)a.B * 2 * W) return;
+    const long long per = (long long)a.B * 2 * W;
+    if (idx >= per) return;
     const long long bc = idx / W;
     const int m = (int)(idx - bc * W);
     double s = 0;
     for (int x = 0; x < a.nx; ++x) s += a.partial[(bc * a.nx + x) * W + m];
     a.R[idx] = s;
+    const int b = (int)(bc >> 1), c = (int)(bc & 1);
+    const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
+    int hi = LAG_T0;
+#pragma unroll
+    for (int lvl = 1; lvl < LAG_NT0; ++lvl) {
+        const int lo = LAG_T0 >> lvl;              // increments lo + 1 .. hi join the statistics
+        for (int i = hi; i > lo; --i)
+            s += ((double)yc[i] - (double)yc[i - 1]) * ((double)yc[i + m] - (double)yc[i + m - 1]);
+        a.R[lvl * per + idx] = s;
+        hi = lo;
+    }
 }
 
 // ---- one (sequence, channel) evaluation, float64: exact sequential filter over the first T0 frames
@@ -159,6 +197,7 @@ struct LagPair {
     double sl, sdl, se, sde, sg;   // transient sums: logS, dlogS, e2 iS, e2 diS, e dm iS
     double E2b, Gb;                // steady-state frames [t_c, T0): sum e^2, sum e dm
     int t_c;
+    int T0, lvl;                   // first frame of the statistics used by this evaluation and its index in R
 };
 
 // yh: this pair's first T0 + 1 observations (centred, float64).  Returns false if the closed form does not apply.
@@ -173,7 +212,7 @@ __device__ bool lag_prepare(const DiagOptArgs<P>& a, int b, int c, double s, con
     const double tol = 8.0 * 2.220446049250313e-16, BOOST = 1e-9;
     double prevP = INFINITY, prevd = INFINITY;
     int stall = 0, t = 0;
-    double iS, diS, K, dK, alpha, S, dS;
+    double iS, diS, K, dK, alpha, S, dS, prodS = 1.0;
     while (true) {
         S = Pv + r;
         iS = 1.0 / S;
@@ -196,7 +235,8 @@ __device__ bool lag_prepare(const DiagOptArgs<P>& a, int b, int c, double s, con
         if (conv) break;
         if (t >= LAG_T0) return false;                          // slow convergence: stream this evaluation
         const double e = yh[t] - m;
-        sl += log(S);
+        prodS *= S;                                             // sum log S_t through products of 8 (S stays in range)
+        if ((t & 7) == 7) { sl += log(prodS); prodS = 1.0; }
         sdl += dS * iS;
         se += e * e * iS;
         sde += e * e * diS;
@@ -209,16 +249,21 @@ __device__ bool lag_prepare(const DiagOptArgs<P>& a, int b, int c, double s, con
     if (!(alpha > 0.0) || !(alpha < 1.0) || !isfinite(alpha)) return false;
     // truncation of the lag series: |sum_{m >= W} 2 alpha^m R_m| <= 2 alpha^W / (1 - alpha) R_0
     if (2.0 * exp((double)W * log(alpha)) > tolF * (1.0 - alpha)) return false;
+    sl += log(prodS);
     o.t_c = t;
+    int lvl = LAG_NT0 - 1;                                      // smallest T0 of the table that is >= t_c
+    while (lvl > 0 && (LAG_T0 >> lvl) < t) --lvl;
+    const int T0 = LAG_T0 >> lvl;
+    o.T0 = T0; o.lvl = lvl;
     double E2b = 0, Gb = 0;
-    for (; t < LAG_T0; ++t) {           // constant-gain frames before the statistics start
+    for (; t < T0; ++t) {               // constant-gain frames before the statistics start
         const double e = yh[t] - m;
         E2b = fma(e, e, E2b);
         Gb = fma(e, dm, Gb);
         dm = fma(alpha, dm, dK * e);
         m = fma(K, e, m);
     }
-    o.e0 = yh[LAG_T0] - m;
+    o.e0 = yh[T0] - m;
     o.de0 = -dm;
     o.alpha = alpha; o.dalpha = -dK; o.iS = iS; o.diS = diS; o.logS = log(S); o.dlogS = dS * iS;
     o.sl = sl; o.sdl = sdl; o.se = se; o.sde = sde; o.sg = sg; o.E2b = E2b; o.Gb = Gb;
@@ -228,7 +273,7 @@ __device__ bool lag_prepare(const DiagOptArgs<P>& a, int b, int c, double s, con
 template <class P>
 struct LagOptArgs {
     DiagOptArgs<P> d;
-    const double* R;   // [2B][W]
+    const double* R;   // [LAG_NT0][2B][W]
     int W;
     int fast;          // 0: the closed form is never applicable (short sequences): stream every evaluation
     double tolF;
@@ -328,7 +373,8 @@ __global__ void __launch_bounds__(OPT_NT, 2) diag_lag_opt_kernel(const __grid_co
                     const int bq = __shfl_sync(0xffffffffu, b, q), cq = __shfl_sync(0xffffffffu, c, q);
                     const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)bq * a.y.seq_stride + a.t_begin +
                                   a.y.chan_off[cq];
-                    const double* Rq = la.R + ((long long)bq * 2 + cq) * W;
+                    const int T0q = __shfl_sync(0xffffffffu, lp.T0, q), lvq = __shfl_sync(0xffffffffu, lp.lvl, q);
+                    const double* Rq = la.R + ((long long)lvq * a.B * 2 + (long long)bq * 2 + cq) * W;
                     const double lal = log(alq);
                     double pw = exp((double)lane * lal);
                     const double pw32 = exp(32.0 * lal), ial = 1.0 / alq;
@@ -343,7 +389,7 @@ __global__ void __launch_bounds__(OPT_NT, 2) diag_lag_opt_kernel(const __grid_co
                         tl = fma(pw, lm, tl);
                         dtl = fma(pm1, lm, dtl);
                         if (m >= 1) {
-                            const double hm = (double)yc[LAG_T0 + m] - (double)yc[LAG_T0 + m - 1];
+                            const double hm = (double)yc[T0q + m] - (double)yc[T0q + m - 1];
                             h = fma(pw, hm, h);
                             dh = fma(pm1, hm, dh);
                         }
@@ -434,7 +480,7 @@ size_t diag_lag_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     const int nchunk = (T + LAG_CH - 1) / LAG_CH + 1;
     const int nx = (nchunk + LAG_CPB - 1) / LAG_CPB;
     size_t bytes = diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
-    bytes += (size_t)B * 2 * W * sizeof(double) + 256;
+    bytes += (size_t)LAG_NT0 * B * 2 * W * sizeof(double) + 256;
     bytes += (size_t)B * 2 * nx * W * sizeof(double) + 256;
     return bytes;
 }
@@ -458,7 +504,7 @@ static int diag_lag_run(DiagOptArgs<P>& a, void* workspace, size_t workspace_byt
     la.W = W;
     la.fast = (a.n >= LAG_T0 + 4 * W) ? 1 : 0;
     la.tolF = dtype == EKS_F32 ? 1e-7 : 1e-13;
-    double* R = (double*)w; w += (size_t)a.B * 2 * W * sizeof(double) + 256;
+    double* R = (double*)w; w += (size_t)LAG_NT0 * a.B * 2 * W * sizeof(double) + 256;
     la.R = R;
     int launches = 1;
     if (la.fast) {
