@@ -36,7 +36,7 @@ _SIGS = {
     'eks_center_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'eks_initial_guess': (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
-    'eks_const_R_median_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'eks_const_R_median_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'eks_const_R_median': (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
     'eks_nll_grad': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

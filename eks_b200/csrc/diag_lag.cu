@@ -63,7 +63,7 @@ __device__ __forceinline__ int lag_phys(int x) { return x + (x >> 4) * (16 / (in
 // from 12 16-byte shared loads.  float32 mode: products and the <= 128-term partial sums per tile in float32, promoted
 // to float64 per tile (error of a partial ~1e-6 relative, of the 10^6-frame sum ~1e-8; the data are float32 anyway).
 template <class P, int W>
-__global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 2 : 1) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
+__global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 3 : 1) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
     constexpr int PADE = 16 / (int)sizeof(P);
     constexpr int NLOG = LAG_CH + W;
     constexpr int NPHYS = NLOG + (NLOG / 16) * PADE + PADE;
@@ -97,9 +97,8 @@ __global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 2 : 1) lag_stats_kern
             if (g >= NG) break;
             const int m0 = g * LAG_RM;
             P acc[LAG_RM];
-            float2 acc2[LAG_RM];
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) { acc[j] = P(0); acc2[j] = make_float2(0.f, 0.f); }
+            for (int j = 0; j < LAG_RM; ++j) acc[j] = P(0);
             for (int step = 0; step < LAG_CH / (32 * LAG_RP); ++step) {
                 const int p = (step * 32 + lane) * LAG_RP;
                 if (step * 32 * LAG_RP >= nvalid) break;      // warp-uniform: nothing left in this tile
@@ -122,35 +121,16 @@ __global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 2 : 1) lag_stats_kern
                         bv[16 + i * VW + k] = e1[k];
                     }
                 }
-                if constexpr (sizeof(P) == 4) {
-                    // packed FFMA2 (sm_100): the even and the odd frames of the 16-frame tile are the two lanes of one
-                    // instruction, acc2[j] = (sum over even i, sum over odd i) of a_i b_{i+j}.  Odd lags need the b pairs
-                    // at odd offsets: a second, shifted copy of the window (register moves, 30 per 128 FFMA2).
-                    float2 a2[LAG_RP / 2], be[(LAG_RP + LAG_RM) / 2], bo[(LAG_RP + LAG_RM) / 2 - 1];
+                // (a packed-FFMA2 version of this tile -- even / odd frames as the two lanes, shifted copy of the window for
+                // the odd lags -- was measured SLOWER: 688 vs 542 us per 80 channel-planes; 12 16-byte shared loads per
+                // 128 FFMA2 make it shared-memory bound, and 114 registers cost a resident CTA)
 #pragma unroll
-                    for (int k = 0; k < LAG_RP / 2; ++k) a2[k] = make_float2((float)av[2 * k], (float)av[2 * k + 1]);
+                for (int i = 0; i < LAG_RP; ++i)
 #pragma unroll
-                    for (int k = 0; k < (LAG_RP + LAG_RM) / 2; ++k) be[k] = make_float2((float)bv[2 * k], (float)bv[2 * k + 1]);
-#pragma unroll
-                    for (int k = 0; k < (LAG_RP + LAG_RM) / 2 - 1; ++k)
-                        bo[k] = make_float2((float)bv[2 * k + 1], (float)bv[2 * k + 2]);
-#pragma unroll
-                    for (int j = 0; j < LAG_RM; ++j)
-#pragma unroll
-                        for (int k = 0; k < LAG_RP / 2; ++k)
-                            acc2[j] = __ffma2_rn(a2[k], (j & 1) ? bo[k + (j >> 1)] : be[k + (j >> 1)], acc2[j]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < LAG_RP; ++i)
-#pragma unroll
-                        for (int j = 0; j < LAG_RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
-                }
+                    for (int j = 0; j < LAG_RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
             }
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) {
-                if constexpr (sizeof(P) == 4) accd[q][j] += (double)acc2[j].x + (double)acc2[j].y;
-                else accd[q][j] += (double)acc[j];
-            }
+            for (int j = 0; j < LAG_RM; ++j) accd[q][j] += (double)acc[j];
         }
     }
 #pragma unroll

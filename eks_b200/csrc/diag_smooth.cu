@@ -359,6 +359,15 @@ __global__ void __launch_bounds__(DIAG_NT, EKS_SMOOTH_MINBLOCKS) diag_rts_kernel
 // sequences are redone by the exact scan kernels above (diag_filter_kernel + diag_rts_kernel, which
 // return immediately for the others).  HBM traffic: 16 bytes per channel-frame x (1 + 2 HALO / SEG).
 // =====================================================================================================
+// reciprocal for the fused pass: float32 uses the hardware approximation (MUFU.RCP, <= 1 ulp) -- the IEEE division
+// sequence is ~8 instructions, three per frame -- float64 the exact division
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+
 template <class P>
 struct FusedShared {
     Mob<P> magg[DIAG_NW];
@@ -421,7 +430,7 @@ diag_smooth_fused_kernel(const __grid_constant__ DiagSmoothArgs<P> a, int seg, i
     Mob<P> M{P(1), P(0), P(0), P(1)};
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-        const P ir = P(1) / r[i];
+        const P ir = rcp_fast(r[i]);
         const Mob<P> Mi{fma(qc2, ir, a2), q, c2 * ir, P(1)};
         M = mob_mul(Mi, M);
         if (i & 1) mob_norm(M);
@@ -455,7 +464,7 @@ diag_smooth_fused_kernel(const __grid_constant__ DiagSmoothArgs<P> a, int seg, i
 #pragma unroll
     for (int i = 0; i < L; ++i) {
         const P S = fma(c2, Pv, r[i]);
-        const P iSb = P(1) / (S + P(1e-9));
+        const P iSb = rcp_fast(S + P(1e-9));
         const P K = Pv * cc * iSb;
         const P Pfi = Pv * iSb * (r[i] + P(1e-9) * (P(1) + cc * K));
         const P alpha = av * iSb * (r[i] + P(1e-9)), beta = av * K;
@@ -494,7 +503,7 @@ diag_smooth_fused_kernel(const __grid_constant__ DiagSmoothArgs<P> a, int seg, i
     for (int ii = 0; ii < L; ++ii) {
         const int i = L - 1 - ii;
         const P Sp = fma(a2, Pf[i], q);
-        const P iSpb = P(1) / (Sp + P(1e-9));
+        const P iSpb = rcp_fast(Sp + P(1e-9));
         P g = av * Pf[i] * iSpb;
         P om = y[i] * iSpb * (q + P(1e-9));
         P oP = Pf[i] * iSpb * (q + P(1e-9) * (P(1) + av * g));

@@ -11,6 +11,7 @@
 // One CTA = one (session, camera, tile of TT frames) for all K keypoints.  Loads walk the AoS
 // input with keypoint fastest (fully coalesced), results are transposed through shared memory and
 // written with frame fastest (fully coalesced).  HBM-bound: 12*M bytes in, 20 bytes out per cell.
+#include <cstdlib>
 #include "common.cuh"
 #include "sort_networks.cuh"
 #include "../../include/eks_b200.h"
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) ensemble_kernel(const Tin* __restrict__ r
         coord_stats<P, MAXM>(xs, M, avg_median != 0, ax, vx);
         coord_stats<P, MAXM>(ys, M, avg_median != 0, ay, vy);
         if (M == 1) {
-            vx = vy = P(1) / fmax(mean_conf, P(1e-5));
+            vx = vy = (mean_conf != mean_conf) ? mean_conf : P(1) / fmax(mean_conf, P(1e-5));   // NaN propagates (jnp.maximum)
         } else if (var_mode == 1) {
             vx = vx / mean_conf;
             vy = vy / mean_conf;
@@ -238,7 +239,17 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
     constexpr int EPG = 16 / (int)sizeof(Tin);
     const bool vec = ((reinterpret_cast<uintptr_t>(base + off0) & 15) == 0) && ((m_stride * (int)sizeof(Tin)) % 16 == 0);
     const int ngran = vec ? nel / EPG : 0;
-    {   // stage the M contiguous seed chunks: coalesced 16-byte cp.async, pointers advanced by constant strides
+    if (EXACT && vec && ngran * EPG == nel) {
+        // whole granules only (every full tile): the seed loop is unrolled and each thread issues its granule of every
+        // seed from ONE address computation (the per-seed loop with its bounds checks was 26 % of the kernel's
+        // instructions, ncu r2a)
+        const Tin* src = base + off0 + (long long)threadIdx.x * EPG;
+        unsigned char* dst = smem_raw + threadIdx.x * 16;
+        for (int g = threadIdx.x; g < ngran; g += blockDim.x, src += blockDim.x * EPG, dst += blockDim.x * 16) {
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) ens_cp_async_16(dst + (size_t)m * chunk_pad, src + (long long)m * m_stride);
+        }
+    } else {   // stage the M contiguous seed chunks: coalesced 16-byte cp.async, pointers advanced by constant strides
         const Tin* src = base + off0;
         unsigned char* dst = smem_raw;
         for (int m = 0; m < M; ++m, src += m_stride, dst += chunk_pad) {
@@ -256,8 +267,7 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         const int tl = (K == 1) ? e : (int)__umulhi((unsigned)e, invK);  // e / K without a divide
         const int k = e - tl * K;
         P xs[MAXM], ys[MAXM];
-        P conf = P(0);
-        bool any_nan = false;
+        P conf = P(0), sumx = P(0), sumy = P(0);
         const unsigned char* sp = smem_raw + (size_t)e * 3 * sizeof(Tin);
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
@@ -266,7 +276,8 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
                 xs[m] = P(q[0]);                     // cast to the compute precision first (core.py:90-92)
                 ys[m] = P(q[1]);
                 conf += P(q[2]);                     // likelihood sum is NOT NaN-aware (core.py:67-68)
-                any_nan = any_nan || isnan(xs[m]) || isnan(ys[m]);
+                sumx += xs[m];
+                sumy += ys[m];
             } else {
                 xs[m] = P(0);
                 ys[m] = P(0);
@@ -274,7 +285,9 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         }
         const P mean_conf = conf / P(M);
         P ax, vx, ay, vy;
-        if (EXACT && !any_nan) {
+        // a NaN among the seeds makes the plain sum NaN: one test per coordinate instead of one per value.  (inf - inf
+        // also lands on the NaN-aware path, which treats +-inf exactly like the plain path does.)
+        if (EXACT && !(sumx != sumx) && !(sumy != sumy)) {
             coord_stats_clean<P, MAXM>(xs, avg_median != 0, ax, vx);
             coord_stats_clean<P, MAXM>(ys, avg_median != 0, ay, vy);
         } else {
@@ -282,14 +295,18 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
             coord_stats<P, MAXM, EXACT>(ys, M, avg_median != 0, ay, vy);
         }
         if (M == 1) {
-            vx = vy = P(1) / fmax(mean_conf, P(1e-5));
+            // jnp.maximum propagates NaN (a NaN likelihood -> NaN variance -> nan_replacement); fmax would drop it
+            vx = vy = (mean_conf != mean_conf) ? mean_conf : P(1) / fmax(mean_conf, P(1e-5));
         } else if (var_mode == 1) {
             vx = vx / mean_conf;
             vy = vy / mean_conf;
         }
-        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max
-        if (isnan(vx)) vx = nan_repl; else if (isinf(vx)) vx = vx > 0 ? real_max<P>() : -real_max<P>();
-        if (isnan(vy)) vy = nan_repl; else if (isinf(vy)) vy = vy > 0 ? real_max<P>() : -real_max<P>();
+        // jnp.nan_to_num(nan=nan_replacement): nan -> repl, +-inf -> +-max  (branch free: clamp, then select)
+        {
+            const P cx = fmin(fmax(vx, -real_max<P>()), real_max<P>()), cy = fmin(fmax(vy, -real_max<P>()), real_max<P>());
+            vx = (vx != vx) ? nan_repl : cx;
+            vy = (vy != vy) ? nan_repl : cy;
+        }
         P* tp = tile + k * ld + tl;
         const int fs = K * ld;
         tp[0] = ax;
@@ -397,7 +414,9 @@ int launch_ensemble(const Tin* raw, long long raw_sess_stride, int S, int M, int
     const int ntiles = (T + TT - 1) / TT;
     // (a CTA sized to the tile's cell count -- 320 threads for 16 frames x 20 keypoints -- was measured slower:
     // 6.1 ms vs 5.3 ms for the stage on the c5 bench; other CTAs on the SM already fill the uneven second round)
-    dim3 grid(ntiles, V, S), block(256);
+    // threads per CTA: EKS_ENS_THREADS overrides (experiments); 256 by default
+    static const int nt_env = [] { const char* e = getenv("EKS_ENS_THREADS"); return e ? atoi(e) : 256; }();
+    dim3 grid(ntiles, V, S), block((nt_env >= 64 && nt_env <= 256 && nt_env % 32 == 0) ? nt_env : 256);
     size_t smem = (size_t)5 * K * (TT + 1) * sizeof(P);
     if (staged) smem += (size_t)M * (((size_t)TT * K * 3 * sizeof(Tin) + 15) / 16 * 16);
     EKS_REQUIRE(smem <= 200 * 1024, "ensemble: K=%d too large for the shared-memory tile", K);

@@ -109,14 +109,23 @@ struct SelState {           // per problem (sequence, channel)
 constexpr int NBINS = 2048;
 constexpr int SEL_CHUNK = 16384;
 
+// extra workspace of the one-pass median (states, fail flags, candidate keys): see run_const_R
+static size_t med_extra_bytes(int nprob, int n_total, size_t key_bytes, size_t state_bytes) {
+    const size_t cap = (size_t)n_total / 8 + 4096;
+    return 256 + (((size_t)nprob * state_bytes + 255) & ~(size_t)255) + (((size_t)nprob * sizeof(int) + 255) & ~(size_t)255) +
+           (size_t)nprob * cap * key_bytes + 256;
+}
+
 template <class P>
 __global__ void __launch_bounds__(256) select_hist_kernel(PlaneView var, int O, Spans sp, int n_total, int level,
                                                           const SelState* __restrict__ state,
-                                                          int* __restrict__ hist /*[prob][2][NBINS]*/) {
+                                                          int* __restrict__ hist /*[prob][2][NBINS]*/,
+                                                          const int* __restrict__ only = nullptr) {
     using KT = KeyT<P>;
     using key_t = typename KT::type;
     __shared__ int sh[2][NBINS];
-    const int prob = blockIdx.y, b = prob / O, o = prob - b * O;
+    const int prob = blockIdx.x, b = prob / O, o = prob - b * O;   // problems on grid x: no 65535 limit
+    if (only && !only[prob]) return;
     for (int i = threadIdx.x; i < 2 * NBINS; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const P* base = reinterpret_cast<const P*>(var.base) + (long long)b * var.seq_stride + var.chan_off[o];
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(256) select_hist_kernel(PlaneView var, int O, 
     key_t pre0 = 0, pre1 = 0;
     if (level > 0) { pre0 = (key_t)state[prob].prefix[0]; pre1 = (key_t)state[prob].prefix[1]; }
     const bool same = (level == 0) || (pre0 == pre1);
-    const int i0 = blockIdx.x * SEL_CHUNK, i1 = min(n_total, i0 + SEL_CHUNK);
+    const int i0 = blockIdx.y * SEL_CHUNK, i1 = min(n_total, i0 + SEL_CHUNK);
     // (warp-aggregating the atomics with match.any was measured slower -- 3.3 ms vs 2.3 ms for this stage on the
     // c5 bench -- the bins hit by one warp are too many for the aggregation loop to pay off)
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
@@ -158,11 +167,12 @@ template <class P>
 __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* __restrict__ state,
                                                           int* __restrict__ hist, double floor_lo, double floor_hi,
                                                           double q /* percent; < 0: nanmedian */,
-                                                          P* __restrict__ out) {
+                                                          P* __restrict__ out, const int* __restrict__ only = nullptr) {
     using KT = KeyT<P>;
     using key_t = typename KT::type;
     __shared__ int sh[2][NBINS];
     const int prob = blockIdx.x;
+    if (only && !only[prob]) return;
     int* gh = hist + (long long)prob * 2 * NBINS;
     for (int i = threadIdx.x; i < 2 * NBINS; i += blockDim.x) {
         (&sh[0][0])[i] = gh[i];
@@ -226,6 +236,199 @@ __global__ void __launch_bounds__(256) select_scan_kernel(int level, SelState* _
     }
 }
 
+// ------------------------------------------------------------------ nanmedian in ONE pass over the data
+// The three radix passes above read every variance plane three times.  For long sequences the median is bracketed
+// first: med_sample_kernel sorts MED_NS jittered samples of a problem and takes the sample quantiles 0.5 -+ MED_DELTA
+// (5 sigma of the sample-quantile rank error) as a key bracket [lo, hi]; med_count_kernel then streams the plane ONCE,
+// counting the NaNs and the keys below the bracket and compacting the ~8 % of the keys inside it; med_final_kernel
+// runs the exact radix select on those candidates with the ranks shifted by the count below.  The result is the same
+// order statistic(s) as the three-pass select -- bit exact -- whenever the true median ranks fall inside the bracket
+// and the candidate buffers did not overflow; otherwise the problem is flagged and the three-pass select redoes it
+// (its CTAs return immediately for unflagged problems).
+constexpr int MED_NS = 4096;
+constexpr float MED_DELTA = 0.04f;
+constexpr int MED_CHUNK = 16384;          // frames per CTA of med_count_kernel
+constexpr int MED_SCAP = 4096;            // candidates a CTA can hold (25 % of its chunk)
+constexpr int MED_MIN_FRAMES = 1 << 17;   // below this the three-pass select is used directly
+
+template <class P>
+struct MedState {
+    typename KeyT<P>::type lo, hi;
+    int n_below, n_nan, n_cand, fail;
+};
+
+template <class P>
+__global__ void __launch_bounds__(512) med_sample_kernel(PlaneView var, int O, Spans sp, int n_total,
+                                                         MedState<P>* __restrict__ state) {
+    using KT = KeyT<P>;
+    using key_t = typename KT::type;
+    __shared__ key_t keys[MED_NS];
+    __shared__ int nvalid_sh;
+    const int prob = blockIdx.x, b = prob / O, o = prob - b * O;
+    const P* base = reinterpret_cast<const P*>(var.base) + (long long)b * var.seq_stride + var.chan_off[o];
+    if (threadIdx.x == 0) nvalid_sh = 0;
+    __syncthreads();
+    const int stride = n_total / MED_NS;          // >= 32 (MED_MIN_FRAMES)
+    int nv = 0;
+    for (int j = threadIdx.x; j < MED_NS; j += blockDim.x) {
+        const unsigned h = (unsigned)j * 2654435761u;
+        const int i = j * stride + (int)((h >> 8) % (unsigned)stride);      // jittered position inside cell j
+        const int t = (sp.n == 1) ? sp.start[0] + i : span_to_frame(sp, i);
+        const P x = base[t];
+        keys[j] = KT::key(x);                     // NaN -> all ones: sorted to the end
+        nv += isnan(x) ? 0 : 1;
+    }
+    nv = warp_sum(nv);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&nvalid_sh, nv);
+    __syncthreads();
+    for (int k = 2; k <= MED_NS; k <<= 1)          // bitonic sort, ascending
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = threadIdx.x; i < MED_NS; i += blockDim.x) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const key_t a = keys[i], c = keys[l];
+                    const bool up = ((i & k) == 0);
+                    if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        MedState<P> st;
+        const int n = nvalid_sh;
+        st.n_below = 0; st.n_nan = 0; st.n_cand = 0;
+        st.fail = (n < 256) ? 1 : 0;               // mostly NaN: no usable bracket
+        const int il = max(0, (int)floorf((float)n * (0.5f - MED_DELTA)) - 1);
+        const int ih = min(max(n - 1, 0), (int)ceilf((float)n * (0.5f + MED_DELTA)) + 1);
+        st.lo = keys[il];
+        st.hi = keys[ih];
+        state[prob] = st;
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) med_count_kernel(PlaneView var, int O, Spans sp, int n_total, int cap,
+                                                        MedState<P>* __restrict__ state,
+                                                        typename KeyT<P>::type* __restrict__ cand) {
+    using KT = KeyT<P>;
+    using key_t = typename KT::type;
+    __shared__ key_t buf[MED_SCAP];
+    __shared__ int sh_n, sh_below, sh_nan, sh_base, sh_fail;
+    const int prob = blockIdx.x, b = prob / O, o = prob - b * O;
+    const key_t lo = state[prob].lo, hi = state[prob].hi;
+    const P* base = reinterpret_cast<const P*>(var.base) + (long long)b * var.seq_stride + var.chan_off[o];
+    if (threadIdx.x == 0) { sh_n = 0; sh_below = 0; sh_nan = 0; sh_fail = state[prob].fail; }
+    __syncthreads();
+    if (sh_fail) return;      // (read once: other CTAs of this problem may set the flag concurrently)
+    const int i0 = blockIdx.y * MED_CHUNK, i1 = min(n_total, i0 + MED_CHUNK);
+    const int lane = threadIdx.x & 31;
+    int below = 0, nans = 0;
+    for (int ib = i0 + (threadIdx.x & ~31); ib < i1; ib += blockDim.x) {      // warp-uniform trip count
+        const int i = ib + lane;
+        bool in = false;
+        key_t k = 0;
+        if (i < i1) {
+            const int t = (sp.n == 1) ? sp.start[0] + i : span_to_frame(sp, i);
+            const P x = base[t];
+            if (isnan(x)) ++nans;
+            else {
+                k = KT::key(x);
+                if (k < lo) ++below;
+                else in = (k <= hi);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (m) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&sh_n, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+            if (in && pos < MED_SCAP) buf[pos] = k;
+        }
+    }
+    below = warp_sum(below);
+    nans = warp_sum(nans);
+    if (lane == 0) { if (below) atomicAdd(&sh_below, below); if (nans) atomicAdd(&sh_nan, nans); }
+    __syncthreads();
+    const int n = sh_n;
+    if (threadIdx.x == 0) {
+        if (sh_below) atomicAdd(&state[prob].n_below, sh_below);
+        if (sh_nan) atomicAdd(&state[prob].n_nan, sh_nan);
+        int gbase = 0;
+        if (n > MED_SCAP) { state[prob].fail = 1; gbase = cap; }          // a CTA's buffer overflowed
+        else if (n > 0) gbase = atomicAdd(&state[prob].n_cand, n);
+        sh_base = gbase;
+    }
+    __syncthreads();
+    const int gbase = sh_base;
+    if (gbase + n > cap) {                                                  // the problem's buffer overflowed
+        if (threadIdx.x == 0) state[prob].fail = 1;
+        return;
+    }
+    key_t* dst = cand + (long long)prob * cap + gbase;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = buf[i];
+}
+
+template <class P>
+__global__ void __launch_bounds__(1024) med_final_kernel(int n_total, int cap, MedState<P>* __restrict__ state,
+                                                         const typename KeyT<P>::type* __restrict__ cand,
+                                                         double floor_lo, double floor_hi, P* __restrict__ out,
+                                                         int* __restrict__ fail_out) {
+    using KT = KeyT<P>;
+    using key_t = typename KT::type;
+    __shared__ int hist[2][NBINS];
+    __shared__ key_t prefix[2];
+    __shared__ int rank[2];
+    __shared__ int ok;
+    const int prob = blockIdx.x;
+    const MedState<P> st = state[prob];
+    const int n_valid = n_total - st.n_nan;
+    if (threadIdx.x == 0) {
+        rank[0] = (n_valid - 1) / 2 - st.n_below;
+        rank[1] = n_valid / 2 - st.n_below;
+        prefix[0] = prefix[1] = 0;
+        ok = !st.fail && n_valid > 0 && rank[0] >= 0 && rank[1] < st.n_cand && st.n_cand <= cap;
+        fail_out[prob] = ok ? 0 : 1;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const key_t* kc = cand + (long long)prob * cap;
+    const int nc = st.n_cand;
+    for (int level = 0; level < KT::nlevels; ++level) {
+        const int shift = KT::shift(level), nb = KT::bits(level), hshift = shift + nb;
+        for (int i = threadIdx.x; i < 2 * NBINS; i += blockDim.x) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        const key_t pre0 = prefix[0], pre1 = prefix[1];
+        const bool same = (level == 0) || (pre0 == pre1);
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+            const key_t k = kc[i];
+            const int bin = (int)((k >> shift) & (key_t)((1 << nb) - 1));
+            const key_t top = (level == 0) ? 0 : (k >> hshift);
+            if (level == 0 || top == pre0) atomicAdd(&hist[0][bin], 1);
+            if (!same && top == pre1) atomicAdd(&hist[1][bin], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int r = threadIdx.x;
+            const int* h = hist[same ? 0 : r];
+            int cum = 0, bin = 0;
+            for (bin = 0; bin < (1 << nb); ++bin) {
+                if (cum + h[bin] > rank[r]) break;
+                cum += h[bin];
+            }
+            rank[r] -= cum;
+            prefix[r] = (prefix[r] << nb) | (key_t)bin;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const P a = KT::unkey(prefix[0]), c = KT::unkey(prefix[1]);
+        P med = (a + c) * P(0.5);
+        med = (P)fmax((double)med, floor_lo);      // build_R_from_vars clip (1e-12) then min_R_var, as select_scan_kernel
+        med = (P)fmax((double)med, floor_hi);
+        out[prob] = med;
+    }
+}
+
 template <class P>
 int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total, double min_var, P* out,
                 void* workspace, size_t workspace_bytes, cudaStream_t st, double q = -1.0) {
@@ -237,10 +440,32 @@ int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total
     int* hist = reinterpret_cast<int*>(state + nprob);
     cudaMemsetAsync(workspace, 0, need, st);
     const int nchunks = (n_total + SEL_CHUNK - 1) / SEL_CHUNK;
-    for (int level = 0; level < KeyT<P>::nlevels; ++level) {
-        select_hist_kernel<P><<<dim3(nchunks, nprob), 256, 0, st>>>(var, O, sp, n_total, level, state, hist);
-        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, 1e-12, min_var, q, out);
+    const int* only = nullptr;
+    int launches = 0;
+    if (q < 0 && n_total >= MED_MIN_FRAMES) {      // nanmedian of a long sequence: bracket + ONE pass, three-pass fallback
+        using key_t = typename KeyT<P>::type;
+        const int cap = n_total / 8 + MED_SCAP;
+        const size_t extra = med_extra_bytes(nprob, n_total, sizeof(key_t), sizeof(MedState<P>));
+        EKS_REQUIRE(workspace_bytes >= need + extra, "const_R_median: workspace too small (%zu < %zu)", workspace_bytes,
+                    need + extra);
+        unsigned char* w = (unsigned char*)workspace + ((need + 255) & ~(size_t)255);
+        MedState<P>* ms = (MedState<P>*)w; w += ((size_t)nprob * sizeof(MedState<P>) + 255) & ~(size_t)255;
+        int* fail = (int*)w; w += ((size_t)nprob * sizeof(int) + 255) & ~(size_t)255;
+        key_t* cand = (key_t*)w;
+        med_sample_kernel<P><<<nprob, 512, 0, st>>>(var, O, sp, n_total, ms);
+        med_count_kernel<P><<<dim3(nprob, (n_total + MED_CHUNK - 1) / MED_CHUNK), 256, 0, st>>>(var, O, sp, n_total, cap, ms,
+                                                                                                 cand);
+        med_final_kernel<P><<<nprob, 1024, 0, st>>>(n_total, cap, ms, cand, 1e-12, min_var, out, fail);
+        const int rc = check_launch("median bracket kernels");
+        if (rc) return rc;
+        only = fail;
+        launches = 3;
     }
+    for (int level = 0; level < KeyT<P>::nlevels; ++level) {
+        select_hist_kernel<P><<<dim3(nprob, nchunks), 256, 0, st>>>(var, O, sp, n_total, level, state, hist, only);
+        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, 1e-12, min_var, q, out, only);
+    }
+    note_launches(launches + 2 * KeyT<P>::nlevels);
     return check_launch("select kernels");
 }
 
@@ -858,8 +1083,11 @@ extern "C" int eks_initial_guess(const void* var_base, long long seq_stride, con
     return check_launch("guess_kernel");
 }
 
-extern "C" size_t eks_const_R_median_workspace_bytes(int B, int O) {
-    return (size_t)B * O * (sizeof(SelState) + 2 * NBINS * sizeof(int));
+extern "C" size_t eks_const_R_median_workspace_bytes(int dtype, int B, int O, int T) {
+    const size_t base = (size_t)B * O * (sizeof(SelState) + 2 * NBINS * sizeof(int));
+    if (T < MED_MIN_FRAMES) return base;
+    return base + 256 + (dtype == EKS_F32 ? med_extra_bytes(B * O, T, 4, sizeof(MedState<float>))
+                                          : med_extra_bytes(B * O, T, 8, sizeof(MedState<double>)));
 }
 
 extern "C" int eks_const_R_median(const void* var_base, long long seq_stride, const long long* chan_off, int dtype,

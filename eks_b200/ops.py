@@ -129,14 +129,14 @@ def const_R_median(var: PlaneView, B: int, T: int, spans=None, min_var: float = 
     dev, dtype = var.base.device, var.base.dtype
     O = var.n_chan
     out = torch.empty((B, O), dtype=dtype, device=dev)
-    nbytes = lib().eks_const_R_median_workspace_bytes(B, O)
+    nbytes = lib().eks_const_R_median_workspace_bytes(dt_code(dtype), B, O, T)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     off = i64_host(var.chan_off)
     n, s0, s1 = _spans(spans, T)
     check(lib().eks_const_R_median(ptr(var.base), var.seq_stride, ptr(off), dt_code(dtype), B, O, T, n, ptr(s0),
                                    ptr(s1), float(min_var), ptr(out), ptr(ws), nbytes, stream_ptr()),
           'eks_const_R_median')
-    _count(6 if dtype == torch.float32 else 12)  # (histogram + scan) per radix level
+    _count(int(lib().eks_last_launch_count()))
     return out
 
 

@@ -69,8 +69,11 @@ int eks_initial_guess(const void* var_base, long long seq_stride, const long lon
 /* ---- constant R for the loss path: constant_R_from_timevarying on cropped frames
  * (eks/core.py:599-602, :702-709; crop_frames eks/utils.py:235-290).  Exact nanmedian over the
  * frames in the spans (n_spans == 0: all frames; spans sorted, non-overlapping, host arrays),
- * floored at max(1e-12, min_var).  Rconst_out: [B][O] real. */
-size_t eks_const_R_median_workspace_bytes(int B, int O);
+ * floored at max(1e-12, min_var).  Rconst_out: [B][O] real.
+ * Sequences of >= 131072 frames: the median is bracketed from 4096 samples, ONE pass over the planes counts the keys
+ * below the bracket and compacts those inside it, and the exact radix select runs on the candidates (bit-identical
+ * order statistics); problems whose bracket missed are redone by the three-pass radix select used for short ones. */
+size_t eks_const_R_median_workspace_bytes(int dtype, int B, int O, int T);
 int eks_const_R_median(const void* var_base, long long seq_stride, const long long* chan_off_host, int dtype, int B,
                        int O, int T, int n_spans, const int* span_start_host, const int* span_end_host,
                        double min_var, void* Rconst_out, void* workspace, size_t workspace_bytes, void* stream);

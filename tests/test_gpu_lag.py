@@ -140,11 +140,14 @@ def test_fused_smoother_slow_forgetting_falls_back():
     kernels redo them -- the result is still the oracle's"""
     from oracle import oracle
     raw = _smooth_walk(M=4, K=2, T=30_000, seed=3, step=0.002, noise=0.8)
-    s = [1e-5, 3e-5]
+    s = [1e-3, 3e-3]
     ref = oracle.singlecam(raw, dtype=np.float64, smooth_param=s)
     from eks_b200.pipeline import singlecam_smooth_sessions
-    res = singlecam_smooth_sessions(torch.as_tensor(raw).cuda()[None], dtype=torch.float64, smooth_param=s)
+    t = torch.as_tensor(raw).cuda()[None]
+    res = singlecam_smooth_sessions(t, dtype=torch.float64, smooth_param=s)
+    exact = singlecam_smooth_sessions(t, dtype=torch.float64, smooth_param=s, exact_scan=True)
     torch.cuda.synchronize()
+    assert torch.equal(res.out, exact.out), 'flagged sequences must come out of the exact scan kernels bit for bit'
     check_columns(_out(res), ref['out'], 1e-5, 'slow forgetting')
 
 
