@@ -246,8 +246,10 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         const Tin* src = base + off0 + (long long)threadIdx.x * EPG;
         unsigned char* dst = smem_raw + threadIdx.x * 16;
         for (int g = threadIdx.x; g < ngran; g += blockDim.x, src += blockDim.x * EPG, dst += blockDim.x * 16) {
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m) ens_cp_async_16(dst + (size_t)m * chunk_pad, src + (long long)m * m_stride);
+            const Tin* sm_ = src;
+            unsigned char* dm = dst;
+#pragma unroll 2       // (fully unrolled, the ten address pairs cost 80 registers and two resident CTAs)
+            for (int m = 0; m < MAXM; ++m, sm_ += m_stride, dm += chunk_pad) ens_cp_async_16(dm, sm_);
         }
     } else {   // stage the M contiguous seed chunks: coalesced 16-byte cp.async, pointers advanced by constant strides
         const Tin* src = base + off0;

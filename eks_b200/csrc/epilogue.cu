@@ -21,8 +21,8 @@ struct ReprojArgs {
 
 template <class P>
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojArgs<P> a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;      // problems on grid x: no 65535 limit
     if (t >= a.T) return;
     const int D = a.D;
     P m[EKS_MAX_STATE], Vm[EKS_MAX_STATE * EKS_MAX_STATE];
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
 
 template <class P>
 int reproject_launch(const ReprojArgs<P>& a, cudaStream_t st) {
-    dim3 grid((a.T + 255) / 256, a.B);
+    dim3 grid(a.B, (a.T + 255) / 256);
     reproject_kernel<P><<<grid, 256, 0, st>>>(a);
     return check_launch("reproject_kernel");
 }

@@ -159,7 +159,7 @@ template <class P>
 __global__ void __launch_bounds__(RUNS_RED_NT) gen_runs_reduce_kernel(const __grid_constant__ GArgs<P> a,
                                                                       const __grid_constant__ RunArgs<P> g) {
     __shared__ double scratch[32];
-    const int b = blockIdx.y, r = blockIdx.x * RUNS_RED_NT + threadIdx.x;
+    const int b = blockIdx.x, r = blockIdx.y * RUNS_RED_NT + threadIdx.x;   // problems on grid x: no 65535 limit
     const int blk = g.seq_block[b];
     if (blk < 0 || g.bstate[blk].done) return;
     const int n = a.sp.total;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(RUNS_RED_NT) gen_runs_reduce_kernel(const __gr
     dv = block_sum(dv, scratch);
     bad = block_sum(bad, scratch);
     if (threadIdx.x == 0) {
-        double* o = g.part2 + ((long long)b * g.nred + blockIdx.x) * 4;
+        double* o = g.part2 + ((long long)b * g.nred + blockIdx.y) * 4;
         o[0] = v; o[1] = dv; o[2] = bad; o[3] = all_ok ? 0.0 : 1.0;
     }
 }
@@ -325,7 +325,7 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
     for (int it = 0; it < slots; ++it) {
         g.final_slot = it;
         gen_nll_runs_kernel<P, DC, OC, FIXED, NL><<<(nthreads + 31) / 32, 32, 0, st>>>(a, g);
-        gen_runs_reduce_kernel<P><<<dim3(g.nred, a.B), RUNS_RED_NT, 0, st>>>(a, g);
+        gen_runs_reduce_kernel<P><<<dim3(a.B, g.nred), RUNS_RED_NT, 0, st>>>(a, g);
         gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 0);
     }
     if (getenv("EKS_DEBUG_RUNS")) {
@@ -881,7 +881,7 @@ static int lin_optimize_launch(const GArgs<P>& a, RunArgs<P> g, const LinArgs<P>
         g.final_slot = it;
         lin_prep_kernel<P, DC, OC, FIXED><<<a.B, 32, 0, st>>>(a, g, l);
         lin_runs_kernel<P, DC, OC, FIXED><<<(nthreads + 63) / 64, 64, 0, st>>>(a, g, l);
-        gen_runs_reduce_kernel<P><<<dim3(g.nred, a.B), RUNS_RED_NT, 0, st>>>(a, g);
+        gen_runs_reduce_kernel<P><<<dim3(a.B, g.nred), RUNS_RED_NT, 0, st>>>(a, g);
         gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 0);
     }
     if (getenv("EKS_DEBUG_RUNS")) {

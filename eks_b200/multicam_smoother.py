@@ -24,7 +24,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from eks_b200 import core, ops
+from eks_b200 import _xfer, core, ops
 from eks_b200._lib import require_cuda
 from eks_b200.core import PinholeProjection, ensemble, run_kalman_smoother
 from eks_b200.marker_array import MarkerArray, input_dfs_to_markerArray, mA_to_stacked_array, stacked_array_to_mA
@@ -262,24 +262,33 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
     dtype = core.get_precision()
     M, V, T, K, _ = marker_array.shape
     t0 = time.perf_counter()
-    raw = torch.as_tensor(marker_array.array).to(device=dev, dtype=dtype)
+    arr = marker_array.array
+    if list(marker_array.data_fields or ['x', 'y', 'likelihood']) != ['x', 'y', 'likelihood']:
+        arr = marker_array.slice_fields('x', 'y', 'likelihood').array      # reorder / drop extra fields (as core.ensemble)
+    raw = _xfer.to_device(arr, dev).to(dtype)
     sp = None
-    if smooth_param is not None:
-        sp = [float(smooth_param)] * K if isinstance(smooth_param, (int, float)) else [float(x) for x in smooth_param]
+    if smooth_param is not None:   # scalar (also NumPy scalars / 0-d arrays) or one value per keypoint, as np.asarray would
+        sp = [float(x) for x in np.broadcast_to(np.asarray(smooth_param, dtype=float), (K,))]
     res = multicam_smooth_sessions(raw[None], smooth_param=sp, spans=normalize_spans(T, s_frames),
                                    quantile_keep_pca=quantile_keep_pca, n_latent=n_latent, avg_mode=avg_mode,
                                    var_mode=var_mode, dtype=dtype, inflate_vars=inflate_vars,
                                    inflate_vars_kwargs=inflate_vars_kwargs, cams=cams)
-    out = res.out[0].permute(1, 3, 0, 2).contiguous().double().cpu().numpy()        # (V,T,K,9)
-    ms = res.ms.double().cpu().numpy()                                              # (K,T,L)
-    Vd = torch.diagonal(res.Vs, dim1=2, dim2=3).double().cpu().numpy()              # (K,T,L)
+    out_dev = torch.empty((V, T, K, 9), dtype=torch.float64, device=dev)
+    out_dev.copy_(res.out[0].permute(1, 3, 0, 2))                                   # planes -> (V,T,K,9) float64
+    out = _xfer.to_host(out_dev)
+    del out_dev
+    # 3-D DataFrame block assembled on the device: per keypoint [x, y, z, var_x, var_y, var_z] (:530-543)
+    lat = torch.cat([res.ms[:, :, :3], torch.diagonal(res.Vs, dim1=2, dim2=3)[:, :, :3]], dim=2)   # (K,T,6)
+    arr3d_dev = torch.empty((T, K, 6), dtype=torch.float64, device=dev)
+    arr3d_dev.copy_(lat.permute(1, 0, 2))
+    arr3d = _xfer.to_host(arr3d_dev.view(T, K * 6))
+    del arr3d_dev, lat
     s_finals = res.s_finals[0].cpu().numpy()
     logger.debug(f'[profile] device pipeline (upload, smooth, download): {time.perf_counter() - t0:.3f}s')
     t0 = time.perf_counter()
     pdindex = make_dlc_pandas_index(keypoint_names, labels=LABELS)
     camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex) for c in range(V)]
     labels_3d = ['x', 'y', 'z', 'x_posterior_var', 'y_posterior_var', 'z_posterior_var']
-    arr3d = np.concatenate([np.concatenate([ms[k][:, :3], Vd[k][:, :3]], axis=1) for k in range(K)], axis=1)
     df_3d = pd.DataFrame(arr3d, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d))
     logger.debug(f'[profile] packaging: {time.perf_counter() - t0:.3f}s')
     return camera_dfs, s_finals, df_3d

@@ -15,7 +15,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from eks_b200 import core, ops
+from eks_b200 import _xfer, core, ops
 from eks_b200._lib import require_cuda
 from eks_b200.marker_array import MarkerArray, input_dfs_to_markerArray
 from eks_b200.pipeline import singlecam_smooth_sessions
@@ -72,13 +72,16 @@ def ensemble_kalman_smoother_singlecam(
         raise ValueError('Not enough frames to compute temporal differences.')
     arr = marker_array.array if list(marker_array.data_fields or ['x', 'y', 'likelihood']) == [
         'x', 'y', 'likelihood'] else marker_array.slice_fields('x', 'y', 'likelihood').array
-    raw = torch.as_tensor(np.ascontiguousarray(arr)).to(dev)
+    raw = _xfer.to_device(arr, dev)                  # chunked, double-buffered through pinned staging
     if raw.dtype not in (torch.float32, torch.float64) or (raw.dtype == torch.float32 and dtype == torch.float64):
         raw = raw.to(torch.float64)
     spans = normalize_spans(T, s_frames)
     res = singlecam_smooth_sessions(raw.reshape(1, M, 1, T, K, 3), smooth_param=smooth_param, spans=spans,
                                     blocks=blocks or None, avg_mode=avg_mode, var_mode=var_mode, dtype=dtype)
-    final = res.out[0].permute(2, 0, 1).reshape(T, K * 9).double().cpu().numpy()  # (T, K*9), keypoint-major
+    final_dev = torch.empty((T, K, 9), dtype=torch.float64, device=dev)
+    final_dev.copy_(res.out[0].permute(2, 0, 1))     # one transpose + cast kernel: planes -> (T, K, 9) float64
+    final = _xfer.to_host(final_dev.view(T, K * 9))  # (T, K*9), keypoint-major
+    del final_dev
     labels = ops.OUT_COLS
     markers_df = pd.DataFrame(final, columns=make_dlc_pandas_index(keypoint_names, labels=labels))
     s_finals = res.s_finals[0].cpu().numpy().astype(float)
