@@ -388,8 +388,10 @@ __global__ void __launch_bounds__(256) moments_finalize_kernel(const double* __r
         // singlecam_smoother.py:262-266)
         mean_out[seq * 2 + 0] = P(mx);
         mean_out[seq * 2 + 1] = P(my);
-        var_out[seq * 2 + 0] = P(fmax(a[2] / n - mx * mx, 0.0));
-        var_out[seq * 2 + 1] = P(fmax(a[3] / n - my * my, 0.0));
+        // np.nanvar of an all-NaN column (a NaN mean makes every centred value NaN) is NaN: keep it, do not clamp to 0
+        const double vx = a[2] / n - mx * mx, vy = a[3] / n - my * my;
+        var_out[seq * 2 + 0] = P(vx != vx ? vx : fmax(vx, 0.0));
+        var_out[seq * 2 + 1] = P(vy != vy ? vy : fmax(vy, 0.0));
     }
 }
 

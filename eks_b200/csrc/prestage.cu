@@ -402,25 +402,24 @@ __global__ void __launch_bounds__(1024) med_final_kernel(int n_total, int cap, M
     if (!ok) return;
     const key_t* kc = cand + (long long)prob * cap;
     const int nc = st.n_cand;
-    for (int level = 0; level < KT::nlevels; ++level) {
-        const int shift = KT::shift(level), nb = KT::bits(level), hshift = shift + nb;
-        if ((st.lo >> shift) == (st.hi >> shift)) {
-            // every candidate lies in [lo, hi]: they all share this digit (and the ones above).  Histogramming it would
-            // be ~10^5 shared-memory atomics on ONE bin (measured: 190 us of this kernel); the ranks do not change.
-            if (threadIdx.x < 2) prefix[threadIdx.x] = (prefix[threadIdx.x] << nb) | ((st.lo >> shift) & (key_t)((1 << nb) - 1));
-            __syncthreads();
-            continue;
-        }
+    // Radix select on the keys RELATIVE to the bracket, k - lo in [0, hi - lo], most significant digit first.  (On the raw
+    // keys every candidate shares the leading digits: ~10^5 shared-memory atomics on one or two bins, measured 190 us.)
+    const key_t span = st.hi - st.lo;
+    int nbits = 0;
+    while (nbits < (int)(8 * sizeof(key_t)) && (span >> nbits) != 0) ++nbits;      // bit length of span
+    for (int top = nbits; top > 0; top -= 11) {
+        const int nb = min(11, top), shift = top - nb;
         for (int i = threadIdx.x; i < 2 * NBINS; i += blockDim.x) (&hist[0][0])[i] = 0;
         __syncthreads();
         const key_t pre0 = prefix[0], pre1 = prefix[1];
-        const bool same = (level == 0) || (pre0 == pre1);
+        const bool first = (top == nbits);
+        const bool same = first || (pre0 == pre1);
         for (int i = threadIdx.x; i < nc; i += blockDim.x) {
-            const key_t k = kc[i];
+            const key_t k = kc[i] - st.lo;
             const int bin = (int)((k >> shift) & (key_t)((1 << nb) - 1));
-            const key_t top = (level == 0) ? 0 : (k >> hshift);
-            if (level == 0 || top == pre0) atomicAdd(&hist[0][bin], 1);
-            if (!same && top == pre1) atomicAdd(&hist[1][bin], 1);
+            const key_t hi_part = first ? 0 : (k >> top);
+            if (first || hi_part == pre0) atomicAdd(&hist[0][bin], 1);
+            if (!same && hi_part == pre1) atomicAdd(&hist[1][bin], 1);
         }
         __syncthreads();
         if (threadIdx.x < 2) {
@@ -437,7 +436,7 @@ __global__ void __launch_bounds__(1024) med_final_kernel(int n_total, int cap, M
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const P a = KT::unkey(prefix[0]), c = KT::unkey(prefix[1]);
+        const P a = KT::unkey(st.lo + prefix[0]), c = KT::unkey(st.lo + prefix[1]);
         P med = (a + c) * P(0.5);
         med = (P)fmax((double)med, floor_lo);      // build_R_from_vars clip (1e-12) then min_R_var, as select_scan_kernel
         med = (P)fmax((double)med, floor_hi);

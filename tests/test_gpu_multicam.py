@@ -76,8 +76,10 @@ def test_multicam_linear_fp32():
     trace = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
     it = res.iters[0].cpu().numpy()
     for k in range(len(kps)):
+        # kappa: the float32 model inputs (PCA components, centring offsets: 6e-8 relative) move each innovation of a
+        # +-100 px coordinate by ~6e-6 px, i.e. the 2000-term loss by ~25 float32 ulps at this tiny T (501 frames)
         fp32_stop_protocol(f'mirror-mouse-separate kp{k}', trace[k], it[k], ref['info']['trace'][k],
-                           ref['info']['iters'][k])
+                           ref['info']['iters'][k], kappa=64.0)
     print('[parity fp32] mirror-mouse-separate |ds|/s vs fp64 oracle', np.abs(s2 - ref['s_finals']) / ref['s_finals'])
 
 
