@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 F32, F64 = 0, 1
+ABI_VERSION = 200      # eks_version() of the library this package was written against (include/eks_b200.h)
 MAX_CHAN, MAX_STATE, CAM_STRIDE = 16, 6, 29
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -53,8 +54,7 @@ _SIGS = {
                                   c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                   c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
-}
-_OPTIONAL_SIGS = {
+    # (round 1 loaded the entry points below only if present; a stale library now fails at load time)
     'eks_triangulate_mean': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'eks_last_launch_count': (c_int, []),
     'eks_mc_valid_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
@@ -94,19 +94,21 @@ def lib() -> ctypes.CDLL:
                 f'{LIB_PATH} not found: build it with `python -m eks_b200.build` '
                 '(eks_b200 has no CPU fallback)')
         L = ctypes.CDLL(LIB_PATH)
+        missing = [name for name in _SIGS if not hasattr(L, name)]
+        if missing:   # every symbol of include/eks_b200.h is mandatory: never select another path on a stale build
+            raise EksB200Error(f'{LIB_PATH} is stale: missing {missing}; rebuild with `python -m eks_b200.build --force`')
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        for name, (res, args) in _OPTIONAL_SIGS.items():
-            if hasattr(L, name):
-                fn = getattr(L, name)
-                fn.restype, fn.argtypes = res, args
+        if L.eks_version() != ABI_VERSION:
+            raise EksB200Error(f'{LIB_PATH} has ABI version {L.eks_version()}, this package needs {ABI_VERSION}; '
+                               'rebuild with `python -m eks_b200.build --force`')
         _lib = L
     return _lib
 
 
 def exported_symbols() -> list[str]:
-    return list(_SIGS) + list(_OPTIONAL_SIGS)
+    return list(_SIGS)
 
 
 def check(rc: int, what: str) -> None:

@@ -9,6 +9,7 @@
 //     EKS_OPT_MODE=stream and as its cross-check.
 // (2) the final filter + RTS smoother pass with time-varying R_t (below).
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 #include "ekf_generic.cuh"
 #include "diag.cuh"
@@ -222,9 +223,11 @@ static int diag_optimize_run(DiagOptArgs<P>& a, void* workspace, size_t workspac
     static int n_streams_dev[64];
     static cudaStream_t hs_dev[64][4];
     static bool hs_init[64];
+    static std::mutex hs_mutex;   // the table is the library's only cross-call state: host threads may race to create it
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
+    std::lock_guard<std::mutex> hs_lock(hs_mutex);
     if (!hs_init[dev]) {   // internal streams belong to the device that is current at first use (one table per device)
         const char* e2 = getenv("EKS_OPT_STREAMS");
         int nsd = e2 ? atoi(e2) : 2;

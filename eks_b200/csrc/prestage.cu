@@ -312,61 +312,72 @@ __global__ void __launch_bounds__(256) med_count_kernel(PlaneView var, int O, Sp
                                                         typename KeyT<P>::type* __restrict__ cand) {
     using KT = KeyT<P>;
     using key_t = typename KT::type;
+    constexpr int LCAP = 16;                 // candidates a thread can hold (its 64 frames contain ~5 on average)
     __shared__ key_t buf[MED_SCAP];
-    __shared__ int sh_n, sh_below, sh_nan, sh_base, sh_fail;
+    __shared__ int wsum[8];
+    __shared__ int sh_base, sh_fail;
     const int prob = blockIdx.x, b = prob / O, o = prob - b * O;
     const key_t lo = state[prob].lo, hi = state[prob].hi;
     const P* base = reinterpret_cast<const P*>(var.base) + (long long)b * var.seq_stride + var.chan_off[o];
-    if (threadIdx.x == 0) { sh_n = 0; sh_below = 0; sh_nan = 0; sh_fail = state[prob].fail; }
+    if (threadIdx.x == 0) sh_fail = state[prob].fail;
     __syncthreads();
     if (sh_fail) return;      // (read once: other CTAs of this problem may set the flag concurrently)
     const int i0 = blockIdx.y * MED_CHUNK, i1 = min(n_total, i0 + MED_CHUNK);
-    const int lane = threadIdx.x & 31;
-    int below = 0, nans = 0;
-    constexpr int UN = 4;       // independent loads in flight per thread (the loop is latency bound otherwise)
-    for (int ib = i0 + (threadIdx.x & ~31); ib < i1; ib += UN * blockDim.x) {      // warp-uniform trip count
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int below = 0, nans = 0, nloc = 0;
+    key_t loc[LCAP];
+    constexpr int UN = 4;       // independent loads in flight per thread
+    for (int ib = i0 + threadIdx.x; ib < i1; ib += UN * blockDim.x) {
         P x[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int i = ib + u * blockDim.x + lane;
+            const int i = ib + u * blockDim.x;
             x[u] = P(0);
             if (i < i1) x[u] = base[(sp.n == 1) ? sp.start[0] + i : span_to_frame(sp, i)];
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            const int i = ib + u * blockDim.x + lane;
-            bool in = false;
-            key_t k = 0;
+            const int i = ib + u * blockDim.x;
             if (i < i1) {
                 if (isnan(x[u])) ++nans;
                 else {
-                    k = KT::key(x[u]);
+                    const key_t k = KT::key(x[u]);
                     if (k < lo) ++below;
-                    else in = (k <= hi);
+                    else if (k <= hi) {
+                        if (nloc < LCAP) loc[nloc] = k;
+                        ++nloc;
+                    }
                 }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (m) {
-                int pos = 0;
-                if (lane == 0) pos = atomicAdd(&sh_n, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                if (in && pos < MED_SCAP) buf[pos] = k;
             }
         }
     }
+    // block-wide exclusive scan of the per-thread candidate counts (no atomics in the streaming loop)
+    const int over = __syncthreads_or(nloc > LCAP ? 1 : 0);
+    int incl = nloc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
     below = warp_sum(below);
     nans = warp_sum(nans);
-    if (lane == 0) { if (below) atomicAdd(&sh_below, below); if (nans) atomicAdd(&sh_nan, nans); }
     __syncthreads();
-    const int n = sh_n;
+    int woff = 0, n = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) woff += wsum[w]; n += wsum[w]; }
+    const int excl = woff + incl - nloc;
+    if (lane == 0) {
+        if (below) atomicAdd(&state[prob].n_below, below);
+        if (nans) atomicAdd(&state[prob].n_nan, nans);
+    }
     if (threadIdx.x == 0) {
-        if (sh_below) atomicAdd(&state[prob].n_below, sh_below);
-        if (sh_nan) atomicAdd(&state[prob].n_nan, sh_nan);
         int gbase = 0;
-        if (n > MED_SCAP) { state[prob].fail = 1; gbase = cap; }          // a CTA's buffer overflowed
+        if (over || n > MED_SCAP) { state[prob].fail = 1; gbase = cap; }   // a thread's or the CTA's buffer overflowed
         else if (n > 0) gbase = atomicAdd(&state[prob].n_cand, n);
         sh_base = gbase;
     }
+    if (!over && n <= MED_SCAP)
+        for (int j = 0; j < nloc; ++j) buf[excl + j] = loc[j];
     __syncthreads();
     const int gbase = sh_base;
     if (gbase + n > cap) {                                                  // the problem's buffer overflowed
@@ -422,16 +433,31 @@ __global__ void __launch_bounds__(1024) med_final_kernel(int n_total, int cap, M
             if (!same && hi_part == pre1) atomicAdd(&hist[1][bin], 1);
         }
         __syncthreads();
-        if (threadIdx.x < 2) {
-            const int r = threadIdx.x;
+        if (threadIdx.x < 64) {     // warp r finds the bin holding rank[r]: 64 bins per lane, warp prefix sum, local scan
+            const int r = threadIdx.x >> 5, ln = threadIdx.x & 31;
             const int* h = hist[same ? 0 : r];
-            int cum = 0, bin = 0;
-            for (bin = 0; bin < (1 << nb); ++bin) {
-                if (cum + h[bin] > rank[r]) break;
-                cum += h[bin];
+            const int per = NBINS / 32;
+            int mine = 0;
+            for (int q = 0; q < per; ++q) mine += h[ln * per + q];
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (ln >= d) incl += v;
             }
-            rank[r] -= cum;
-            prefix[r] = (prefix[r] << nb) | (key_t)bin;
+            const int target = rank[r];
+            const unsigned hit = __ballot_sync(0xffffffffu, incl > target);     // first lane whose cumulative count passes
+            const int owner = hit ? __ffs(hit) - 1 : 31;
+            __syncwarp();
+            if (ln == owner) {
+                int cum = incl - mine, bin = ln * per;
+                for (; bin < ln * per + per - 1; ++bin) {
+                    if (cum + h[bin] > target) break;
+                    cum += h[bin];
+                }
+                rank[r] = target - cum;
+                prefix[r] = (prefix[r] << nb) | (key_t)bin;
+            }
         }
         __syncthreads();
     }

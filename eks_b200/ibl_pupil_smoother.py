@@ -153,7 +153,8 @@ def ensemble_kalman_smoother_ibl_pupil(
         data.extend([processed[kx], processed[ky], ensemble_likes[:, i], ensemble_preds[:, ens_idx[i][0]],
                      ensemble_preds[:, ens_idx[i][1]], ensemble_vars[:, ens_idx[i][0]], ensemble_vars[:, ens_idx[i][1]],
                      y_v[:, i, i], y_v[:, i + 1, i + 1]])
-    df = pd.DataFrame(np.asarray(data, dtype=np.float64).T, columns=make_dlc_pandas_index(keypoint_names, labels=labels))
+    df = pd.DataFrame(np.asarray(data, dtype=np.float64).T, columns=make_dlc_pandas_index(keypoint_names, labels=labels),
+                      copy=False)
     return df, s_finals
 
 

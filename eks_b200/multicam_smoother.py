@@ -287,9 +287,9 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
     logger.debug(f'[profile] device pipeline (upload, smooth, download): {time.perf_counter() - t0:.3f}s')
     t0 = time.perf_counter()
     pdindex = make_dlc_pandas_index(keypoint_names, labels=LABELS)
-    camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex) for c in range(V)]
+    camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex, copy=False) for c in range(V)]   # fresh arrays: no copy
     labels_3d = ['x', 'y', 'z', 'x_posterior_var', 'y_posterior_var', 'z_posterior_var']
-    df_3d = pd.DataFrame(arr3d, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d))
+    df_3d = pd.DataFrame(arr3d, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d), copy=False)
     logger.debug(f'[profile] packaging: {time.perf_counter() - t0:.3f}s')
     return camera_dfs, s_finals, df_3d
 
@@ -402,12 +402,12 @@ def ensemble_kalman_smoother_multicam(
             cols.extend([proj[k, c, 0], proj[k, c, 1], emA_likes.array[0, c, :, k, 0], emA_unsm.array[0, c, :, k, 0],
                          emA_unsm.array[0, c, :, k, 1], out_vars.array[0, c, :, k, 0], out_vars.array[0, c, :, k, 1],
                          proj[k, c, 2], proj[k, c, 3]])
-        camera_dfs.append(pd.DataFrame(np.asarray(cols, dtype=np.float64).T, columns=pdindex))
+        camera_dfs.append(pd.DataFrame(np.asarray(cols, dtype=np.float64).T, columns=pdindex, copy=False))
     labels_3d = ['x', 'y', 'z', 'x_posterior_var', 'y_posterior_var', 'z_posterior_var']
     arr_3d = []
     for k in range(K):
         arr_3d.extend([ms[k][:, 0], ms[k][:, 1], ms[k][:, 2], Vs[k][:, 0, 0], Vs[k][:, 1, 1], Vs[k][:, 2, 2]])
-    df_3d = pd.DataFrame(np.asarray(arr_3d).T, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d))
+    df_3d = pd.DataFrame(np.asarray(arr_3d).T, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d), copy=False)
     logger.debug(f'[profile] reprojection + packaging: {time.perf_counter() - t0:.3f}s')
     logger.debug(f'[profile] ensemble_kalman_smoother_multicam total: {time.perf_counter() - t_total:.3f}s')
     return camera_dfs, s_finals, df_3d

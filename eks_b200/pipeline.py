@@ -116,7 +116,7 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
         singlecam_smooth_sessions.last_opt = opt
     # 3) final filter + RTS smoother (time-varying R_t), outputs into planes 0,1,7,8
     s_dev = s_finals.reshape(B).to(dtype)
-    if not force_generic and hasattr(lib(), 'eks_diag_smooth'):
+    if not force_generic:
         with _Stage('filter_smooth'):
             ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T], exact_scan=exact_scan)
     else:

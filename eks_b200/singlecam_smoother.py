@@ -83,7 +83,8 @@ def ensemble_kalman_smoother_singlecam(
     final = _xfer.to_host(final_dev.view(T, K * 9))  # (T, K*9), keypoint-major
     del final_dev
     labels = ops.OUT_COLS
-    markers_df = pd.DataFrame(final, columns=make_dlc_pandas_index(keypoint_names, labels=labels))
+    # copy=False: `final` is a fresh array this function owns (pandas 3 would otherwise copy 1.4 GB per 10^6 frames: 0.8 s)
+    markers_df = pd.DataFrame(final, columns=make_dlc_pandas_index(keypoint_names, labels=labels), copy=False)
     s_finals = res.s_finals[0].cpu().numpy().astype(float)
     return markers_df, s_finals
 

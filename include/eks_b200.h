@@ -11,8 +11,13 @@
  *    reference is float32; float64 is the parity mode.
  *  - The caller owns every buffer; the library never allocates or frees caller memory.  Scratch is
  *    passed as (workspace, workspace_bytes); sizes come from the *_workspace_bytes queries.
- *  - All calls only ENQUEUE work on `stream` (a cudaStream_t cast to void*) and return immediately;
- *    the caller synchronises.  No global state.
+ *  - Calls ENQUEUE work on `stream` (a cudaStream_t cast to void*) and return; the caller synchronises.
+ *    Exceptions, stated at the entry point: eks_pupil_optimize and eks_filter_smooth (sequences of >= 512 frames)
+ *    read a completion / verification flag and therefore synchronise `stream` themselves.
+ *  - State kept by the library: a thread-local error string and launch counter (eks_last_error,
+ *    eks_last_launch_count), and -- only for EKS_STRUCT_DIAG_STREAM -- a per-device table of two internal streams,
+ *    created on first use under a mutex and forked from / joined to the caller's stream by events.  Nothing else
+ *    persists between calls.  Entry points may be called concurrently from several host threads (different streams).
  *  - Return value: 0 ok; <0 invalid argument; >0 a cudaError_t.  eks_last_error() returns a
  *    thread-local message for the last non-zero return.
  *  - Per-frame data are "channel planes": element (sequence b, channel o, frame t) of a view
@@ -36,8 +41,9 @@ extern "C" {
 #define EKS_CAM_STRIDE 29  /* R(9 row-major) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 */
 
 const char* eks_last_error(void);
-int eks_version(void);
-/* Number of kernels the most recent eks_optimize_s call of this thread enqueued (bench.py's gpu_launches). */
+int eks_version(void);   /* 200 for this header; the Python binding refuses any other value */
+/* Number of kernels the most recent eks_optimize_s / eks_diag_smooth / eks_const_R_median call of this thread
+ * enqueued (bench.py's gpu_launches). */
 int eks_last_launch_count(void);
 
 /* ---- ensemble statistics: replaces eks.core.ensemble / compute_stats (eks/core.py:25-101) --------
@@ -122,7 +128,10 @@ int eks_optimize_s(int dtype, int B, int D, int O, int T, const void* m0, const 
 
 /* Final pass: EKF filter + RTS smoother over ALL frames with time-varying diagonal R_t from the var
  * view: replaces vmap(_smooth_one) / extended_kalman_smoother (eks/core.py:274-295).
- * s: [B] real.  ms_out [B][T][D], Vs_out [B][T][D][D] real (reference return layout, core.py:296-297). */
+ * s: [B] real.  ms_out [B][T][D], Vs_out [B][T][D][D] real (reference return layout, core.py:296-297).
+ * The filter represents dynamax's 1e-9 gain boost exactly (updates with R + eps, then P_f += eps P_f (H^T R'^-2 H) P_f).
+ * T >= 512: run-parallel execution with verified warm-up; this entry point then SYNCHRONISES `stream` (it reads two
+ * verification flags and repeats the pass with a longer warm-up if a run boundary disagreed). */
 size_t eks_filter_smooth_workspace_bytes(int dtype, int B, int D, int T);
 int eks_filter_smooth(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
                       const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
