@@ -61,6 +61,21 @@ class PinholeProjection:
     def n_cameras(self) -> int:
         return self.cams.shape[0]
 
+    def __call__(self, object_points) -> np.ndarray:
+        """h(X): (..., 3) world points -> (..., 2V) pixels [u_0, v_0, u_1, v_1, ...] (one camera: (..., 2)), evaluated
+        by the device projection of the library (eks_reproject) in float64 -- the same code the EKF linearises."""
+        dev = require_cuda()
+        X = np.asarray(object_points, dtype=np.float64)
+        lead, pts = X.shape[:-1], X.reshape(-1, 3)
+        N, V = pts.shape[0], self.n_cameras
+        ms = torch.as_tensor(np.ascontiguousarray(pts)).to(dev).reshape(1, N, 3)
+        Vs = torch.zeros((1, N, 3, 3), dtype=torch.float64, device=dev)
+        out = torch.empty((V, 4, N), dtype=torch.float64, device=dev)
+        ops.reproject(ms, Vs, V, out, V * 4 * N, 4 * N, [0, N, 2 * N, 3 * N],
+                      cams=torch.as_tensor(self.cams).to(dev))
+        uv = out[:, :2, :].permute(2, 0, 1).reshape(N, 2 * V).cpu().numpy()
+        return uv.reshape(lead + (2 * V,))
+
 
 def _to_device(x, dtype, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):

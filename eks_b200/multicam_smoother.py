@@ -73,6 +73,12 @@ def pack_camera(rvec_or_R, tvec, Kmat, dist) -> np.ndarray:
     return out
 
 
+def make_jax_projection_fn(rvec, tvec, K, dist_coeffs) -> PinholeProjection:
+    """One calibrated camera as an emission object (eks/multicam_smoother.py:806-859): callable (..., 3) -> (..., 2)
+    like the reference's JAX closure (the name is kept for drop-in compatibility; there is no JAX here)."""
+    return PinholeProjection(pack_camera(rvec, tvec, K, dist_coeffs)[None])
+
+
 class Camera:
     """Minimal stand-in for aniposelib.cameras.Camera (only what the EKS path uses)."""
 

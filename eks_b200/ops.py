@@ -162,13 +162,19 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
     dtype, dev = model.m0.dtype, model.m0.device
     B, D, O = model.B, model.D, model.O()
     if not blocks:
-        blocks = [[k] for k in range(B)]
-    nb = len(blocks)
-    boff = np.zeros(nb + 1, dtype=np.int32)
-    boff[1:] = np.cumsum([len(b) for b in blocks])
-    members = np.asarray([k for b in blocks for k in b], dtype=np.int32)
-    d_boff = torch.from_numpy(boff).to(dev)
-    d_mem = torch.from_numpy(members).to(dev)
+        # singleton blocks: built on the device (a pageable host->device copy would synchronise the stream with the
+        # host and serialise the session groups of pipeline.singlecam_smooth_sessions)
+        blocks = None
+        nb = B
+        d_boff = torch.arange(nb + 1, dtype=torch.int32, device=dev)
+        d_mem = torch.arange(nb, dtype=torch.int32, device=dev)
+    else:
+        nb = len(blocks)
+        boff = np.zeros(nb + 1, dtype=np.int32)
+        boff[1:] = np.cumsum([len(b) for b in blocks])
+        members = np.asarray([k for b in blocks for k in b], dtype=np.int32)
+        d_boff = torch.from_numpy(boff).to(dev)
+        d_mem = torch.from_numpy(members).to(dev)
     s_log = torch.empty(nb, dtype=dtype, device=dev)
     loss = torch.empty(nb, dtype=dtype, device=dev)
     iters = torch.empty(nb, dtype=torch.int32, device=dev)
@@ -184,7 +190,8 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
                                int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
     _count(int(lib().eks_last_launch_count()))   # the library reports what this call enqueued
-    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, blocks=blocks, _keep=(d_boff, d_mem, ws))
+    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace,
+                blocks=blocks if blocks is not None else [[k] for k in range(B)], _keep=(d_boff, d_mem, ws))
 
 
 def filter_smooth(model: Model, y: PlaneView, var: PlaneView, T: int, s: torch.Tensor, ymean=None):

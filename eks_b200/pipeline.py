@@ -31,18 +31,71 @@ class SinglecamResult:
     means: torch.Tensor      # (S, K, 2) centring offsets
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_streams(dev: torch.device, n: int) -> list:
+    """n non-default streams of `dev`, created once per device (session groups of one call run on them)."""
+    pool = _SIDE_STREAMS.setdefault((dev.type, dev.index), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+def _auto_groups(S: int, K: int, T: int) -> int:
+    """Session groups of one call.  The stages of the path alternate between HBM-bound (ensemble, final pass),
+    FP32-pipe-bound (lag statistics) and latency-bound (median select, the persistent Adam kernel: one warp per
+    sequence for ~120 dependent evaluations) work; independent session groups on separate streams let one group's
+    latency-bound stage run underneath another group's streaming stage.  A group must still fill the GPU on its own in
+    the streaming stages (>= ~16 sequences of >= 10^5 frames)."""
+    if S < 2 or K * T < 1_600_000:
+        return 1
+    return min(4, S)
+
+
 def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, blocks=None,
                               avg_mode='median', var_mode='confidence_weighted_var', dtype=torch.float32,
                               lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300, min_R_var=1e-4,
                               out: torch.Tensor | None = None, force_generic: bool = False,
                               trace_cap: int = 0, timers: dict | None = None,
-                              opt_mode: str = 'lag', exact_scan: bool = False) -> SinglecamResult:
+                              opt_mode: str = 'lag', exact_scan: bool = False,
+                              n_groups: int | None = None) -> SinglecamResult:
     """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
 
     spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks.
     opt_mode: 'lag' (one pass over the observations, closed-form NLL from lag statistics -- the default) or 'stream'
-    (one streaming pass per Adam evaluation); both are the same optimisation (tests compare them)."""
+    (one streaming pass per Adam evaluation); both are the same optimisation (tests compare them).
+    n_groups: sessions are independent problems; n_groups > 1 runs groups of sessions on separate streams (forked
+    from and joined to the caller's stream) so that their stages overlap.  None = automatic (1 for small inputs and
+    whenever per-stage timers or an optimiser trace are requested)."""
     assert raw.is_cuda and raw.dim() == 6 and raw.shape[2] == 1 and raw.shape[-1] == 3
+    S_all = raw.shape[0]
+    if n_groups is None:
+        n_groups = 1 if (timers is not None or trace_cap or force_generic) else _auto_groups(S_all, raw.shape[4],
+                                                                                           raw.shape[3])
+    n_groups = max(1, min(int(n_groups), S_all))
+    if n_groups > 1:
+        raw = raw.contiguous()
+        dev = raw.device
+        if out is None:
+            out = torch.empty((S_all, raw.shape[4], 9, raw.shape[3]), dtype=dtype, device=dev)
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        bounds = [(g * S_all) // n_groups for g in range(n_groups + 1)]
+        parts = []
+        for g, st in enumerate(_side_streams(dev, n_groups)):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                parts.append(singlecam_smooth_sessions(
+                    raw[bounds[g]:bounds[g + 1]], smooth_param=smooth_param, spans=spans, blocks=blocks,
+                    avg_mode=avg_mode, var_mode=var_mode, dtype=dtype, lr=lr, s_bounds_log=s_bounds_log, tol=tol,
+                    safety_cap=safety_cap, min_R_var=min_R_var, out=out[bounds[g]:bounds[g + 1]], opt_mode=opt_mode,
+                    exact_scan=exact_scan, n_groups=1))
+            main.wait_stream(st)
+        cat = lambda xs: None if xs[0] is None else torch.cat(xs, dim=0)
+        return SinglecamResult(out, cat([p.s_finals for p in parts]), cat([p.iters for p in parts]),
+                               cat([p.loss for p in parts]), cat([p.means for p in parts]))
 
     class _Stage:  # optional CUDA-event bracket per stage on the launching stream (bench.py)
         def __init__(self, name):

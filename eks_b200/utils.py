@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 import pandas as pd
 
+from eks_b200.io import convert_lp_dlc, format_data, get_keypoint_names  # noqa: F401  (eks/utils.py:35-232 live in io.py)
 from eks_b200.marker_array import MarkerArray
 
 

