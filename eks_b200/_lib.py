@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 F32, F64 = 0, 1
-ABI_VERSION = 200      # eks_version() of the library this package was written against (include/eks_b200.h)
+ABI_VERSION = 201      # eks_version() of the library this package was written against (include/eks_b200.h)
 MAX_CHAN, MAX_STATE, CAM_STRIDE = 16, 6, 29
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -56,6 +56,8 @@ _SIGS = {
                                   c_void_p]),
     # (round 1 loaded the entry points below only if present; a stale library now fails at load time)
     'eks_triangulate_mean': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'eks_geometric_init_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'eks_geometric_init': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'eks_last_launch_count': (c_int, []),
     'eks_mc_valid_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_double, c_double,

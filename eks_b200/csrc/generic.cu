@@ -231,7 +231,7 @@ using namespace eks;
 
 extern "C" const char* eks_last_error(void) { return g_err; }
 extern "C" int eks_last_launch_count(void) { return g_launches; }
-extern "C" int eks_version(void) { return 200; }
+extern "C" int eks_version(void) { return 201; }
 
 extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
                             const void* Q, const void* C, int ncam, const void* cams, const void* y_base,

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(1024) med_final_kernel(int n_total, int cap, M
 
 template <class P>
 int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total, double min_var, P* out,
-                void* workspace, size_t workspace_bytes, cudaStream_t st, double q = -1.0) {
+                void* workspace, size_t workspace_bytes, cudaStream_t st, double q = -1.0, double floor_lo = 1e-12) {
     const int nprob = B * O;
     const size_t need = (size_t)nprob * (sizeof(SelState) + 2 * NBINS * sizeof(int));
     EKS_REQUIRE(workspace && workspace_bytes >= need, "const_R_median: workspace too small (%zu < %zu)",
@@ -496,7 +496,7 @@ int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total
         med_sample_kernel<P><<<nprob, 512, 0, st>>>(var, O, sp, n_total, ms);
         med_count_kernel<P><<<dim3(nprob, (n_total + MED_CHUNK - 1) / MED_CHUNK), 256, 0, st>>>(var, O, sp, n_total, cap, ms,
                                                                                                  cand);
-        med_final_kernel<P><<<nprob, 1024, 0, st>>>(n_total, cap, ms, cand, 1e-12, min_var, out, fail);
+        med_final_kernel<P><<<nprob, 1024, 0, st>>>(n_total, cap, ms, cand, floor_lo, min_var, out, fail);
         const int rc = check_launch("median bracket kernels");
         if (rc) return rc;
         only = fail;
@@ -504,7 +504,7 @@ int run_const_R(const PlaneView& var, int B, int O, const Spans& sp, int n_total
     }
     for (int level = 0; level < KeyT<P>::nlevels; ++level) {
         select_hist_kernel<P><<<dim3(nprob, nchunks), 256, 0, st>>>(var, O, sp, n_total, level, state, hist, only);
-        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, 1e-12, min_var, q, out, only);
+        select_scan_kernel<P><<<nprob, 256, 0, st>>>(level, state, hist, floor_lo, min_var, q, out, only);
     }
     note_launches(launches + 2 * KeyT<P>::nlevels);
     return check_launch("select kernels");
@@ -1122,6 +1122,115 @@ extern "C" int eks_initial_guess(const void* var_base, long long seq_stride, con
     if (dtype == EKS_F32) guess_kernel<float><<<B, 256, 0, st>>>(v, B, O, T, guess_out, (float*)s_log0_out);
     else guess_kernel<double><<<B, 256, 0, st>>>(v, B, O, T, guess_out, (double*)s_log0_out);
     return check_launch("guess_kernel");
+}
+
+namespace eks {
+// ====================================================================================================
+// Geometric initialisation of the calibrated model (eks/multicam_smoother.py:600-650) on the device.
+// tri [B][T][3] float64 = triangulated ensemble means.  Per (sequence b, dimension d):
+//   m0   = mean of the first min(10, T) frames                                   (:618)
+//   S0   = nanvar over all frames (ddof 0, two passes like numpy) + 1e-4         (:619-625)
+//   Q    = max((1.4826 (median |dx - median dx| + 1e-12))^2, 1e-8), dx = lag-1 differences   (:632-642)
+// np.median is not NaN-aware: any NaN in the column makes Q NaN, which is reproduced.  The two medians are the exact
+// radix select of this file on float64 keys (one-pass bracketed form for long sequences).
+constexpr int GEO_NT = 1024;
+
+__global__ void __launch_bounds__(GEO_NT) geo_moments_kernel(const double* __restrict__ tri, int T,
+                                                             double* __restrict__ m0, double* __restrict__ S0d,
+                                                             int* __restrict__ n_nan) {
+    __shared__ double scratch[32];
+    const int prob = blockIdx.x, b = prob / 3, d = prob - b * 3;
+    const double* x = tri + (long long)b * T * 3 + d;
+    double s = 0, c = 0;
+    for (int t = threadIdx.x; t < T; t += GEO_NT) {
+        const double v = x[(long long)t * 3];
+        if (!isnan(v)) { s += v; c += 1.0; }
+    }
+    s = block_sum(s, scratch);
+    c = block_sum(c, scratch);
+    const double mean = s / c;
+    double ss = 0;
+    for (int t = threadIdx.x; t < T; t += GEO_NT) {
+        const double v = x[(long long)t * 3];
+        if (!isnan(v)) { const double e = v - mean; ss = fma(e, e, ss); }
+    }
+    ss = block_sum(ss, scratch);
+    if (threadIdx.x == 0) {
+        const int nh = min(10, T);
+        double h = 0;
+        for (int t = 0; t < nh; ++t) h += x[(long long)t * 3];
+        m0[prob] = h / (double)nh;
+        S0d[prob] = ss / c + 1e-4;
+        n_nan[prob] = T - (int)c;
+    }
+}
+
+__global__ void __launch_bounds__(256) geo_diff_kernel(const double* __restrict__ tri, int T, double* __restrict__ dx) {
+    const int prob = blockIdx.y, b = prob / 3, d = prob - b * 3;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= T - 1) return;
+    const double* x = tri + (long long)b * T * 3 + d;
+    dx[(long long)prob * (T - 1) + t] = x[(long long)(t + 1) * 3] - x[(long long)t * 3];
+}
+
+__global__ void __launch_bounds__(256) geo_absdev_kernel(int n, const double* __restrict__ med, double* __restrict__ dx) {
+    const int prob = blockIdx.y;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    double* p = dx + (long long)prob * n + t;
+    *p = fabs(*p - med[prob]);
+}
+
+__global__ void geo_final_kernel(int nprob, const double* __restrict__ mad, const int* __restrict__ n_nan,
+                                 double* __restrict__ Qd) {
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= nprob) return;
+    const double sigma = 1.4826 * (mad[prob] + 1e-12);
+    const double v = sigma * sigma;
+    Qd[prob] = (n_nan[prob] > 0 || isnan(v)) ? nan("") : fmax(v, 1e-8);      // np.maximum propagates NaN
+}
+
+}  // namespace eks
+
+static size_t geo_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t eks_geometric_init_workspace_bytes(int B, int T) {
+    const size_t np3 = (size_t)B * 3, n = (size_t)(T > 1 ? T - 1 : 1);
+    return geo_align(np3 * n * sizeof(double)) + 3 * geo_align(np3 * sizeof(double)) + geo_align(np3 * sizeof(int)) +
+           geo_align(eks_const_R_median_workspace_bytes(EKS_F64, B, 3, (int)n)) + 256;
+}
+
+extern "C" int eks_geometric_init(int B, int T, const void* tri, void* m0_out, void* S0_diag_out, void* Q_diag_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    EKS_REQUIRE(tri && m0_out && S0_diag_out && Q_diag_out, "geometric_init: null pointer");
+    EKS_REQUIRE(B >= 1 && T >= 2, "geometric_init: need at least two frames (B=%d, T=%d)", B, T);
+    EKS_REQUIRE(workspace && workspace_bytes >= eks_geometric_init_workspace_bytes(B, T),
+                "geometric_init: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np3 = B * 3, n = T - 1;
+    unsigned char* w = (unsigned char*)workspace;
+    double* dx = (double*)w; w += geo_align((size_t)np3 * n * sizeof(double));
+    double* med = (double*)w; w += geo_align((size_t)np3 * sizeof(double));
+    double* mad = (double*)w; w += geo_align((size_t)np3 * sizeof(double));
+    w += geo_align((size_t)np3 * sizeof(double));
+    int* n_nan = (int*)w; w += geo_align((size_t)np3 * sizeof(int));
+    const size_t sel_bytes = eks_const_R_median_workspace_bytes(EKS_F64, B, 3, n);
+    geo_moments_kernel<<<np3, GEO_NT, 0, st>>>((const double*)tri, T, (double*)m0_out, (double*)S0_diag_out, n_nan);
+    const dim3 grid((n + 255) / 256, np3);
+    geo_diff_kernel<<<grid, 256, 0, st>>>((const double*)tri, T, dx);
+    PlaneView v;
+    v.base = dx; v.seq_stride = 3LL * n;
+    for (int i = 0; i < MAX_CHAN; ++i) v.chan_off[i] = i < 3 ? (long long)i * n : 0;
+    Spans sp; sp.n = 1; sp.start[0] = 0; sp.cum[0] = 0; sp.cum[1] = n;
+    const double NOFLOOR = -HUGE_VAL;
+    if (int rc = run_const_R<double>(v, B, 3, sp, n, NOFLOOR, med, w, sel_bytes, st, -1.0, NOFLOOR)) return rc;
+    int launches = 2 + eks_last_launch_count();
+    geo_absdev_kernel<<<grid, 256, 0, st>>>(n, med, dx);
+    if (int rc = run_const_R<double>(v, B, 3, sp, n, NOFLOOR, mad, w, sel_bytes, st, -1.0, NOFLOOR)) return rc;
+    launches += 2 + eks_last_launch_count();
+    geo_final_kernel<<<(np3 + 127) / 128, 128, 0, st>>>(np3, mad, n_nan, (double*)Q_diag_out);
+    note_launches(launches);
+    return check_launch("geometric initialisation kernels");
 }
 
 extern "C" size_t eks_const_R_median_workspace_bytes(int dtype, int B, int O, int T) {

@@ -259,7 +259,8 @@ def project_3d_covariance_to_2d(ms_k, Vs_k, h_cam: PinholeProjection, inflated_v
 
 
 def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames, avg_mode,
-                            var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None, cams=None) -> tuple:
+                            var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None, cams=None,
+                            n_cams_out: int | None = None) -> tuple:
     """Linear PCA-latent model without variance inflation: every per-frame stage runs on the device
     (eks_b200.pipeline.multicam_smooth_sessions); the host only packs the DataFrames."""
     from eks_b200.pipeline import multicam_smooth_sessions
@@ -293,7 +294,9 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
     logger.debug(f'[profile] device pipeline (upload, smooth, download): {time.perf_counter() - t0:.3f}s')
     t0 = time.perf_counter()
     pdindex = make_dlc_pandas_index(keypoint_names, labels=LABELS)
-    camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex, copy=False) for c in range(V)]   # fresh arrays: no copy
+    # one DataFrame per NAMED camera (the reference loops over camera_names, eks/multicam_smoother.py:452, :490)
+    camera_dfs = [pd.DataFrame(out[c].reshape(T, K * 9), columns=pdindex, copy=False)
+                  for c in range(min(V, n_cams_out or V))]                              # fresh arrays: no copy
     labels_3d = ['x', 'y', 'z', 'x_posterior_var', 'y_posterior_var', 'z_posterior_var']
     df_3d = pd.DataFrame(arr3d, columns=make_dlc_pandas_index(keypoint_names, labels=labels_3d), copy=False)
     logger.debug(f'[profile] packaging: {time.perf_counter() - t0:.3f}s')
@@ -329,11 +332,12 @@ def ensemble_kalman_smoother_multicam(
         if inflate_vars and inflate_vars_kwargs.get('mean', None) is not None:      # :355-357
             inflate_vars_kwargs['mean'] = np.zeros_like(inflate_vars_kwargs['mean'])
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
-                                       avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs)
+                                       avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs,
+                                       n_cams_out=len(camera_names))
     if camgroup is not None and not inflate_vars and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
         h_all, _ = make_projection_from_camgroup(camgroup)          # calibrated model, device-resident pipeline
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
-                                       avg_mode, var_mode, 3, cams=h_all.cams)
+                                       avg_mode, var_mode, 3, cams=h_all.cams, n_cams_out=len(camera_names))
 
     t0 = time.perf_counter()
     ema = ensemble(marker_array, avg_mode=avg_mode, var_mode=var_mode)
@@ -402,7 +406,7 @@ def ensemble_kalman_smoother_multicam(
     out_vars = emA_vars if nonlinear else emA_inflated    # :474-477 vs :505-508
     pdindex = make_dlc_pandas_index(keypoint_names, labels=LABELS)
     camera_dfs = []
-    for c in range(V):
+    for c in range(min(V, len(camera_names))):     # one DataFrame per named camera (:452, :490)
         cols = []
         for k in range(K):
             cols.extend([proj[k, c, 0], proj[k, c, 1], emA_likes.array[0, c, :, k, 0], emA_unsm.array[0, c, :, k, 0],

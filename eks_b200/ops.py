@@ -342,6 +342,24 @@ def mc_inflate_step(y: PlaneView, ymean: torch.Tensor, var: PlaneView, T: int, l
     return flags
 
 
+def geometric_init(tri: torch.Tensor):
+    """initialize_kalman_filter_geometric (eks/multicam_smoother.py:600-650) on the device.
+    tri: (B, T, 3) float64 CUDA tensor of triangulated ensemble means -> (m0 (B,3), S0_diag (B,3), Q_diag (B,3)) float64."""
+    assert tri.is_cuda and tri.dtype == torch.float64 and tri.dim() == 3 and tri.shape[-1] == 3
+    tri = tri.contiguous()
+    B, T, _ = tri.shape
+    dev = tri.device
+    m0 = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    S0d = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    Qd = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    nbytes = lib().eks_geometric_init_workspace_bytes(B, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib().eks_geometric_init(B, T, ptr(tri), ptr(m0), ptr(S0d), ptr(Qd), ptr(ws), nbytes, stream_ptr()),
+          'eks_geometric_init')
+    _count(int(lib().eks_last_launch_count()))
+    return m0, S0d, Qd
+
+
 def triangulate_mean(raw: torch.Tensor, cams: torch.Tensor) -> torch.Tensor:
     """raw (M,V,T,K,3) device tensor (pixels), cams (V,29) float64 -> (K,T,3) float64: mean over the ensemble of
     the triangulated points (triangulate_3d_models(...).mean(axis=0))."""

@@ -13,6 +13,7 @@ Stages: ensemble statistics (+ fused centring moments) -> initial guess / median
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -32,14 +33,59 @@ class SinglecamResult:
 
 
 _SIDE_STREAMS: dict = {}
+# stage -> stream priority inside a session group (0 = default, more negative = dispatched first).  Measured on B200
+# (8 sessions x 20 keypoints x 10^6 frames, scripts/groups_bench.py): one stream 11.20 ms/step; 4 groups with equal
+# priorities 10.96; "later stages outrank earlier ones" (0,-1,-3,-2) 11.66; only the Adam kernel raised 10.94;
+# reversed 12.62.  The streaming kernels each fill the SMs on their own, so priorities only add hand-over gaps:
+# all stages stay at the default priority and the mechanism is kept for experiments (EKS_STAGE_PRIO).
+_STAGE_PRIO = {'ensemble': 0, 'prestage': 0, 'optimize_s': 0, 'filter_smooth': 0}
+if os.environ.get('EKS_STAGE_PRIO'):   # experiments: "ensemble,prestage,optimize_s,filter_smooth" priorities
+    _STAGE_PRIO = dict(zip(_STAGE_PRIO, [int(x) for x in os.environ['EKS_STAGE_PRIO'].split(',')]))
 
 
-def _side_streams(dev: torch.device, n: int) -> list:
-    """n non-default streams of `dev`, created once per device (session groups of one call run on them)."""
-    pool = _SIDE_STREAMS.setdefault((dev.type, dev.index), [])
-    while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
-    return pool[:n]
+class _Chain:
+    """All work of one session group is ONE dependency chain that hops between the group's streams of different
+    priority (`stage`); memory stays safe because every launch of the group is ordered after all earlier ones."""
+
+    def __init__(self, dev: torch.device, g: int):
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -5)
+        key = (dev.type, dev.index, g)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = {p: torch.cuda.Stream(device=dev, priority=max(p, min(lo, hi)))
+                                  for p in sorted(set(_STAGE_PRIO.values()), reverse=True)}
+        self.streams = _SIDE_STREAMS[key]
+        self.base = self.streams[0]
+        self.where = self.base
+
+    def hop(self, st):
+        if st is not self.where:
+            ev = torch.cuda.Event()
+            ev.record(self.where)
+            st.wait_event(ev)
+            self.where = st
+
+    def stage(self, name):
+        chain, st = self, self.streams[_STAGE_PRIO.get(name, -1)]
+
+        class _Ctx:
+            def __enter__(self_):
+                chain.hop(st)
+                self_.inner = torch.cuda.stream(st)
+                self_.inner.__enter__()
+
+            def __exit__(self_, *exc):
+                self_.inner.__exit__(*exc)
+                chain.hop(chain.base)      # torch ops between the stages run on the group's base stream, in order
+        return _Ctx()
+
+
+class _NoChain:
+    def stage(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def hop(self, st):
+        pass
 
 
 def _auto_groups(S: int, K: int, T: int) -> int:
@@ -59,7 +105,7 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
                               out: torch.Tensor | None = None, force_generic: bool = False,
                               trace_cap: int = 0, timers: dict | None = None,
                               opt_mode: str = 'lag', exact_scan: bool = False,
-                              n_groups: int | None = None) -> SinglecamResult:
+                              n_groups: int | None = None, _chain=None) -> SinglecamResult:
     """raw: (S, M, 1, T, K, 3) CUDA tensor (float32 or float64) in the MarkerArray layout.
 
     spans: validated [(start, end)] list (s_frames) or None; blocks: per-session keypoint blocks.
@@ -84,15 +130,17 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
         fork.record(main)
         bounds = [(g * S_all) // n_groups for g in range(n_groups + 1)]
         parts = []
-        for g, st in enumerate(_side_streams(dev, n_groups)):
-            st.wait_event(fork)
-            with torch.cuda.stream(st):
+        for g in range(n_groups):
+            chain = _Chain(dev, g)
+            chain.base.wait_event(fork)
+            with torch.cuda.stream(chain.base):
                 parts.append(singlecam_smooth_sessions(
                     raw[bounds[g]:bounds[g + 1]], smooth_param=smooth_param, spans=spans, blocks=blocks,
                     avg_mode=avg_mode, var_mode=var_mode, dtype=dtype, lr=lr, s_bounds_log=s_bounds_log, tol=tol,
                     safety_cap=safety_cap, min_R_var=min_R_var, out=out[bounds[g]:bounds[g + 1]], opt_mode=opt_mode,
-                    exact_scan=exact_scan, n_groups=1))
-            main.wait_stream(st)
+                    exact_scan=exact_scan, n_groups=1, _chain=chain))
+            chain.hop(chain.base)
+            main.wait_stream(chain.base)
         cat = lambda xs: None if xs[0] is None else torch.cat(xs, dim=0)
         return SinglecamResult(out, cat([p.s_finals for p in parts]), cat([p.iters for p in parts]),
                                cat([p.loss for p in parts]), cat([p.means for p in parts]))
@@ -115,14 +163,17 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
     S, M, _, T, K, _ = raw.shape
     dev = raw.device
     B = S * K
+    chain = _chain if _chain is not None else _NoChain()
     if out is None:
         out = torch.empty((S, K, 9, T), dtype=dtype, device=dev)
     assert out.shape == (S, K, 9, T) and out.dtype == dtype and out.is_contiguous()
     # 1) ensemble statistics straight into the output planes + centring moments
     plane_off = [c * T for c in ops.ENS_TO_OUT]
-    with _Stage('ensemble'):
+    with _Stage('ensemble'), chain.stage('ensemble'):
         partials = ops.ensemble_stats(raw, out, K * 9 * T, 0, 9 * T, plane_off, avg_mode=avg_mode,
                                       var_mode=var_mode, moments=True)
+    pre = chain.stage('prestage')
+    pre.__enter__()
     with _Stage('center_moments'):
         ymean, yvar = ops.center_moments(partials, T, dtype)      # (B,2) each
     # 2) model: m0 = 0, S0 = diag(var), A = C = Q = I (singlecam_smoother.py:246-284)
@@ -134,6 +185,7 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
     if smooth_param is not None:
         s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)
         s_finals = (s.expand(K) if s.dim() == 0 or s.numel() == 1 else s).expand(S, K).contiguous()
+        pre.__exit__(None, None, None)
     else:
         with _Stage('initial_guess'):
             guess, s_log0 = ops.initial_guess(vv, B, T)
@@ -147,7 +199,8 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
             g = guess.view(-1)
             s0 = torch.stack([g[torch.as_tensor(b, device=dev)].mean() for b in all_blocks])
             s_log0 = torch.log(s0.clamp(1e-6, 1e3)).float().to(dtype)
-        with _Stage('optimize_s'):
+        pre.__exit__(None, None, None)
+        with _Stage('optimize_s'), chain.stage('optimize_s'):
             opt = ops.optimize_s(model, yv, T, Rconst, s_log0, blocks=all_blocks, ymean=ymean, spans=spans, lr=lr,
                                  s_bounds_log=s_bounds_log, tol=tol, safety_cap=safety_cap, trace_cap=trace_cap,
                                  structure=ops.STRUCT_GENERAL if force_generic else (
@@ -168,11 +221,12 @@ def singlecam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, 
             s_finals, iters, loss = s_flat.view(S, K), it_flat.view(S, K), lo_flat.view(S, K)
         singlecam_smooth_sessions.last_opt = opt
     # 3) final filter + RTS smoother (time-varying R_t), outputs into planes 0,1,7,8
-    s_dev = s_finals.reshape(B).to(dtype)
     if not force_generic:
-        with _Stage('filter_smooth'):
+        with _Stage('filter_smooth'), chain.stage('filter_smooth'):
+            s_dev = s_finals.reshape(B).to(dtype)
             ops.diag_smooth(model, yv, vv, T, s_dev, ymean, out, 9 * T, [0, T, 7 * T, 8 * T], exact_scan=exact_scan)
     else:
+        s_dev = s_finals.reshape(B).to(dtype)
         ms, Vs = ops.filter_smooth(model, yv, vv, T, s_dev, ymean=ymean)
         o = out.view(B, 9, T)
         o[:, 0, :] = ms[:, :, 0] + ymean[:, 0:1]
@@ -377,18 +431,19 @@ def _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_
     """Calibrated branch of multicam_smooth_sessions (eks/multicam_smoother.py:380-405, 446-480): un-centred
     observations, 3-D state initialised from the triangulated ensemble mean, pinhole emission."""
     import numpy as np
-    from eks_b200.multicam_smoother import initialize_kalman_filter_geometric
     S, M, V, T, K, _ = raw.shape
     dev, B = raw.device, S * K
     cams64 = torch.as_tensor(np.asarray(cams, dtype=np.float64))
     assert cams64.shape == (V, 29), 'cams must be (n_cameras, 29) packed camera parameters'
     with stage('triangulate'):
         tri = torch.stack([ops.triangulate_mean(raw[s_], cams64) for s_ in range(S)])       # (S,K,T,3) float64
-    with stage('geometric_init'):
-        m0s, S0s, As, Qs, _ = initialize_kalman_filter_geometric(tri.reshape(B, T, 3).cpu().numpy())
-    f = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dtype).contiguous()
+    with stage('geometric_init'):      # means / variances / MAD of the differences on the device (eks_geometric_init)
+        m0d, S0d, Qd = ops.geometric_init(tri.reshape(B, T, 3))
+        eye = torch.eye(3, dtype=dtype, device=dev).expand(B, 3, 3).contiguous()
+        model_args = (m0d.to(dtype).contiguous(), torch.diag_embed(S0d).to(dtype).contiguous(), eye,
+                      torch.diag_embed(Qd).to(dtype).contiguous())
     d_cams = cams64.to(device=dev, dtype=dtype).contiguous()
-    model = Model(f(m0s), f(S0s), f(As), f(Qs), None, d_cams)
+    model = Model(*model_args, None, d_cams)
     iters = loss = None
     if smooth_param is not None:
         s = torch.as_tensor(smooth_param, dtype=torch.float64, device=dev)

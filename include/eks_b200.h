@@ -250,6 +250,15 @@ int eks_mc_inflate_step(int dtype, int B, int V, int L, int T, const void* y_bas
 int eks_triangulate_mean(const void* raw, int raw_dtype, int M, int V, int T, int K, const double* cams, double* out,
                          void* stream);
 
+/* Geometric initialisation of the calibrated model: replaces initialize_kalman_filter_geometric
+ * (eks/multicam_smoother.py:600-650).  tri [B][T][3] DOUBLE (eks_triangulate_mean's layout, B = sessions x keypoints).
+ * Outputs, DOUBLE: m0_out [B][3] = mean of the first min(10, T) frames; S0_diag_out [B][3] = nanvar over time + 1e-4;
+ * Q_diag_out [B][3] = max((1.4826 (median|dx - median dx| + 1e-12))^2, 1e-8) of the lag-1 differences dx (NaN if the
+ * column holds a NaN: np.median is not NaN-aware).  A = C = I are the caller's.  Exact radix-select medians. */
+size_t eks_geometric_init_workspace_bytes(int B, int T);
+int eks_geometric_init(int B, int T, const void* tri, void* m0_out, void* S0_diag_out, void* Q_diag_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,24 @@ def test_fit_eks_mirrored_multicam(tmp_path):
     ref_dfs, _, _ = ensemble_kalman_smoother_multicam(MarkerArray(raw.astype(np.float32), data_fields=['x', 'y', 'likelihood']),
                                                       parts, cams, smooth_param=3.0)
     np.testing.assert_allclose(final_df.to_numpy(), np.concatenate([d.to_numpy() for d in ref_dfs], axis=1), rtol=1e-6)
+
+
+@pytest.mark.parametrize('T', [2, 7, 1000, 150_001])
+def test_geometric_init_on_device_matches_oracle(T):
+    """eks_geometric_init (means, nan-variances, median / MAD of the lag-1 differences by the exact radix select, short
+    sequences through the multi-pass select, long ones through the one-pass bracketed median) against the oracle's
+    NumPy restatement of initialize_kalman_filter_geometric (eks/multicam_smoother.py:600-650)."""
+    from eks_b200 import ops
+    from oracle import oracle
+    rng = np.random.default_rng(T)
+    B = 4
+    tri = np.cumsum(rng.normal(0, [1e-3, 2e-3, 5e-4], size=(B, T, 3)), axis=1) + rng.uniform(-2, 4, size=(B, 1, 3))
+    tri[0, :, 1] += (rng.random(T) < 0.05) * rng.normal(0, 0.3, size=T)       # heavy-tailed jumps: MAD != std
+    if T > 20:
+        tri[2, T // 2, 2] = np.nan                                            # np.median propagates, nanvar does not
+    m0, S0d, Qd = ops.geometric_init(torch.as_tensor(tri).cuda())
+    with np.errstate(all='ignore'):
+        m0s, S0s, _, Qs, _ = oracle.geometric_init(tri)
+    np.testing.assert_allclose(m0.cpu().numpy(), m0s, rtol=1e-13)
+    np.testing.assert_allclose(S0d.cpu().numpy(), np.diagonal(S0s, axis1=1, axis2=2), rtol=1e-11)
+    np.testing.assert_allclose(Qd.cpu().numpy(), np.diagonal(Qs, axis1=1, axis2=2), rtol=1e-12, equal_nan=True)
