@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libeks_b200.so')
-SOURCES = ["generic.cu", "generic_runs.cu", "ensemble.cu", "prestage.cu", "diag.cu", "diag_lag.cu", "diag_smooth.cu", "epilogue.cu", "triangulate.cu"]
+SOURCES = ["generic.cu", "generic_runs.cu", "lin_lag.cu", "ensemble.cu", "prestage.cu", "diag.cu", "diag_lag.cu", "diag_smooth.cu", "epilogue.cu", "triangulate.cu"]
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "generic.cuh"
+#include "lin_lag.cuh"
 #include "diag.cuh"
 #include "../../include/eks_b200.h"
 
@@ -249,7 +250,9 @@ extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m
 extern "C" size_t eks_optimize_s_workspace_bytes(int dtype, int n_blocks, int B, int D, int O, int T) {
     const size_t a1 = diag_lag_workspace_bytes(dtype, n_blocks, B, T);   // >= diag_optimize_workspace_bytes
     const size_t a2 = T >= GEN_RUNS_MIN_FRAMES ? generic_runs_optimize_workspace_bytes(dtype, n_blocks, B, D, T) +
-                                                     linear_steady_workspace_bytes(dtype, B, D, O, T) : 0;
+                                                     linear_steady_workspace_bytes(dtype, B, D, O, T) + 256 +
+                                                     (lin_lag_applicable(dtype, D, O, 1, T)
+                                                          ? lin_lag_workspace_bytes(dtype, n_blocks, B, O, T) : 0) : 0;
     return a1 > a2 ? a1 : a2;
 }
 

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "ekf_generic.cuh"
 #include "generic.cuh"
+#include "lin_lag.cuh"
 #include "../../include/eks_b200.h"
 #include <cstdio>
 #include <vector>
@@ -913,6 +914,18 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
                                                     (a.ncam == 0 ? linear_steady_workspace_bytes(dtype, a.B, a.D, a.O, a.T) : 0),
                 "optimize_s: workspace too small for the run-parallel generic path");
     unsigned char* w = (unsigned char*)workspace;
+    // Linear model with A = I, one span, long sequence: lag-statistics optimiser (lin_lag.cu) -- one pass over the
+    // observations and one persistent launch; its scratch lies behind the run-parallel path's, which stays the
+    // fallback for blocks where the closed form does not apply.
+    if (a.ncam == 0 && !g.probe && lin_lag_applicable(dtype, a.D, a.O, a.sp.n, n)) {
+        const size_t front = ((generic_runs_optimize_workspace_bytes(dtype, a.n_blocks, a.B, a.D, a.T) +
+                               linear_steady_workspace_bytes(dtype, a.B, a.D, a.O, a.T)) + 255) / 256 * 256;
+        if (workspace_bytes > front) {
+            int used = 0;
+            if (int rc = lin_lag_optimize<P>(a, w + front, workspace_bytes - front, st, &used)) return rc;
+            if (used) return 0;
+        }
+    }
     auto take = [&](size_t bytes) { unsigned char* p = w; w += (bytes + 255) / 256 * 256; return p; };
     g.bstate = (RunBlockState<P>*)take((size_t)a.n_blocks * 128);
     g.warm = (int*)take((size_t)a.B * sizeof(int));

@@ -189,8 +189,9 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                ptr(s_log0), float(lr), float(s_bounds_log[0]), float(s_bounds_log[1]), float(tol),
                                int(safety_cap), ptr(s_log), ptr(loss), ptr(iters), ptr(trace), int(trace_cap),
                                int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
-    _count(int(lib().eks_last_launch_count()))   # the library reports what this call enqueued
-    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace,
+    launches = int(lib().eks_last_launch_count())   # the library reports what this call enqueued
+    _count(launches)
+    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, launches=launches,
                 blocks=blocks if blocks is not None else [[k] for k in range(B)], _keep=(d_boff, d_mem, ws))
 
 

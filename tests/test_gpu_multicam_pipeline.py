@@ -240,3 +240,36 @@ def test_geometric_init_on_device_matches_oracle(T):
     np.testing.assert_allclose(m0.cpu().numpy(), m0s, rtol=1e-13)
     np.testing.assert_allclose(S0d.cpu().numpy(), np.diagonal(S0s, axis1=1, axis2=2), rtol=1e-11)
     np.testing.assert_allclose(Qd.cpu().numpy(), np.diagonal(Qs, axis1=1, axis2=2), rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize('V,dtype,T', [(2, torch.float64, 3000), (3, torch.float64, 2500), (4, torch.float64, 2400),
+                                       (2, torch.float32, 30_000)])
+def test_lag_statistics_optimiser_equals_run_parallel_path(V, dtype, T, monkeypatch):
+    """lin_lag.cu (one pass over the observations: O x O x W lag statistics of the stationary signal + closed-form NLL
+    in a persistent Adam kernel) against the run-parallel evaluation of generic_runs.cu on the same data: same
+    iteration counts and, iterate by iterate, the same loss / gradient (float64: to 1e-9 relative)."""
+    from eks_b200.pipeline import multicam_smooth_sessions
+    raw = synth_multicam(M=4, V=V, K=3, T=T, seed=40 + V)
+    x = torch.as_tensor(raw).cuda()[None].to(dtype)
+    monkeypatch.setenv('EKS_NO_LINLAG', '1')
+    # float32 mode is checked against the float64 run-parallel evaluation of the same (float32-exact) data
+    ref = multicam_smooth_sessions(x.double(), dtype=torch.float64, trace_cap=300)
+    tr_ref = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
+    monkeypatch.delenv('EKS_NO_LINLAG')
+    monkeypatch.setenv('EKS_DEBUG_RUNS', '1')
+    res = multicam_smooth_sessions(x, dtype=dtype, trace_cap=300)
+    tr = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
+    assert multicam_smooth_sessions.last_opt['launches'] == 4, \
+        'the lag-statistics path did not run (fell back to the run-parallel path)'
+    it, it_ref = res.iters[0].cpu().numpy(), ref.iters[0].cpu().numpy()
+    if dtype == torch.float64:
+        np.testing.assert_array_equal(it, it_ref)
+        for k in range(raw.shape[3]):
+            n = it[k]
+            np.testing.assert_allclose(tr[k, :n, 1], tr_ref[k, :n, 1], rtol=1e-9)
+            np.testing.assert_allclose(tr[k, :n, 2], tr_ref[k, :n, 2], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(res.s_finals.cpu().numpy(), ref.s_finals.cpu().numpy(), rtol=1e-8)
+    else:   # float32 mode: the lag path evaluates the float32 data and model in float64 arithmetic
+        from parity import fp32_stop_protocol
+        for k in range(raw.shape[3]):
+            fp32_stop_protocol(f'lag (float32) vs runs (float64) kp{k}', tr[k], it[k], tr_ref[k], it_ref[k])
