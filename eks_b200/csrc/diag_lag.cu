@@ -35,7 +35,10 @@ namespace eks {
 constexpr int LAG_T0 = 256;     // frames [0, T0) are filtered sequentially in an evaluation; statistics start after
 constexpr int LAG_NT0 = 3;      // statistics are kept for T0 = 256, 128, 64 (lag_reduce_kernel); the evaluation picks
 constexpr int LAG_CH = 4096;    // increments per shared-memory tile of lag_stats_kernel
-constexpr int LAG_RM = 16;      // lags per thread (register tile)
+constexpr int LAG_RM = 16;      // lags per thread (register tile), float64; float32 uses LAG_RM32
+constexpr int LAG_RM32 = 32;    // float32: 16 frames x 32 lags per step = 16 16-byte shared loads per 512 FMAs (16 x 16: 12 per
+                                // 256, measured shared-memory bound at 54 % of the FMA pipe)
+constexpr int LAG_NPART_MAX = 2;   // warps sharing one lag group split the tile's steps between them
 constexpr int LAG_RP = 16;      // frames per thread and step (register tile)
 constexpr int LAG_NT = 256;
 constexpr int LAG_CPB = 8;      // tiles per CTA (accumulated in registers before the partial sums are written)
@@ -63,84 +66,103 @@ __device__ __forceinline__ int lag_phys(int x) { return x + (x >> 4) * (16 / (in
 // from 12 16-byte shared loads.  float32 mode: products and the <= 128-term partial sums per tile in float32, promoted
 // to float64 per tile (error of a partial ~1e-6 relative, of the 10^6-frame sum ~1e-8; the data are float32 anyway).
 template <class P, int W>
-__global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 3 : 1) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
+__global__ void __launch_bounds__(LAG_NT, sizeof(P) == 4 ? 2 : 1) lag_stats_kernel(const __grid_constant__ LagStatArgs<P> a) {
     constexpr int PADE = 16 / (int)sizeof(P);
     constexpr int NLOG = LAG_CH + W;
     constexpr int NPHYS = NLOG + (NLOG / 16) * PADE + PADE;
-    constexpr int NG = W / LAG_RM;          // lag groups
-    constexpr int GPW = (NG + 7) / 8;       // lag groups per warp
+    constexpr int RM = sizeof(P) == 4 ? LAG_RM32 : LAG_RM;   // lags per thread
+    constexpr int NG = W / RM;              // lag groups
+    constexpr int NW = LAG_NT / 32;
+    constexpr int GPW = (NG + NW - 1) / NW; // lag groups per warp (NG >= 8)
+    constexpr int NPART = NG < NW ? NW / NG : 1;   // warps per lag group (NG < 8): they interleave the steps of a tile
+    static_assert(NPART <= LAG_NPART_MAX && (NG >= NW || NW % NG == 0), "lag tile geometry");
     constexpr int VW = LagVec<P>::VW;
     using V = typename LagVec<P>::type;
     __shared__ __align__(16) P sm[NPHYS];
     const int bc = blockIdx.y, b = bc >> 1, c = bc & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int part = NPART > 1 ? warp / NG : 0;
     const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
-    double accd[GPW][LAG_RM];
+    double accd[GPW][RM];
 #pragma unroll
     for (int q = 0; q < GPW; ++q)
 #pragma unroll
-        for (int j = 0; j < LAG_RM; ++j) accd[q][j] = 0.0;
+        for (int j = 0; j < RM; ++j) accd[q][j] = 0.0;
     for (int chunk = blockIdx.x; chunk < a.nchunk; chunk += a.nx) {
         const int i0 = LAG_T0 + 1 + chunk * LAG_CH;
         __syncthreads();   // the previous tile has been consumed
-        for (int x = threadIdx.x; x < NLOG; x += LAG_NT) {
-            const int i = i0 + x;
-            P d = P(0);
-            if (i < a.n) d = __ldg(yc + i) - __ldg(yc + i - 1);
-            sm[lag_phys<P>(x)] = d;
+        {   // staging: every load of the tile is issued before the first use (a rolled loop exposed one DRAM latency per
+            // element: ncu long_scoreboard 27 % of the stalls); the left neighbour comes from the previous lane
+            constexpr int U = (NLOG + LAG_NT - 1) / LAG_NT;
+            P cur[U], left[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + threadIdx.x + u * LAG_NT;
+                cur[u] = (i < a.n) ? __ldg(yc + i) : P(0);
+                left[u] = (lane == 0 && i < a.n) ? __ldg(yc + i - 1) : P(0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = threadIdx.x + u * LAG_NT;
+                const int i = i0 + x;
+                const P up = __shfl_up_sync(0xffffffffu, cur[u], 1);
+                const P prev = lane == 0 ? left[u] : up;
+                if (x < NLOG) sm[lag_phys<P>(x)] = (i < a.n) ? cur[u] - prev : P(0);
+            }
         }
         __syncthreads();
         const int nvalid = min(LAG_CH, a.n - i0);   // increments of this tile that exist
 #pragma unroll
         for (int q = 0; q < GPW; ++q) {
-            const int g = warp + 8 * q;
+            const int g = NPART > 1 ? warp % NG : warp + NW * q;
             if (g >= NG) break;
-            const int m0 = g * LAG_RM;
-            P acc[LAG_RM];
+            const int m0 = g * RM;
+            P acc[RM];
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) acc[j] = P(0);
-            for (int step = 0; step < LAG_CH / (32 * LAG_RP); ++step) {
+            for (int j = 0; j < RM; ++j) acc[j] = P(0);
+            for (int step = part; step < LAG_CH / (32 * LAG_RP); step += NPART) {
                 const int p = (step * 32 + lane) * LAG_RP;
                 if (step * 32 * LAG_RP >= nvalid) break;      // warp-uniform: nothing left in this tile
-                P av[LAG_RP], bv[LAG_RP + LAG_RM];
+                P av[LAG_RP], bv[LAG_RP + RM];
                 const P* pa = sm + lag_phys<P>(p);
-                const P* pb0 = sm + lag_phys<P>(p + m0);
-                const P* pb1 = sm + lag_phys<P>(p + m0 + 16);
 #pragma unroll
                 for (int i = 0; i < LAG_RP / VW; ++i) {
                     const V v = *reinterpret_cast<const V*>(pa + i * VW);
-                    const V w0 = *reinterpret_cast<const V*>(pb0 + i * VW);
-                    const V w1 = *reinterpret_cast<const V*>(pb1 + i * VW);
                     const P* ev = reinterpret_cast<const P*>(&v);
-                    const P* e0 = reinterpret_cast<const P*>(&w0);
-                    const P* e1 = reinterpret_cast<const P*>(&w1);
 #pragma unroll
-                    for (int k = 0; k < VW; ++k) {
-                        av[i * VW + k] = ev[k];
-                        bv[i * VW + k] = e0[k];
-                        bv[16 + i * VW + k] = e1[k];
+                    for (int k = 0; k < VW; ++k) av[i * VW + k] = ev[k];
+                }
+#pragma unroll
+                for (int blk = 0; blk < (LAG_RP + RM) / 16; ++blk) {     // the lag window, 16 elements (one padded run) at a time
+                    const P* pb = sm + lag_phys<P>(p + m0 + 16 * blk);
+#pragma unroll
+                    for (int i = 0; i < 16 / VW; ++i) {
+                        const V w0 = *reinterpret_cast<const V*>(pb + i * VW);
+                        const P* e0 = reinterpret_cast<const P*>(&w0);
+#pragma unroll
+                        for (int k = 0; k < VW; ++k) bv[16 * blk + i * VW + k] = e0[k];
                     }
                 }
-                // (a packed-FFMA2 version of this tile -- even / odd frames as the two lanes, shifted copy of the window for
-                // the odd lags -- was measured SLOWER: 688 vs 542 us per 80 channel-planes; 12 16-byte shared loads per
-                // 128 FFMA2 make it shared-memory bound, and 114 registers cost a resident CTA)
+                // (a packed-FFMA2 version of the 16 x 16 tile -- even / odd frames as the two lanes, shifted copy of the
+                // window for the odd lags -- was measured SLOWER: 688 vs 542 us per 80 channel-planes; shared-memory bound)
 #pragma unroll
                 for (int i = 0; i < LAG_RP; ++i)
 #pragma unroll
-                    for (int j = 0; j < LAG_RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
+                    for (int j = 0; j < RM; ++j) acc[j] = fma(av[i], bv[i + j], acc[j]);
             }
 #pragma unroll
-            for (int j = 0; j < LAG_RM; ++j) accd[q][j] += (double)acc[j];
+            for (int j = 0; j < RM; ++j) accd[q][j] += (double)acc[j];
         }
     }
 #pragma unroll
     for (int q = 0; q < GPW; ++q) {
-        const int g = warp + 8 * q;
+        const int g = NPART > 1 ? warp % NG : warp + NW * q;
         if (g >= NG) break;
 #pragma unroll
-        for (int j = 0; j < LAG_RM; ++j) {
+        for (int j = 0; j < RM; ++j) {
             const double v = warp_sum(accd[q][j]);
-            if (lane == 0) a.partial[((long long)bc * a.nx + blockIdx.x) * W + g * LAG_RM + j] = v;
+            if (lane == 0)
+                a.partial[(((long long)bc * a.nx + blockIdx.x) * LAG_NPART_MAX + part) * W + g * RM + j] = v;
         }
     }
 }
@@ -156,7 +178,7 @@ __global__ void lag_reduce_kernel(const __grid_constant__ LagStatArgs<P> a) {
     const long long bc = idx / W;
     const int m = (int)(idx - bc * W);
     double s = 0;
-    for (int x = 0; x < a.nx; ++x) s += a.partial[(bc * a.nx + x) * W + m];
+    for (int x = 0; x < a.nx * LAG_NPART_MAX; ++x) s += a.partial[(bc * a.nx * LAG_NPART_MAX + x) * W + m];   // unused slots are zero
     a.R[idx] = s;
     const int b = (int)(bc >> 1), c = (int)(bc & 1);
     const P* yc = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin + a.y.chan_off[c];
@@ -486,7 +508,7 @@ size_t diag_lag_workspace_bytes(int dtype, int n_blocks, int B, int T) {
     const int nx = (nchunk + LAG_CPB - 1) / LAG_CPB;
     size_t bytes = diag_optimize_workspace_bytes(dtype, n_blocks, B, T);
     bytes += (size_t)LAG_NT0 * B * 2 * W * sizeof(double) + 256;
-    bytes += (size_t)B * 2 * nx * W * sizeof(double) + 256;
+    bytes += (size_t)B * 2 * nx * LAG_NPART_MAX * W * sizeof(double) + 256;
     return bytes;
 }
 
@@ -519,6 +541,7 @@ static int diag_lag_run(DiagOptArgs<P>& a, void* workspace, size_t workspace_byt
         sa.nx = (sa.nchunk + LAG_CPB - 1) / LAG_CPB;
         sa.partial = (double*)w;
         sa.R = R;
+        cudaMemsetAsync(sa.partial, 0, (size_t)a.B * 2 * sa.nx * LAG_NPART_MAX * W * sizeof(double), st);
         lag_stats_kernel<P, W><<<dim3(sa.nx, 2 * a.B), LAG_NT, 0, st>>>(sa);
         int rc = check_launch("lag_stats_kernel");
         if (rc) return rc;

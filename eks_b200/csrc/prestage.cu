@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(256) med_count_kernel(PlaneView var, int O, Sp
                                                         typename KeyT<P>::type* __restrict__ cand) {
     using KT = KeyT<P>;
     using key_t = typename KT::type;
-    constexpr int LCAP = 16;                 // candidates a thread can hold (its 64 frames contain ~5 on average)
+    // candidates a thread can hold: its 64 frames contain Poisson(~5.3) of them.  16 overflowed in ~2e-5 of the threads,
+    // i.e. in ~25 % of the 10^6-frame problems (15 600 threads each), which then took the three-pass fallback (ncu launch
+    // list of round 2: select_hist / select_scan doing real work); with 24 the overflow probability per problem is < 1e-5
+    constexpr int LCAP = 24;
     __shared__ key_t buf[MED_SCAP];
     __shared__ int wsum[8];
     __shared__ int sh_base, sh_fail;
