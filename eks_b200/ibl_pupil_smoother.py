@@ -168,5 +168,6 @@ def fit_eks_pupil(input_source, save_file: str, smooth_params: list | None = Non
     df, s = ensemble_kalman_smoother_ibl_pupil(marker_array, bodypart_list, smooth_params=smooth_params,
                                                s_frames=s_frames, avg_mode=avg_mode, var_mode=var_mode)
     os.makedirs(os.path.dirname(save_file), exist_ok=True)
-    df.to_csv(save_file)
+    from eks_b200.io import write_dlc_csv
+    write_dlc_csv(df, save_file)
     return df, s, input_dfs_list, bodypart_list

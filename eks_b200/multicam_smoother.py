@@ -27,6 +27,7 @@ import torch
 from eks_b200 import _xfer, core, ops
 from eks_b200._lib import require_cuda
 from eks_b200.core import PinholeProjection, ensemble, run_kalman_smoother
+from eks_b200.io import write_dlc_csv
 from eks_b200.marker_array import MarkerArray, input_dfs_to_markerArray, mA_to_stacked_array, stacked_array_to_mA
 from eks_b200.stats import compute_mahalanobis, compute_pca
 from eks_b200.utils import center_predictions, make_dlc_pandas_index
@@ -450,9 +451,9 @@ def fit_eks_multicam(input_source, save_dir: str, bodypart_list: list | None = N
         var_mode=var_mode, inflate_vars=inflate_vars, n_latent=n_latent, camgroup=camgroup)
     os.makedirs(save_dir, exist_ok=True)
     for c, name in enumerate(camera_names):
-        camera_dfs[c].to_csv(os.path.join(save_dir, f'multicam_{name}_results.csv'))
+        write_dlc_csv(camera_dfs[c], os.path.join(save_dir, f'multicam_{name}_results.csv'))
     if save_3d_outputs and calibration is not None:
-        df_3d.to_csv(os.path.join(save_dir, 'multicam_3d_results.csv'))
+        write_dlc_csv(df_3d, os.path.join(save_dir, 'multicam_3d_results.csv'))
     return camera_dfs, s_finals, input_dfs_list, bodypart_list, df_3d
 
 
@@ -488,5 +489,5 @@ def fit_eks_mirrored_multicam(input_source, save_file: str, bodypart_list: list 
         parts.append(cdf)
     final_df = pd.concat(parts, axis=1)
     os.makedirs(os.path.dirname(save_file), exist_ok=True)
-    final_df.to_csv(save_file)
+    write_dlc_csv(final_df, save_file)
     return final_df, s_finals, input_dfs_list, bodypart_list

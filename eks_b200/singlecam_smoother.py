@@ -49,7 +49,8 @@ def fit_eks_singlecam(
         blocks=blocks, avg_mode=avg_mode, var_mode=var_mode,
     )
     os.makedirs(os.path.dirname(save_file), exist_ok=True)
-    df_smoothed.to_csv(save_file)
+    from eks_b200.io import write_dlc_csv
+    write_dlc_csv(df_smoothed, save_file)
     logger.info('dataframes successfully converted to CSV')
     return df_smoothed, smooth_params_final, input_dfs_list, bodypart_list
 
