@@ -350,8 +350,14 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # one rank per GPU: run on the CPUs of the GPU's NUMA node so that the pinned host buffers of the e2e leg are local
+    from eks_b200.parallel import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {'node': None, 'why': 'single rank: not bound'}
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, numa)
+        numa = gathered                      # every rank's binding, in rank order
     w = workload_of(args)
     kind, M, V, K, T, S = w['kind'], w['M'], w['V'], w['K'], w['T'], w['S']
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
@@ -594,7 +600,8 @@ def run_b200(args):
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': cfg,
-        'e2e': e2e, 'e2e_public': e2e_public, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+        'e2e': e2e, 'e2e_public': e2e_public, 'gpu_launches': launches, 'clocks': clocks, 'numa': numa,
+        'roofline': roofline,
         'kernels': kernels,
         'pipeline_one_touch': {'bytes_per_kf': b_alg, 'frac_of_hbm_peak': pipeline_frac,
                                'achieved_gbs': kf_step * b_alg / (ms_step * 1e-3) / 1e9},

@@ -34,22 +34,40 @@ EKS_HD void project_cam_jac(const P* __restrict__ cam, const S* X, S* uv, S* J /
     const S iz = S(P(1)) / Xc[2];
     const S x = Xc[0] * iz, y = Xc[1] * iz;
     const S r2 = x * x + y * y;
-    const S r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r6 * r6;
-    const S radial = S(P(1)) + S(k1) * r2 + S(k2) * r4 + S(k3) * r6 + S(k4) * r8 + S(k5) * r10 + S(k6) * r12;
-    // d radial / d r2
-    const S drad = S(k1) + S(P(2) * k2) * r2 + S(P(3) * k3) * r4 + S(P(4) * k4) * r6 + S(P(5) * k5) * r8 +
-                   S(P(6) * k6) * r10;
-    const S xd = x * radial + S(P(2) * p1) * x * y + S(p2) * (r2 + S(P(2)) * x * x) + S(s1) * r2 + S(s2) * r4;
-    const S yd = y * radial + S(p1) * (r2 + S(P(2)) * y * y) + S(P(2) * p2) * x * y + S(s3) * r2 + S(s4) * r4;
-    uv[0] = S(fx) * xd + S(skew) * yd + S(cx);
-    uv[1] = S(fy) * yd + S(cy);
     const S two_x = x + x, two_y = y + y;
-    const S tpx = S(s1) + S(P(2) * s2) * r2, tpy = S(s3) + S(P(2) * s4) * r2;  // d thin-prism / d r2
-    // d(xd,yd)/d(x,y)
-    const S dxd_dx = radial + x * drad * two_x + S(P(2) * p1) * y + S(P(6) * p2) * x + tpx * two_x;
-    const S dxd_dy = x * drad * two_y + S(P(2) * p1) * x + S(P(2) * p2) * y + tpx * two_y;
-    const S dyd_dx = y * drad * two_x + S(P(2) * p1) * x + S(P(2) * p2) * y + tpy * two_x;
-    const S dyd_dy = radial + y * drad * two_y + S(P(6) * p1) * y + S(P(2) * p2) * x + tpy * two_y;
+    S dxd_dx, dxd_dy, dyd_dx, dyd_dy;
+    // Anipose calibrates k1 only by default: every other coefficient is exactly zero.  Their terms then add exact
+    // zeros (0 * finite = 0, a + 0 = a), so skipping them is bit-identical for finite inputs and removes ~45 % of the
+    // projection's arithmetic (the test is uniform across the warp: the cameras are shared by all sequences).
+    const bool k1_only = k2 == P(0) && k3 == P(0) && k4 == P(0) && k5 == P(0) && k6 == P(0) && p1 == P(0) &&
+                         p2 == P(0) && s1 == P(0) && s2 == P(0) && s3 == P(0) && s4 == P(0);
+    if (k1_only) {
+        const S radial = S(P(1)) + S(k1) * r2;
+        const S drad = S(k1);
+        const S xd = x * radial, yd = y * radial;
+        uv[0] = S(fx) * xd + S(skew) * yd + S(cx);
+        uv[1] = S(fy) * yd + S(cy);
+        dxd_dx = radial + x * drad * two_x;
+        dxd_dy = x * drad * two_y;
+        dyd_dx = y * drad * two_x;
+        dyd_dy = radial + y * drad * two_y;
+    } else {
+        const S r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r6 * r6;
+        const S radial = S(P(1)) + S(k1) * r2 + S(k2) * r4 + S(k3) * r6 + S(k4) * r8 + S(k5) * r10 + S(k6) * r12;
+        // d radial / d r2
+        const S drad = S(k1) + S(P(2) * k2) * r2 + S(P(3) * k3) * r4 + S(P(4) * k4) * r6 + S(P(5) * k5) * r8 +
+                       S(P(6) * k6) * r10;
+        const S xd = x * radial + S(P(2) * p1) * x * y + S(p2) * (r2 + S(P(2)) * x * x) + S(s1) * r2 + S(s2) * r4;
+        const S yd = y * radial + S(p1) * (r2 + S(P(2)) * y * y) + S(P(2) * p2) * x * y + S(s3) * r2 + S(s4) * r4;
+        uv[0] = S(fx) * xd + S(skew) * yd + S(cx);
+        uv[1] = S(fy) * yd + S(cy);
+        const S tpx = S(s1) + S(P(2) * s2) * r2, tpy = S(s3) + S(P(2) * s4) * r2;  // d thin-prism / d r2
+        // d(xd,yd)/d(x,y)
+        dxd_dx = radial + x * drad * two_x + S(P(2) * p1) * y + S(P(6) * p2) * x + tpx * two_x;
+        dxd_dy = x * drad * two_y + S(P(2) * p1) * x + S(P(2) * p2) * y + tpx * two_y;
+        dyd_dx = y * drad * two_x + S(P(2) * p1) * x + S(P(2) * p2) * y + tpy * two_x;
+        dyd_dy = radial + y * drad * two_y + S(P(6) * p1) * y + S(P(2) * p2) * x + tpy * two_y;
+    }
     // d(u,v)/d(x,y)
     const S du_dx = S(fx) * dxd_dx + S(skew) * dyd_dx, du_dy = S(fx) * dxd_dy + S(skew) * dyd_dy;
     const S dv_dx = S(fy) * dyd_dx, dv_dy = S(fy) * dyd_dy;
