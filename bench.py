@@ -409,6 +409,7 @@ def run_b200(args):
     # per-stage device times: a SEPARATE serial pass after the timed region (per-stage CUDA events need the stages of
     # all sessions in ONE stream; the timed steps above run session groups on several streams so that stages overlap,
     # which is why the stage times sum to more than ms_per_step)
+    step(raw, out, {})      # untimed: the serial pass has its own workspace sizes (first use = cudaMalloc inside a stage)
     for _ in range(2):
         if flush is not None:
             flush.fill_(1)

@@ -33,7 +33,7 @@
 namespace eks {
 
 constexpr int LAG_T0 = 256;     // frames [0, T0) are filtered sequentially in an evaluation; statistics start after
-constexpr int LAG_NT0 = 3;      // statistics are kept for T0 = 256, 128, 64 (lag_reduce_kernel); the evaluation picks
+constexpr int LAG_NT0 = 5;      // statistics are kept for T0 = 256, 128, 64, 32, 16 (lag_reduce_kernel); the evaluation picks
 constexpr int LAG_CH = 4096;    // increments per shared-memory tile of lag_stats_kernel
 constexpr int LAG_RM = 16;      // lags per thread (register tile), float64; float32 uses LAG_RM32
 constexpr int LAG_RM32 = 32;    // float32: 16 frames x 32 lags per step = 16 16-byte shared loads per 512 FMAs (16 x 16: 12 per

@@ -120,7 +120,8 @@ struct Dims {
 // relative); the loss path (constant R >= 1e-4) keeps BOOST = false: its effect there is O(eps / S) on the NLL.
 template <class S, class P, int DC, int OC, bool FIXED, bool NL, bool BOOST = false>
 EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, const P* yv, const P* rv, S s, S* m,
-                     S* Pm, S& nll, S* mf_out, S* Pf_out, const S* Adiag = nullptr, const S* Qdiag = nullptr) {
+                     S* Pm, S& nll, S* mf_out, S* Pf_out, const S* Adiag = nullptr, const S* Qdiag = nullptr,
+                     bool a_identity = false) {
     const int D = dm.D(), O = dm.O();
     S Mb[BOOST ? DC * DC : 1];   // H^T R'^-2 H
     if (BOOST) {
@@ -261,6 +262,13 @@ EKS_HD bool ekf_step(const Dims<DC, OC, FIXED>& dm, const SeqModel<P>& mdl, cons
                     if (j < D) Pm[i * D + j] = Adiag[i] * Pm[i * D + j] * Adiag[j] + (i == j ? Qdiag[i] : S(P(0)));
             }
         }
+        return ok;
+    }
+    if (a_identity) {   // A = I (every multi-camera model of the reference): A m_f = m_f and A P A^T = P, bit for bit
+#pragma unroll
+        for (int i = 0; i < DC; ++i) if (i < D) m[i] = mf[i];
+#pragma unroll
+        for (int i = 0; i < DC * DC; ++i) if (i < D * D) Pm[i] = Pm[i] + s * S(mdl.Q[i]);
         return ok;
     }
     S AP[DC * DC];
