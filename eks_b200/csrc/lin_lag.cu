@@ -15,8 +15,9 @@
 // computes Rg in one streaming pass; lin_lag_opt_kernel then runs the WHOLE Adam loop of a block in one warp: per
 // evaluation the exact filter (sequential scalar updates, covariance recursion with its s-sensitivity in forward duals)
 // over the first T0 frames, the steady-state algebra in Dual<double>, the Adam step and the reference's stop rule.
-// K and N are assembled from the SAME sequential-scalar-update gains the run-parallel path uses (lin_cov_step in
-// generic_runs.cu): with M[g][j] = h_g . k_j (j < g) and Wm = (I + M)^-1, K = [k_0 .. k_{O-1}] Wm, N = Wm^T diag(1/s_g) Wm.
+// The head filter and the steady-state gain use the information form of the update (R diagonal and constant:
+// P+ = (P^-1 + C^T R^-1 C)^-1, K = P+ C^T R^-1, N = R^-1 - R^-1 C P+ C^T R^-1): the same numbers as the sequential scalar
+// updates of the run-parallel path up to float64 rounding.
 //
 // The closed form is used only when it is exact to rounding: A = I, one contiguous span, n >= T0 + 4 W, the covariance
 // recursion converged within T0 = 256 frames, and |Phi^W| below 1e-7 (float32 mode, W = 128) / 1e-13 (float64 mode,
@@ -309,58 +310,75 @@ __device__ bool linlag_eval(const GArgs<P>& a, const LinLagArgs& la, int b, doub
     for (int i = 0; i < D * D; ++i) Pm[i] = SD((double)a.S0[(long long)b * D * D + i]);
 #pragma unroll
     for (int i = 0; i < D; ++i) mu[i] = SD((double)a.m0[(long long)b * D + i]);
-    SD kg[O * D], isi[O], lsum(0.0), nll(0.0);
-    bool bad = false;
-
-    // one covariance step (sequential scalar updates on the predicted covariance, symmetrise, + s Q): gains -> kg, isi
-    auto cov_step = [&]() {
-        lsum = SD(0.0);
+    SD lsum(0.0), nll(0.0);
+    bool bad = false, singular = false;
+    // INFORMATION FORM of the measurement update (R is diagonal and constant): with J = C^T R^-1 C,
+    //     P+ = (P^-1 + J)^-1,   K = P+ C^T R^-1,   log det S = sum log r_g + log(det P det(P^-1 + J)),
+    //     e^T S^-1 e = e^T R^-1 e - z^T P+ z,  z = C^T R^-1 e                       (Woodbury / determinant lemma)
+    // -- two symmetric 3 x 3 inverses per frame instead of O rank-one updates (O divisions, O logarithms): the same
+    // numbers as the sequential scalar updates of ekf_step up to float64 rounding, at half the dependent instructions
+    // (this loop is the critical path of the optimiser: one warp per sequence, ~45 frames per evaluation).
+    double Jm[D * D], CtRi[D * O], ri[O], sumlogr = 0.0;
 #pragma unroll
-        for (int g = 0; g < O; ++g) {
-            SD Ph[D];
+    for (int g = 0; g < O; ++g) { ri[g] = 1.0 / rc[g]; sumlogr += log(rc[g]); if (!(rc[g] > 0.0)) bad = true; }
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                SD acc(0.0);
+    for (int i = 0; i < D; ++i) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) acc += ml_scale(Cm[g * D + j], Pm[i * D + j]);
-                Ph[i] = acc;
-            }
-            SD si(rc[g]);
+        for (int g = 0; g < O; ++g) CtRi[i * O + g] = Cm[g * D + i] * ri[g];
 #pragma unroll
-            for (int j = 0; j < D; ++j) si += ml_scale(Cm[g * D + j], Ph[j]);
-            if (!(si.v > 0) || !isfinite(si.v)) bad = true;
-            const SD inv = SD(1.0) / si;
-            lsum += log_(si);
-            isi[g] = inv;
+        for (int j = 0; j < D; ++j) {
+            double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                const SD k = Ph[i] * inv;
-                kg[g * D + i] = k;
-#pragma unroll
-                for (int j = 0; j < D; ++j) Pm[i * D + j] -= k * Ph[j];
-            }
+            for (int g = 0; g < O; ++g) acc += Cm[g * D + i] * ri[g] * Cm[g * D + j];
+            Jm[i * D + j] = acc;
         }
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = i + 1; j < D; ++j) {
-                const SD v = ml_scale(0.5, Pm[i * D + j] + Pm[j * D + i]);
-                Pm[i * D + j] = v; Pm[j * D + i] = v;
-            }
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) Pm[i] = Pm[i] + ml_scale(Qm[i], s);
+    }
+    SD Pp[D * D];          // filtered covariance P+ of the current frame
+    // symmetric 3 x 3 inverse by cofactors; returns the determinant
+    auto inv3 = [](const SD* A, SD* Inv) {
+        const SD c00 = A[4] * A[8] - A[5] * A[5], c01 = A[2] * A[5] - A[1] * A[8], c02 = A[1] * A[5] - A[2] * A[4];
+        const SD c11 = A[0] * A[8] - A[2] * A[2], c12 = A[1] * A[2] - A[0] * A[5], c22 = A[0] * A[4] - A[1] * A[1];
+        const SD det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+        const SD id = SD(1.0) / det;
+        Inv[0] = c00 * id; Inv[1] = c01 * id; Inv[2] = c02 * id;
+        Inv[3] = Inv[1];   Inv[4] = c11 * id; Inv[5] = c12 * id;
+        Inv[6] = Inv[2];   Inv[7] = Inv[5];   Inv[8] = c22 * id;
+        return det;
     };
-    // the observations of frame t through the current gains: NLL terms and the mean update
+    // one covariance step: Pm (predicted) -> Pp (filtered), lsum = log det S; then Pm <- Pp + s Q
+    auto cov_step = [&]() {
+        SD Lam[D * D];
+        const SD detP = inv3(Pm, Lam);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Lam[i] = Lam[i] + SD(Jm[i]);
+        const SD detL = inv3(Lam, Pp);
+        const SD dd = detP * detL;                         // det(I + P J) = det S / det R
+        if (!(detP.v > 0) || !(dd.v > 0) || !isfinite(dd.v)) singular = true;   // (near-)singular P: not for this form
+        lsum = SD(sumlogr) + log_(dd);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Pm[i] = Pp[i] + ml_scale(Qm[i], s);
+    };
+    // the observations of frame t through the current filtered covariance: NLL terms and the mean update
     auto obs_step = [&](int t) {
-        SD q(0.0);
+        SD z[D], q(0.0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = SD(0.0);
 #pragma unroll
         for (int g = 0; g < O; ++g) {
             SD e((double)__ldg(yb + a.y.chan_off[g] + t) - bs.ym[g]);
 #pragma unroll
             for (int j = 0; j < D; ++j) e -= ml_scale(Cm[g * D + j], mu[j]);
-            q += e * e * isi[g];
+            q += ml_scale(ri[g], e * e);
 #pragma unroll
-            for (int i = 0; i < D; ++i) mu[i] += kg[g * D + i] * e;
+            for (int i = 0; i < D; ++i) z[i] += ml_scale(CtRi[i * O + g], e);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            SD pz(0.0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) pz += Pp[i * D + j] * z[j];
+            q -= z[i] * pz;
+            mu[i] += pz;
         }
         nll += SD((double)O * HALF_LOG2PI) + ml_scale(0.5, lsum) + ml_scale(0.5, q);
     };
@@ -395,7 +413,7 @@ __device__ bool linlag_eval(const GArgs<P>& a, const LinLagArgs& la, int b, doub
         conv = (cvok && cdok) || stall >= 24;
         prev_cv = cv; prev_cd = cd;
     }
-    if (!conv) return false;
+    if (!conv || singular) return false;   // the run-parallel path (sequential scalar updates) handles these
     cov_step();                         // steady gains from the converged predicted covariance
     int lvl = ML_NT0 - 1;               // smallest statistics start frame >= the transient length
     while (lvl > 0 && ml_level_T0(lvl) < t) --lvl;
@@ -407,40 +425,24 @@ __device__ bool linlag_eval(const GArgs<P>& a, const LinLagArgs& la, int b, doub
     SD Phi[D * D], Bm[D * (E > 0 ? E : 1)], N11[D * D], N12[D * (E > 0 ? E : 1)], N22[(E > 0 ? E : 1) * (E > 0 ? E : 1)];
     SD e0h[D];
     {
-        SD Wm[O * O], Nn[O * O], Kj[D * O];
-#pragma unroll
-        for (int g = 0; g < O; ++g)
-#pragma unroll
-            for (int c = 0; c < O; ++c) {
-                SD acc(g == c ? 1.0 : 0.0);
-#pragma unroll
-                for (int j = 0; j < O; ++j) {
-                    if (j < g) {
-                        SD mgj(0.0);
-#pragma unroll
-                        for (int i = 0; i < D; ++i) mgj += ml_scale(Cm[g * D + i], kg[j * D + i]);
-                        acc -= mgj * Wm[j * O + c];
-                    }
-                }
-                Wm[g * O + c] = acc;
-            }
-#pragma unroll
-        for (int x = 0; x < O; ++x)
-#pragma unroll
-            for (int c = 0; c < O; ++c) {
-                SD acc(0.0);
-#pragma unroll
-                for (int g = 0; g < O; ++g) acc += Wm[g * O + x] * isi[g] * Wm[g * O + c];
-                Nn[x * O + c] = acc;
-            }
+        SD Nn[O * O], Kj[D * O];      // K = P+ C^T R^-1,  N = S^-1 = R^-1 - R^-1 C P+ C^T R^-1
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int c = 0; c < O; ++c) {
                 SD acc(0.0);
 #pragma unroll
-                for (int g = 0; g < O; ++g) acc += kg[g * D + i] * Wm[g * O + c];
+                for (int j = 0; j < D; ++j) acc += ml_scale(CtRi[j * O + c], Pp[i * D + j]);
                 Kj[i * O + c] = acc;
+            }
+#pragma unroll
+        for (int x = 0; x < O; ++x)
+#pragma unroll
+            for (int c = 0; c < O; ++c) {
+                SD acc(x == c ? ri[x] : 0.0);
+#pragma unroll
+                for (int i = 0; i < D; ++i) acc -= ml_scale(CtRi[i * O + x], Kj[i * O + c]);
+                Nn[x * O + c] = acc;
             }
         SD Kh[D * O];          // K U
 #pragma unroll
