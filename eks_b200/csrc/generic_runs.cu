@@ -25,7 +25,12 @@
 
 namespace eks {
 
-constexpr int RUNS_W0 = 64;       // initial warm-up length (frames)
+static int runs_w0() {            // initial warm-up length (frames); escalated x4 per failed boundary verification
+    static int w0 = 0;
+    if (w0 == 0) { const char* e = getenv("EKS_RUNS_W0"); w0 = e ? atoi(e) : 64; if (w0 < 4) w0 = 4; }
+    return w0;
+}
+#define RUNS_W0 (runs_w0())
 constexpr int RUNS_WMAX32 = 16384;  // fp32: beyond this warm-up a remaining boundary mismatch is rounding noise, not memory
 constexpr int RUNS_EXTRA = 12;
 constexpr int RUNS_RED_NT = 256;   // runs per CTA of the verification / reduction kernel    // extra evaluation slots for warm-up escalations (64 * 4^10 > 10^7 frames)
@@ -1125,7 +1130,7 @@ __global__ void __launch_bounds__(32) pupil_adam_kernel(const __grid_constant__ 
             st.prev = P(INFINITY);
             st.iters = 0; st.redo = 0;
             st.done = (a.cap <= 0);
-            a.warm[b] = RUNS_W0;
+            a.warm[b] = 64;
         }
         return;
     }
