@@ -240,16 +240,36 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
     const bool vec = ((reinterpret_cast<uintptr_t>(base + off0) & 15) == 0) && ((m_stride * (int)sizeof(Tin)) % 16 == 0);
     const int ngran = vec ? nel / EPG : 0;
     if (EXACT && vec && ngran * EPG == nel) {
-        // whole granules only (every full tile): the seed loop is unrolled and each thread issues its granule of every
-        // seed from ONE address computation (the per-seed loop with its bounds checks was 26 % of the kernel's
-        // instructions, ncu r2a)
-        const Tin* src = base + off0 + (long long)threadIdx.x * EPG;
-        unsigned char* dst = smem_raw + threadIdx.x * 16;
-        for (int g = threadIdx.x; g < ngran; g += blockDim.x, src += blockDim.x * EPG, dst += blockDim.x * 16) {
-            const Tin* sm_ = src;
-            unsigned char* dm = dst;
-#pragma unroll 2       // (fully unrolled, the ten address pairs cost 80 registers and two resident CTAs)
-            for (int m = 0; m < MAXM; ++m, sm_ += m_stride, dm += chunk_pad) ens_cp_async_16(dm, sm_);
+        // whole 16-byte granules (every full tile): each seed's chunk is ONE contiguous run in global memory, so the M
+        // chunks are brought in by M bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) issued by a
+        // single thread and completed on an mbarrier.  The per-granule cp.async loop this replaces was 13 % of the
+        // kernel's instructions (ncu r2: issue slots 83 % busy, the kernel was issue bound, not HBM bound).
+        __shared__ __align__(8) unsigned long long mbar;
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mb) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)nel * (unsigned)sizeof(Tin);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(bytes * (unsigned)MAXM)
+                         : "memory");
+            const Tin* src = base + off0;
+            unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
+#pragma unroll 1
+            for (int m = 0; m < MAXM; ++m, src += m_stride, dst += chunk_pad)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                             "l"(src), "r"(bytes), "r"(mb)
+                             : "memory");
+        }
+        {   // every thread waits for the phase (parity 0) to complete: the copied bytes are then visible to it
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done)
+                             : "r"(mb)
+                             : "memory");
         }
     } else {   // stage the M contiguous seed chunks: coalesced 16-byte cp.async, pointers advanced by constant strides
         const Tin* src = base + off0;
@@ -259,10 +279,10 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
             for (int e = ngran * EPG + threadIdx.x; e < nel; e += blockDim.x)
                 ens_cp_async_small<(int)sizeof(Tin)>(dst + e * sizeof(Tin), src + e);
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
     // one thread per cell (frame, keypoint): 3*M shared-memory reads at a constant stride
     const int ncell = nt * K;
     for (int e = threadIdx.x; e < ncell; e += blockDim.x) {
@@ -318,29 +338,34 @@ __global__ void __launch_bounds__(256) ensemble_staged_kernel(const Tin* __restr
         tp[4 * fs] = mean_conf;
     }
     __syncthreads();
-    // coalesced plane writes: frame fastest (TT is a power of two: no integer division)
-    P* obase = out + (long long)sess * eo.sess_stride + (long long)v * eo.cam_stride;
+    // coalesced plane writes: frame fastest (TT is a power of two: no integer division).  A thread owns fixed
+    // (keypoint, frame) slots and computes their addresses ONCE for the five planes (the per-plane loops with a 64-bit
+    // multiply per element were 21 % of the kernel's instructions).
+    P* obase = out + (long long)sess * eo.sess_stride + (long long)v * eo.cam_stride + t0;
+    const int fstride = K * ld;
+    for (int idx = threadIdx.x; idx < (K << log2TT); idx += blockDim.x) {
+        const int k = idx >> log2TT, tl = idx & (TT - 1);
+        if (tl < nt) {
+            P* o = obase + (long long)k * eo.kp_stride + tl;
+            const P* tsrc = tile + k * ld + tl;
 #pragma unroll
-    for (int f = 0; f < 5; ++f) {
-        P* of = obase + eo.plane_off[f] + t0;
-        const P* tf = tile + (size_t)f * K * ld;
-        for (int idx = threadIdx.x; idx < (K << log2TT); idx += blockDim.x) {
-            const int k = idx >> log2TT, tl = idx & (TT - 1);
-            if (tl < nt) of[(long long)k * eo.kp_stride + tl] = tf[k * ld + tl];
+            for (int f = 0; f < 5; ++f) o[eo.plane_off[f]] = tsrc[f * fstride];
         }
     }
     if (partials != nullptr) {
         // per-tile moments of the averaged coordinates: row = (coordinate, keypoint), LPR lanes per row with
         // 4 frames each, fixed xor tree inside the lane group (deterministic)
-        const int LPR = TT >> 2;                       // TT in {8,16,32,64} -> 2..16 lanes per row
-        const int rows_per_pass = blockDim.x / LPR;
+        const int log2LPR = log2TT - 2;                // TT in {8,16,32,64} -> 2..16 lanes per row (powers of two:
+        const int LPR = 1 << log2LPR;                  // shifts instead of the integer divisions, 12 % of the instructions)
+        const int log2RPP = 8 - log2LPR;               // blockDim.x == 256
+        const int rows_per_pass = 1 << log2RPP;
         const int q = threadIdx.x & (LPR - 1);
         const int ntiles = gridDim.x;
-        const int npass = (2 * K + rows_per_pass - 1) / rows_per_pass;
+        const int npass = (2 * K + rows_per_pass - 1) >> log2RPP;
         for (int ps = 0; ps < npass; ++ps) {
-            const int row = ps * rows_per_pass + threadIdx.x / LPR;
+            const int row = (ps << log2RPP) + (threadIdx.x >> log2LPR);
             const bool rv = row < 2 * K;
-            const int c = rv ? row / K : 0, k = rv ? row - c * K : 0;
+            const int c = (rv && row >= K) ? 1 : 0, k = rv ? row - c * K : 0;
             double sm = 0, sq = 0;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {

@@ -5,12 +5,24 @@ set -u
 TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 1 --warmup 1 --sessions 2 --no-e2e --no-cpu --no-public"
-# (1) every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/launches_$TAG.log 2>&1
+C5="python bench.py --steps 1 --warmup 1 --sessions 2 --no-e2e --no-cpu --no-public"
+C3="python bench.py --workload c3 --steps 1 --warmup 1 --no-e2e --no-cpu --no-public"
+C4="python bench.py --workload c4 --steps 1 --warmup 1 --no-e2e --no-cpu --no-public"
+KSEL='regex:eks::'
+# (1) every launch of the library with its device time (cold-cache, serialised: compare SHARES, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL --log-file $OUT/launches_${TAG}_c5.csv $C5 > $OUT/launches_${TAG}_c5.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL --log-file $OUT/launches_${TAG}_c3.csv $C3 > $OUT/launches_${TAG}_c3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL -c 400 --log-file $OUT/launches_${TAG}_c4.csv $C4 > $OUT/launches_${TAG}_c4.log 2>&1
 if [ "${2:-}" = "full" ]; then
-# (2) full captures, one launch of each kernel of the step (second step = after warm-up)
-for K in lag_stats diag_lag_opt ensemble_staged select_hist select_scan diag_filter diag_rts; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o $OUT/prof_${TAG}_$K $CMD > $OUT/prof_${TAG}_$K.log 2>&1
+# (2) full captures, one launch of each kernel of the step (after the warm-up step)
+for K in lag_stats diag_lag_opt ensemble_staged med_count med_final diag_smooth_fused; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o $OUT/prof_${TAG}_$K $C5 > $OUT/prof_${TAG}_$K.log 2>&1
+done
+for K in mlag_stats lin_lag_opt; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o $OUT/prof_${TAG}_$K $C3 > $OUT/prof_${TAG}_$K.log 2>&1
+done
+for K in gen_nll_runs triangulate_mean; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -o $OUT/prof_${TAG}_$K $C4 > $OUT/prof_${TAG}_$K.log 2>&1
 done
 fi
+ls -la $OUT | tail -30
