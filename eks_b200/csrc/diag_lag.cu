@@ -41,7 +41,8 @@ constexpr int LAG_RM32 = 32;    // float32: 16 frames x 32 lags per step = 16 16
 constexpr int LAG_NPART_MAX = 2;   // warps sharing one lag group split the tile's steps between them
 constexpr int LAG_RP = 16;      // frames per thread and step (register tile)
 constexpr int LAG_NT = 256;
-constexpr int LAG_CPB = 8;      // tiles per CTA (accumulated in registers before the partial sums are written)
+constexpr int LAG_CPB = 16;     // tiles per CTA (accumulated in registers before the partial sums are written; the final warp reduction
+                                // of a CTA was 5 % of the instructions at 8 tiles)
 
 template <class P>
 struct LagStatArgs {
