@@ -276,7 +276,9 @@ __device__ bool lag_prepare(const DiagOptArgs<P>& a, int b, int c, double s, con
     }
     if (!(alpha > 0.0) || !(alpha < 1.0) || !isfinite(alpha)) return false;
     // truncation of the lag series: |sum_{m >= W} 2 alpha^m R_m| <= 2 alpha^W / (1 - alpha) R_0
-    if (2.0 * exp((double)W * log(alpha)) > tolF * (1.0 - alpha)) return false;
+    double aW = alpha;                                           // alpha^W, W a power of two: log2(W) squarings
+    for (int w = W; w > 1; w >>= 1) aW *= aW;
+    if (2.0 * aW > tolF * (1.0 - alpha)) return false;
     sl += log(prodS);
     o.t_c = t;
     int lvl = LAG_NT0 - 1;                                      // smallest T0 of the table that is >= t_c
@@ -403,9 +405,15 @@ __global__ void __launch_bounds__(OPT_NT, 2) diag_lag_opt_kernel(const __grid_co
                                   a.y.chan_off[cq];
                     const int T0q = __shfl_sync(0xffffffffu, lp.T0, q), lvq = __shfl_sync(0xffffffffu, lp.lvl, q);
                     const double* Rq = la.R + ((long long)lvq * a.B * 2 + (long long)bq * 2 + cq) * W;
-                    const double lal = log(alq);
-                    double pw = exp((double)lane * lal);
-                    const double pw32 = exp(32.0 * lal), ial = 1.0 / alq;
+                    // alpha^lane and alpha^32 by binary powering (10 multiplications; log + two exp calls were ~300
+                    // instructions on the critical path of every evaluation, ncu r2); relative error a few ulps
+                    double pw = 1.0, sq = alq;
+#pragma unroll
+                    for (int bit = 0; bit < 5; ++bit) {
+                        if ((lane >> bit) & 1) pw *= sq;
+                        sq *= sq;
+                    }
+                    const double pw32 = sq, ial = 1.0 / alq;
                     double f = 0, df = 0, h = 0, dh = 0, tl = 0, dtl = 0;
                     for (int m = lane; m < W; m += 32) {
                         const double pm1 = (double)m * pw * ial;            // m alpha^(m-1)

@@ -335,10 +335,13 @@ def ensemble_kalman_smoother_multicam(
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
                                        avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs,
                                        n_cams_out=len(camera_names))
-    if camgroup is not None and not inflate_vars and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
+    if camgroup is not None and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
         h_all, _ = make_projection_from_camgroup(camgroup)          # calibrated model, device-resident pipeline
+        if inflate_vars and inflate_vars_kwargs.get('mean', None) is not None:      # :355-357
+            inflate_vars_kwargs['mean'] = np.zeros_like(inflate_vars_kwargs['mean'])
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
-                                       avg_mode, var_mode, 3, cams=h_all.cams, n_cams_out=len(camera_names))
+                                       avg_mode, var_mode, n_latent if inflate_vars else 3, inflate_vars,
+                                       inflate_vars_kwargs, cams=h_all.cams, n_cams_out=len(camera_names))
 
     t0 = time.perf_counter()
     ema = ensemble(marker_array, avg_mode=avg_mode, var_mode=var_mode)

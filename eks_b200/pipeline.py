@@ -351,7 +351,7 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
     """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551) for S sessions at once, every per-frame
     stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.  cams = None: linear PCA-latent model; cams = (V, 29)
     packed camera parameters: calibrated pinhole EKF (triangulation on the device, geometric initialisation of the
-    3-D state on the host from the (K, T, 3) triangulated means; no variance inflation on this branch).
+    3-D state on the device: eks_geometric_init; variance inflation on the centred predictions as in the linear branch).
 
     The only host work is the O x O eigen-decomposition per keypoint (O = 2V <= 16) on the moments the device
     reduced -- one small device->host copy and one host->device copy of the components."""
@@ -384,8 +384,25 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
     yv = PlaneView(out, V * 9 * T, [v * 9 * T + (3 + j) * T for v in range(V) for j in range(2)])
     vv = PlaneView(out, V * 9 * T, [v * 9 * T + (5 + j) * T for v in range(V) for j in range(2)])
     if cams is not None:
-        return _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap,
-                                 min_R_var, stage, trace_cap)
+        raw_var = None
+        if inflate_vars:
+            # eks/multicam_smoother.py:353-361 applies to both branches: Mahalanobis inflation on the CENTRED predictions;
+            # the calibrated model then smooths the un-centred observations with the inflated variances but REPORTS the
+            # raw ensemble variances (:474-477), so planes 5, 6 are saved and restored around the smoother
+            with stage('center'):
+                ymean_c, _, ws_c = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
+            raw_var = out[:, :, :, 5:7, :].clone()
+            kw = dict(inflate_vars_kwargs or {})
+            lik = None
+            if kw.pop('likelihoods', None) is not None:
+                lik = PlaneView(out, V * 9 * T, [v * 9 * T + 2 * T for v in range(V)])
+            with stage('inflate_vars'):
+                mc_inflate_variances(yv, vv, ymean_c, T, ws_c, kw.pop('n_latent', L), lik=lik, **kw)
+        res = _multicam_pinhole(raw, out, yv, vv, cams, smooth_param, spans, dtype, lr, s_bounds_log, tol, safety_cap,
+                                min_R_var, stage, trace_cap)
+        if raw_var is not None:
+            out[:, :, :, 5:7, :] = raw_var
+        return res
     with stage('center'):
         ymean, n_good, ws = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
     with stage('pca'):

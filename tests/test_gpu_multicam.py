@@ -101,6 +101,32 @@ def test_multicam_nonlinear_fp64_matches_oracle():
     _check(df3.to_numpy().reshape(-1, len(kps), 6), g['out3d_f64'], 1e-4, 'multicam nonlinear 3d')
 
 
+def test_multicam_nonlinear_with_inflation_fp64_matches_oracle():
+    """Calibrated model with inflate_vars=True (the CLI default; reference integration call
+    tests/integration/test_multicam.py:31-41): Mahalanobis inflation on the centred predictions runs on the device for
+    this branch too, the smoother uses the inflated variances, the output reports the raw ensemble variances."""
+    import eks_b200
+    from eks_b200.multicam_smoother import CameraGroup, ensemble_kalman_smoother_multicam
+    from oracle import oracle
+    g = load_golden('multicam_fly_nonlinear')
+    cal = os.path.join(GOLDEN, 'fly_calibration.toml')
+    raw = g['raw'].astype(np.float64).copy()
+    raw[:, 1, 100:140, 0, 0:2] += 25.0            # one camera disagrees for a while: these frames must be inflated
+    ref = oracle.multicam(raw, camgroup=cal, quantile_keep_pca=95.0, dtype=np.float64, inflate_vars=True)
+    ref_plain = oracle.multicam(raw, camgroup=cal, quantile_keep_pca=95.0, dtype=np.float64, inflate_vars=False)
+    assert np.abs(ref['cam_out'] - ref_plain['cam_out']).max() > 1e-3, 'the inflation did not change anything'
+    eks_b200.set_precision('float64')
+    kps = [str(k) for k in g['keypoints']]
+    cams = [str(c) for c in g['cameras']]
+    try:
+        dfs, s, df3 = ensemble_kalman_smoother_multicam(_ma(raw), kps, cams, quantile_keep_pca=95.0,
+                                                        camgroup=CameraGroup.load(cal), inflate_vars=True)
+    finally:
+        eks_b200.set_precision('float32')
+    np.testing.assert_allclose(s, ref['s_finals'], rtol=1e-4)
+    _check(_cam_array(dfs, len(kps)), ref['cam_out'], 1e-4, 'multicam nonlinear + inflation')
+
+
 def test_fixed_smooth_param_and_latent_dims():
     """reference tests/test_multicam_smoother.py:196-228: n_latent in {3,4,5} with 4 cameras, s echoed."""
     from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
