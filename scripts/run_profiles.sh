@@ -8,11 +8,11 @@ mkdir -p $OUT
 C5="python bench.py --steps 1 --warmup 1 --sessions 2 --no-e2e --no-cpu --no-public"
 C3="python bench.py --workload c3 --steps 1 --warmup 1 --no-e2e --no-cpu --no-public"
 C4="python bench.py --workload c4 --steps 1 --warmup 1 --no-e2e --no-cpu --no-public"
-KSEL='regex:eks::'
+KSEL='regex:_ZN3eks'
 # (1) every launch of the library with its device time (cold-cache, serialised: compare SHARES, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL --log-file $OUT/launches_${TAG}_c5.csv $C5 > $OUT/launches_${TAG}_c5.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL --log-file $OUT/launches_${TAG}_c3.csv $C3 > $OUT/launches_${TAG}_c3.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv -k $KSEL -c 400 --log-file $OUT/launches_${TAG}_c4.csv $C4 > $OUT/launches_${TAG}_c4.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --kernel-name-base mangled -k $KSEL --log-file $OUT/launches_${TAG}_c5.csv $C5 > $OUT/launches_${TAG}_c5.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --kernel-name-base mangled -k $KSEL --log-file $OUT/launches_${TAG}_c3.csv $C3 > $OUT/launches_${TAG}_c3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --kernel-name-base mangled -k $KSEL -c 400 --log-file $OUT/launches_${TAG}_c4.csv $C4 > $OUT/launches_${TAG}_c4.log 2>&1
 if [ "${2:-}" = "full" ]; then
 # (2) full captures, one launch of each kernel of the step (after the warm-up step)
 # (the .ncu-rep files are summarised on the box and removed: gpurun brings back at most 64 MiB)
