@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 F32, F64 = 0, 1
-ABI_VERSION = 201      # eks_version() of the library this package was written against (include/eks_b200.h)
+ABI_VERSION = 202      # eks_version() of the library this package was written against (include/eks_b200.h)
 MAX_CHAN, MAX_STATE, CAM_STRIDE = 16, 6, 29
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,6 +59,7 @@ _SIGS = {
     'eks_geometric_init_workspace_bytes': (c_size_t, [c_int, c_int]),
     'eks_geometric_init': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'eks_last_launch_count': (c_int, []),
+    'eks_last_unverified_count': (c_int, []),
     'eks_mc_valid_moments': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_double, c_double,
                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -27,6 +27,7 @@ struct PlaneView {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void note_launches(int n);   // kernels enqueued by the current entry point (eks_last_launch_count)
+void note_unverified(int n); // evaluations accepted with an unverified run boundary (eks_last_unverified_count)
 
 #define EKS_REQUIRE(cond, ...)            \
     do {                                  \

@@ -15,7 +15,9 @@ namespace eks {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static thread_local int g_unverified = 0;
 void note_launches(int n) { g_launches = n; }
+void note_unverified(int n) { g_unverified = n; }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -232,7 +234,8 @@ using namespace eks;
 
 extern "C" const char* eks_last_error(void) { return g_err; }
 extern "C" int eks_last_launch_count(void) { return g_launches; }
-extern "C" int eks_version(void) { return 201; }
+extern "C" int eks_last_unverified_count(void) { return g_unverified; }
+extern "C" int eks_version(void) { return 202; }
 
 extern "C" int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const void* S0, const void* A,
                             const void* Q, const void* C, int ncam, const void* cams, const void* y_base,
@@ -265,6 +268,7 @@ extern "C" int eks_optimize_s(int dtype, int B, int D, int O, int T, const void*
                               int trace_cap, int model_structure, void* workspace, size_t workspace_bytes,
                               void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    note_unverified(0);
     // model_structure == EKS_STRUCT_DIAG: the caller asserts D == O == 2 with diagonal A, C, Q, S0
     // (single-camera model) -> time-parallel persistent kernel (diag.cu); one contiguous span only
     if ((model_structure == EKS_STRUCT_DIAG || model_structure == EKS_STRUCT_DIAG_STREAM) && D == 2 && O == 2 &&

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(ADAM_RUNS_NT) gen_adam_runs_kernel(const __gri
         mism = block_sum(mism, scratch);
         if (mism > 0) {
             if (sizeof(P) == 4 && warm >= RUNS_WMAX32) {
-                if (tid == 0) bs.unverified += 1;
+                if (tid == 0) { bs.unverified += 1; if (g.ndone) atomicAdd(g.ndone + 1, 1); }
             } else {
                 verified = false;
                 if (tid == 0) g.warm[b] = (warm >= n / 4) ? n : warm * 4;
@@ -335,10 +335,11 @@ size_t linear_steady_workspace_bytes(int dtype, int B, int D, int O, int T);
 // cost ~700 no-op launches per call).  This entry point therefore synchronises the stream once per chunk.
 constexpr int RUNS_SLOT_CHUNK = 32;
 static bool runs_all_done(const int* ndone, int n_blocks, cudaStream_t st) {
-    int h = 0;
-    if (cudaMemcpyAsync(&h, ndone, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+    int h[2] = {0, 0};      // [0] finished blocks, [1] evaluations accepted with an unverified boundary (float32 cap)
+    if (cudaMemcpyAsync(h, ndone, 2 * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
     if (cudaStreamSynchronize(st) != cudaSuccess) return false;
-    return h >= n_blocks;
+    note_unverified(h[1]);
+    return h[0] >= n_blocks;
 }
 
 template <class P, int DC, int OC, bool FIXED, bool NL>
@@ -368,6 +369,7 @@ static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st
         fprintf(stderr, "\n");
     }
     note_launches(launched);
+    runs_all_done(g.ndone, a.n_blocks, st);     // final counters (this entry point synchronises the stream)
     return check_launch("generic run-parallel optimise kernels");
 }
 
@@ -929,6 +931,7 @@ static int lin_optimize_launch(const GArgs<P>& a, RunArgs<P> g, const LinArgs<P>
         fprintf(stderr, "\n");
     }
     note_launches(launched);
+    runs_all_done(g.ndone, a.n_blocks, st);
     return check_launch("linear steady-state optimise kernels");
 }
 
@@ -970,8 +973,9 @@ int generic_runs_optimize(const GArgs<P>& a, void* workspace, size_t workspace_b
     g.nred = (g.nruns + RUNS_RED_NT - 1) / RUNS_RED_NT;
     g.part2 = (double*)take((size_t)a.B * g.nred * 4 * sizeof(double));
     g.flag = nullptr;
-    g.ndone = (int*)take(sizeof(int));
-    cudaMemsetAsync(g.ndone, 0, sizeof(int), st);
+    g.ndone = (int*)take(2 * sizeof(int));
+    cudaMemsetAsync(g.ndone, 0, 2 * sizeof(int), st);
+    note_unverified(0);
     cudaMemsetAsync(seq_block, 0xFF, (size_t)a.B * sizeof(int), st);
     const int nmax = a.B > a.n_blocks ? a.B : a.n_blocks;
     gen_runs_init_kernel<<<(nmax + 127) / 128, 128, 0, st>>>(a.B, a.n_blocks, a.block_off, a.members, seq_block,

@@ -191,7 +191,13 @@ def optimize_s(model: Model, y: PlaneView, T: int, Rconst: torch.Tensor, s_log0:
                                int(structure), ptr(ws), nbytes, stream_ptr()), 'eks_optimize_s')
     launches = int(lib().eks_last_launch_count())   # the library reports what this call enqueued
     _count(launches)
-    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, launches=launches,
+    unverified = int(lib().eks_last_unverified_count())
+    if unverified:
+        import logging
+        logging.getLogger(__name__).warning(
+            f'optimize_s: {unverified} evaluation(s) were accepted with a run boundary that still disagreed at the '
+            f'float32 warm-up cap (rounding-level disagreement of ill-conditioned covariances)')
+    return dict(s_log=s_log, loss=loss, iters=iters, trace=trace, launches=launches, unverified=unverified,
                 blocks=blocks if blocks is not None else [[k] for k in range(B)], _keep=(d_boff, d_mem, ws))
 
 

@@ -278,8 +278,11 @@ def pca_from_moments(mom, O: int, L: int):
 def fa_from_moments(mom_b, O: int, L: int, tol: float = 1e-2, max_iter: int = 1000):
     """sklearn FactorAnalysis(n_components=L).fit restated on the sufficient statistics (n, sum x, sum x x^T)
     (sklearn/decomposition/_factor_analysis.py::fit): the SVD of X / (sqrt(psi) sqrt(n)) is taken through the
-    eigen-decomposition of its O x O Gram matrix (exact here: the randomized solver's sketch, n_components + 10
-    columns, spans all O <= 16 features).  Returns (mean (O,), loading (O,L) = components_.T) float64."""
+    eigen-decomposition of its O x O Gram matrix.  sklearn's default randomized solver sketches n_components + 10
+    columns with 3 power iterations: for O <= n_components + 10 (up to 6 cameras at n_latent = 3) the sketch spans every
+    feature and the two agree to rounding; for 7-8 cameras (O = 14, 16) sklearn's result carries the sketch's own
+    approximation error and seed dependence, this one is the exact decomposition it approximates.
+    Returns (mean (O,), loading (O,L) = components_.T) float64."""
     import numpy as np
     n = mom_b[0]
     mean = mom_b[1:1 + O] / n
@@ -339,6 +342,11 @@ def mc_inflate_variances(yv: PlaneView, vv: PlaneView, ymean: torch.Tensor, T: i
         active = active * (flags != 0).to(torch.int32)
         if int(active.sum().item()) == 0:
             break
+    else:   # the reference loops until no variance is inflated any more; x10 per round makes 64 rounds unreachable
+        import logging
+        logging.getLogger(__name__).warning(
+            f'variance inflation stopped after {max_rounds} rounds with {int(active.sum().item())} keypoints still '
+            f'inflating (the reference would continue)')
     return rounds
 
 

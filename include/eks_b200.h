@@ -45,6 +45,9 @@ int eks_version(void);   /* 200 for this header; the Python binding refuses any 
 /* Number of kernels the most recent eks_optimize_s / eks_diag_smooth / eks_const_R_median call of this thread
  * enqueued (bench.py's gpu_launches). */
 int eks_last_launch_count(void);
+/* Evaluations of the last run-parallel eks_optimize_s / eks_nll_grad call on this thread that were accepted although a
+ * run boundary still disagreed at the float32 warm-up cap (16384 frames): 0 means every accepted loss was verified. */
+int eks_last_unverified_count(void);
 
 /* ---- ensemble statistics: replaces eks.core.ensemble / compute_stats (eks/core.py:25-101) --------
  * raw: [n_sessions][M][V][T][K][3] in the reference MarkerArray layout (eks/marker_array.py:15-30),
