@@ -57,6 +57,7 @@ struct MLagStatArgs {
     PlaneView y;
     int B, O, t_begin, n, nsig, nchunk, nx;   // nsig = n + 1: the signal g_i is defined for i = 1 .. n
     const MLBasis* basis;
+    P* gsig;           // [B][O][nsig]: the stationary signal g_i, i = 0 .. n (ml_signal_kernel), working precision
     double* partial;   // [B O O][nx][W]
     double* R;         // [ML_NT0][B O O][W]
 };
@@ -125,6 +126,22 @@ __device__ __forceinline__ double ml_g(const P* __restrict__ yb, const long long
     return acc;
 }
 
+// The signal planes: g[b][o][i] for i = 0 .. n, formed in float64 from the O observation planes and rounded ONCE to the
+// working precision (the statistics kernel then stages plain loads; forming the signal while staging, once per channel
+// PAIR, made it 63 % non-FMA instructions).  grid = (ceil(nsig / 256), B O).
+template <class P>
+__global__ void __launch_bounds__(256) ml_signal_kernel(const __grid_constant__ MLagStatArgs<P> a) {
+    __shared__ MLBasis bs;
+    const int bo = blockIdx.y, b = bo / a.O, o = bo - b * a.O;
+    for (int i = threadIdx.x; i < (int)(sizeof(MLBasis) / sizeof(double)); i += 256)
+        reinterpret_cast<double*>(&bs)[i] = reinterpret_cast<const double*>(a.basis + b)[i];
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.nsig) return;
+    const P* yb = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin;
+    a.gsig[(long long)bo * a.nsig + i] = (P)ml_g<P>(yb, a.y.chan_off, bs, a.O, a.n, i, o);
+}
+
 // Rg_m[a][c] partial sums.  grid = (nx, B O O); CTA (x, (b, a, c)) handles the tiles x, x + nx, ... : the signal
 // components a (frames of the tile) and c (tile + W halo) are formed in float64 from the observations and staged in
 // shared memory in the working precision; warp w owns lag groups w, w + 8, ... and lane l the frames
@@ -139,15 +156,13 @@ __global__ void __launch_bounds__(ML_NT) mlag_stats_kernel(const __grid_constant
     constexpr int VW = MLVec<P>::VW;
     using V = typename MLVec<P>::type;
     extern __shared__ __align__(16) unsigned char ml_smem[];
-    __shared__ MLBasis bs;
     P* smA = reinterpret_cast<P*>(ml_smem);
     P* smC = smA + NPHYS;
     const int O = a.O;
     const int bac = blockIdx.y, b = bac / (O * O), ac = bac - b * O * O, ca = ac / O, cc = ac - ca * O;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (int)(sizeof(MLBasis) / sizeof(double)); i += ML_NT)
-        reinterpret_cast<double*>(&bs)[i] = reinterpret_cast<const double*>(a.basis + b)[i];
-    const P* yb = reinterpret_cast<const P*>(a.y.base) + (long long)b * a.y.seq_stride + a.t_begin;
+    const P* ga = a.gsig + ((long long)b * O + ca) * a.nsig;
+    const P* gc = a.gsig + ((long long)b * O + cc) * a.nsig;
     double accd[GPW][ML_RM];
 #pragma unroll
     for (int q = 0; q < GPW; ++q)
@@ -156,10 +171,21 @@ __global__ void __launch_bounds__(ML_NT) mlag_stats_kernel(const __grid_constant
     for (int chunk = blockIdx.x; chunk < a.nchunk; chunk += a.nx) {
         const int i0 = ML_T0 + 1 + chunk * ML_CH;
         __syncthreads();
-        for (int x = threadIdx.x; x < NLOG; x += ML_NT) {
-            const int i = i0 + x;
-            smC[ml_phys<P>(x)] = (P)ml_g<P>(yb, a.y.chan_off, bs, O, a.n, i, cc);
-            if (x < ML_CH) smA[ml_phys<P>(x)] = (P)ml_g<P>(yb, a.y.chan_off, bs, O, a.n, i, ca);
+        {   // every load of the tile is issued before the first use
+            constexpr int U = (NLOG + ML_NT - 1) / ML_NT;
+            P vc[U], va[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = threadIdx.x + u * ML_NT, i = i0 + x;
+                vc[u] = (x < NLOG && i < a.nsig) ? __ldg(gc + i) : P(0);
+                va[u] = (x < ML_CH && i < a.nsig) ? __ldg(ga + i) : P(0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int x = threadIdx.x + u * ML_NT;
+                if (x < NLOG) smC[ml_phys<P>(x)] = vc[u];
+                if (x < ML_CH) smA[ml_phys<P>(x)] = va[u];
+            }
         }
         __syncthreads();
         const int nvalid = min(ML_CH, a.nsig - i0);
@@ -741,7 +767,8 @@ size_t lin_lag_workspace_bytes(int dtype, int n_blocks, int B, int O, int T) {
     const int nchunk = (T + ML_CH - 1) / ML_CH + 1;
     const int nx = (nchunk + ML_CPB - 1) / ML_CPB;
     return ml_align((size_t)ML_NT0 * B * O * O * W * sizeof(double)) + ml_align((size_t)B * O * O * nx * W * sizeof(double)) +
-           ml_align((size_t)B * sizeof(MLBasis)) + ml_align((size_t)n_blocks * sizeof(int)) + 256;
+           ml_align((size_t)B * sizeof(MLBasis)) + ml_align((size_t)n_blocks * sizeof(int)) +
+           ml_align((size_t)B * O * (T + 1) * (dtype == EKS_F32 ? 4 : 8)) + 256;
 }
 
 template <class P, int W>
@@ -760,7 +787,8 @@ static int lin_lag_run(const GArgs<P>& a, void* workspace, size_t workspace_byte
     MLBasis* basis = (MLBasis*)w; w += ml_align((size_t)a.B * sizeof(MLBasis));
     sa.basis = basis;
     sa.R = R;
-    int* flag = (int*)w;
+    int* flag = (int*)w; w += ml_align((size_t)a.n_blocks * sizeof(int));
+    sa.gsig = (P*)w;
     constexpr int PADE = 16 / (int)sizeof(P);
     constexpr int NLOG = ML_CH + W;
     constexpr int NPHYS = NLOG + (NLOG / 16) * PADE + PADE;
@@ -772,6 +800,7 @@ static int lin_lag_run(const GArgs<P>& a, void* workspace, size_t workspace_byte
     }
     cudaMemsetAsync(flag, 0xFF, (size_t)a.n_blocks * sizeof(int), st);     // -1: not finished
     ml_basis_kernel<P><<<(a.B + 63) / 64, 64, 0, st>>>(a.B, O, a.C, a.ymean, basis);
+    ml_signal_kernel<P><<<dim3((sa.nsig + 255) / 256, a.B * O), 256, 0, st>>>(sa);
     mlag_stats_kernel<P, W><<<dim3(sa.nx, a.B * O * O), ML_NT, smem, st>>>(sa);
     int rc = check_launch("mlag_stats_kernel");
     if (rc) return rc;
@@ -805,7 +834,7 @@ static int lin_lag_run(const GArgs<P>& a, void* workspace, size_t workspace_byte
     }
     if (all_ok) {
         *used = 1;
-        note_launches(4);
+        note_launches(5);
     }
     return 0;
 }

@@ -259,7 +259,7 @@ def test_lag_statistics_optimiser_equals_run_parallel_path(V, dtype, T, monkeypa
     monkeypatch.setenv('EKS_DEBUG_RUNS', '1')
     res = multicam_smooth_sessions(x, dtype=dtype, trace_cap=300)
     tr = multicam_smooth_sessions.last_opt['trace'].double().cpu().numpy()
-    assert multicam_smooth_sessions.last_opt['launches'] == 4, \
+    assert multicam_smooth_sessions.last_opt['launches'] == 5, \
         'the lag-statistics path did not run (fell back to the run-parallel path)'
     it, it_ref = res.iters[0].cpu().numpy(), ref.iters[0].cpu().numpy()
     if dtype == torch.float64:
