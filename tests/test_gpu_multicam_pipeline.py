@@ -273,3 +273,17 @@ def test_lag_statistics_optimiser_equals_run_parallel_path(V, dtype, T, monkeypa
         from parity import fp32_stop_protocol
         for k in range(raw.shape[3]):
             fp32_stop_protocol(f'lag (float32) vs runs (float64) kp{k}', tr[k], it[k], tr_ref[k], it_ref[k])
+
+
+def test_lag_statistics_path_with_one_offset_span_fp64():
+    """s_frames with ONE span that does not start at frame 0: the lag-statistics optimiser runs on the cropped frames
+    (t_begin > 0, n < T) and must still reproduce the oracle's iteration counts; the final pass covers every frame."""
+    from eks_b200.pipeline import multicam_smooth_sessions
+    from oracle import oracle
+    raw = synth_multicam(T=3000, seed=9)
+    res = _run(raw, torch.float64, spans=[(250, 2900)])
+    assert multicam_smooth_sessions.last_opt['launches'] == 5, 'the lag-statistics path did not run'
+    ref = oracle.multicam(raw, dtype=np.float64, s_frames=[(250, 2900)])
+    assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
+    np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=RTOL64)
+    _check(_cam_out(res), ref['cam_out'], RTOL64, 'one offset span')
