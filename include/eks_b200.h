@@ -12,10 +12,11 @@
  *  - The caller owns every buffer; the library never allocates or frees caller memory.  Scratch is
  *    passed as (workspace, workspace_bytes); sizes come from the *_workspace_bytes queries.
  *  - Calls ENQUEUE work on `stream` (a cudaStream_t cast to void*) and return; the caller synchronises.
- *    Exceptions, stated at the entry point: eks_pupil_optimize and eks_filter_smooth (sequences of >= 512 frames)
- *    read a completion / verification flag and therefore synchronise `stream` themselves.
- *  - State kept by the library: a thread-local error string and launch counter (eks_last_error,
- *    eks_last_launch_count), and -- only for EKS_STRUCT_DIAG_STREAM -- a per-device table of two internal streams,
+ *    Exceptions, stated at the entry point: eks_pupil_optimize, eks_filter_smooth (sequences of >= 512 frames) and
+ *    eks_optimize_s / eks_nll_grad for generic models with >= 512 frames (everything except EKS_STRUCT_DIAG*) read a
+ *    completion / verification flag and therefore synchronise `stream` themselves.
+ *  - State kept by the library: a thread-local error string and two counters (eks_last_error,
+ *    eks_last_launch_count, eks_last_unverified_count), and -- only for EKS_STRUCT_DIAG_STREAM -- a per-device table of two internal streams,
  *    created on first use under a mutex and forked from / joined to the caller's stream by events.  Nothing else
  *    persists between calls.  Entry points may be called concurrently from several host threads (different streams).
  *  - Return value: 0 ok; <0 invalid argument; >0 a cudaError_t.  eks_last_error() returns a
@@ -41,7 +42,7 @@ extern "C" {
 #define EKS_CAM_STRIDE 29  /* R(9 row-major) t(3) fx fy cx cy skew k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 */
 
 const char* eks_last_error(void);
-int eks_version(void);   /* 200 for this header; the Python binding refuses any other value */
+int eks_version(void);   /* 202 for this header; the Python binding refuses any other value */
 /* Number of kernels the most recent eks_optimize_s / eks_diag_smooth / eks_const_R_median call of this thread
  * enqueued (bench.py's gpu_launches). */
 int eks_last_launch_count(void);
@@ -113,8 +114,12 @@ int eks_nll_grad(int dtype, int B, int D, int O, int T, const void* m0, const vo
  * loss = sum of member NLLs.  s_log0: [n_blocks] real (float32-rounded seed).  Outputs [n_blocks]:
  * s_log_out (real, the value AFTER the last update, core.py:675), last_loss_out (real), iters_out (int).
  * The caller forms s = exp(clip(s_log, lo, hi)) (core.py:694).  trace (nullable): [n_blocks][trace_cap][3]
- * real rows (s_log, loss, lr*grad) per iteration.  model_structure: EKS_STRUCT_GENERAL (one block per thread,
- * sequential in time), EKS_STRUCT_DIAG (needs <= 1 span: lag statistics of the increments in ONE pass over the
+ * real rows (s_log, loss, lr*grad) per iteration.  model_structure: EKS_STRUCT_GENERAL (T < 512: one block per thread,
+ * sequential in time; T >= 512: linear models with A = I, D = 3, O in {4, 6, 8} and one span use the lag statistics of
+ * the stationary signal in ONE pass over the observations and a persistent Adam warp per block with the closed-form
+ * NLL -- eks_b200/csrc/lin_lag.cu; every other model, and blocks for which the closed form is not exact, use the
+ * verified run-parallel evaluation of generic_runs.cu, enqueued in chunks of 32 evaluations.  Both synchronise
+ * `stream`), EKS_STRUCT_DIAG (needs <= 1 span: lag statistics of the increments in ONE pass over the
  * observations, then the whole Adam loop of a block in one persistent CTA evaluating the NLL in closed form from them,
  * streaming an evaluation only where the closed form is not exact to rounding -- eks_b200/csrc/diag_lag.cu) or
  * EKS_STRUCT_DIAG_STREAM (the exact time-parallel streaming evaluation once per Adam iteration, one launch each --
