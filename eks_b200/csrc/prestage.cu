@@ -330,13 +330,35 @@ __global__ void __launch_bounds__(256) med_count_kernel(PlaneView var, int O, Sp
     int below = 0, nans = 0, nloc = 0;
     key_t loc[LCAP];
     constexpr int UN = 4;       // independent loads in flight per thread
+    const bool one_span = (sp.n == 1);
+    const P* src = base + (one_span ? sp.start[0] : 0);
+    const key_t NANKEY = ~(key_t)0;
     for (int ib = i0 + threadIdx.x; ib < i1; ib += UN * blockDim.x) {
         P x[UN];
+        if (one_span && ib + (UN - 1) * (int)blockDim.x < i1) {
+            // full batch of one contiguous span (all but the last batch of a chunk): no bounds checks, no span lookup,
+            // branch-free counting -- the checked path below cost ~41 instructions per element (ncu r2f: ISETP + BRA +
+            // IMAD + BSSY/BSYNC 60 % of the kernel), which kept this pass at half the HBM rate
+#pragma unroll
+            for (int u = 0; u < UN; ++u) x[u] = src[ib + u * blockDim.x];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const key_t k = KT::key(x[u]);                 // NaN -> all ones
+                const bool isn = (k == NANKEY);
+                nans += isn ? 1 : 0;
+                below += (k < lo) ? 1 : 0;
+                if (k >= lo && k <= hi && !isn) {
+                    if (nloc < LCAP) loc[nloc] = k;
+                    ++nloc;
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int i = ib + u * blockDim.x;
             x[u] = P(0);
-            if (i < i1) x[u] = base[(sp.n == 1) ? sp.start[0] + i : span_to_frame(sp, i)];
+            if (i < i1) x[u] = base[one_span ? sp.start[0] + i : span_to_frame(sp, i)];
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
