@@ -323,7 +323,7 @@ def stage_bytes_per_kf(w, wbytes, stage, n_eval_mean, opt_mode):
     if stage == 'const_R_median':
         return wbytes * obs                                 # one read of the variance planes
     if stage == 'optimize_s':
-        if w['kind'] == 'singlecam' and opt_mode == 'lag':
+        if (w['kind'] == 'singlecam' and opt_mode == 'lag') or w['kind'] == 'multicam':
             return wbytes * obs                             # the observations are read ONCE (lag statistics)
         return wbytes * obs * n_eval_mean                   # one read of the observations per evaluation
     if stage == 'filter_smooth':
@@ -539,12 +539,13 @@ def run_b200(args):
     else:
         peak, peak_src = 6650.0, 'fallback 6.65 TB/s (of fallback)'
     # ---- every stage against the HBM roofline: algorithmic bytes of the stage / its CUDA-event time
-    kernel_names = {'ensemble': 'ensemble_staged_kernel', 'const_R_median': 'select_hist_kernel + select_scan_kernel',
+    kernel_names = {'ensemble': 'ensemble_staged_kernel',
+                    'const_R_median': 'med_sample_kernel + med_count_kernel + med_final_kernel',
                     'optimize_s': ('lag_stats_kernel + diag_lag_opt_kernel' if kind == 'singlecam' and args.opt_mode == 'lag'
                                    else 'diag_nll_kernel' if kind == 'singlecam' else
-                                   'lin_prep_kernel + lin_runs_kernel + gen_runs_reduce_kernel' if kind == 'multicam' else
+                                   'ml_signal_kernel + mlag_stats_kernel + lin_lag_opt_kernel' if kind == 'multicam' else
                                    'gen_nll_runs_kernel + gen_runs_reduce_kernel'),
-                    'filter_smooth': 'diag_filter_kernel + diag_rts_kernel' if kind == 'singlecam' else
+                    'filter_smooth': 'diag_smooth_fused_kernel' if kind == 'singlecam' else
                                      'gen_filter_runs_kernel + gen_rts_runs_kernel',
                     'reproject': 'reproject_kernel', 'triangulate': 'triangulate_mean_kernel'}
     tj = {}
@@ -558,7 +559,8 @@ def run_b200(args):
             continue
         alg = bpk * kf_step
         ach = alg / (ms * 1e-3) / 1e9
-        ratio = tj.get(kernel_names.get(st, st), {}).get('dram_per_algorithmic')
+        tje = tj.get(kernel_names.get(st, st), {})
+        ratio = (tje['dram_bytes'] / tje['algorithmic_bytes']) if tje.get('algorithmic_bytes') else None
         kernels[st] = {'kernel': kernel_names.get(st, st), 'ms': ms, 'algorithmic_bytes': alg, 'achieved': ach,
                        'frac': ach / peak, 'share_of_step': ms / sum(stage_ms.values()),
                        'traffic': (alg * ratio) if ratio else None}
