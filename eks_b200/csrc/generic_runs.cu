@@ -345,7 +345,11 @@ static bool runs_all_done(const int* ndone, int n_blocks, cudaStream_t st) {
 template <class P, int DC, int OC, bool FIXED, bool NL>
 static int runs_optimize_launch(const GArgs<P>& a, RunArgs<P> g, cudaStream_t st) {
     const int nthreads = a.B * g.nruns;
-    const int slots = a.cap + RUNS_EXTRA;
+    // extra slots for warm-up escalations (a repeated evaluation consumes a slot): every member of a shared-s block can
+    // escalate at a different iteration, so the allowance grows with the largest possible block (B - n_blocks + 1
+    // members); unused slots cost nothing, the loop stops when every block is done
+    const int max_members = a.B - a.n_blocks + 1 < 1 ? 1 : (a.B - a.n_blocks + 1 > 8 ? 8 : a.B - a.n_blocks + 1);
+    const int slots = a.cap + RUNS_EXTRA * max_members;
     g.total_slots = slots;
     g.final_slot = -1;
     // (splitting the blocks over internal streams as diag_optimize_run does was measured and does not pay here:
@@ -906,7 +910,11 @@ size_t linear_steady_workspace_bytes(int dtype, int B, int D, int O, int T) {
 template <class P, int DC, int OC, bool FIXED>
 static int lin_optimize_launch(const GArgs<P>& a, RunArgs<P> g, const LinArgs<P>& l, cudaStream_t st) {
     const int nthreads = a.B * g.nruns;
-    const int slots = a.cap + RUNS_EXTRA;
+    // extra slots for warm-up escalations (a repeated evaluation consumes a slot): every member of a shared-s block can
+    // escalate at a different iteration, so the allowance grows with the largest possible block (B - n_blocks + 1
+    // members); unused slots cost nothing, the loop stops when every block is done
+    const int max_members = a.B - a.n_blocks + 1 < 1 ? 1 : (a.B - a.n_blocks + 1 > 8 ? 8 : a.B - a.n_blocks + 1);
+    const int slots = a.cap + RUNS_EXTRA * max_members;
     g.total_slots = slots;
     g.final_slot = -1;
     gen_adam_runs_kernel<P><<<a.n_blocks, ADAM_RUNS_NT, 0, st>>>(a, g, 1);
