@@ -259,3 +259,20 @@ def test_device_triangulation_matches_oracle():
     for dt in (torch.float64, torch.float32):
         got = ops.triangulate_mean(torch.as_tensor(raw).to('cuda', dt).contiguous(), cams).cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=1e-6 if dt == torch.float64 else 1e-4, atol=1e-8)
+
+
+def test_shared_s_block_of_linear_sequences_through_the_lag_path():
+    """blocks=[[0, 1], [2]] on a D = 3 / O = 4 model with A = I and 3000 frames: the lag-statistics optimiser sums the
+    member losses of a shared-s block (eks/core.py:474-476) and must reproduce the oracle's iteration counts and s."""
+    import eks_b200
+    from oracle import oracle
+    args = _linear_case(3, 3000, seed=21)
+    eks_b200.set_precision('float64')
+    try:
+        s, ms, Vs = eks_b200.run_kalman_smoother(*args, blocks=[[0, 1], [2]])
+    finally:
+        eks_b200.set_precision('float32')
+    s_o, ms_o, Vs_o, info = oracle.run_kalman_smoother(*args, blocks=[[0, 1], [2]], dtype=np.float64)
+    assert s[0] == s[1]
+    np.testing.assert_allclose(s, s_o, rtol=1e-5)
+    np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-6)
