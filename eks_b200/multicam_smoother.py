@@ -261,7 +261,7 @@ def project_3d_covariance_to_2d(ms_k, Vs_k, h_cam: PinholeProjection, inflated_v
 
 def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames, avg_mode,
                             var_mode, n_latent, inflate_vars=False, inflate_vars_kwargs=None, cams=None,
-                            n_cams_out: int | None = None) -> tuple:
+                            n_cams_out: int | None = None, pca=None) -> tuple:
     """Linear PCA-latent model without variance inflation: every per-frame stage runs on the device
     (eks_b200.pipeline.multicam_smooth_sessions); the host only packs the DataFrames."""
     from eks_b200.pipeline import multicam_smooth_sessions
@@ -280,7 +280,7 @@ def _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile
     res = multicam_smooth_sessions(raw[None], smooth_param=sp, spans=normalize_spans(T, s_frames),
                                    quantile_keep_pca=quantile_keep_pca, n_latent=n_latent, avg_mode=avg_mode,
                                    var_mode=var_mode, dtype=dtype, inflate_vars=inflate_vars,
-                                   inflate_vars_kwargs=inflate_vars_kwargs, cams=cams)
+                                   inflate_vars_kwargs=inflate_vars_kwargs, cams=cams, pca=pca)
     out_dev = torch.empty((V, T, K, 9), dtype=torch.float64, device=dev)
     out_dev.copy_(res.out[0].permute(1, 3, 0, 2))                                   # planes -> (V,T,K,9) float64
     out = _xfer.to_host(out_dev)
@@ -329,12 +329,16 @@ def ensemble_kalman_smoother_multicam(
     M, V, T, K, _ = marker_array.shape
     t_total = time.perf_counter()
 
-    if camgroup is None and pca_object is None:
+    if camgroup is None and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
         if inflate_vars and inflate_vars_kwargs.get('mean', None) is not None:      # :355-357
             inflate_vars_kwargs['mean'] = np.zeros_like(inflate_vars_kwargs['mean'])
+        pca = None
+        if pca_object is not None:   # the caller's fitted PCA replaces the per-keypoint fit (eks/stats.py:52-56)
+            pca = (np.asarray(pca_object.mean_, dtype=np.float64),
+                   np.asarray(pca_object.components_, dtype=np.float64)[:n_latent])
         return _multicam_linear_device(marker_array, keypoint_names, smooth_param, quantile_keep_pca, s_frames,
                                        avg_mode, var_mode, n_latent, inflate_vars, inflate_vars_kwargs,
-                                       n_cams_out=len(camera_names))
+                                       n_cams_out=len(camera_names), pca=pca)
     if camgroup is not None and os.environ.get('EKS_B200_HOST_PRESTAGE') != '1':
         h_all, _ = make_projection_from_camgroup(camgroup)          # calibrated model, device-resident pipeline
         if inflate_vars and inflate_vars_kwargs.get('mean', None) is not None:      # :355-357

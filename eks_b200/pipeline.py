@@ -355,7 +355,7 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
                              dtype=torch.float32, lr=0.25, s_bounds_log=(-8.0, 8.0), tol=1e-2, safety_cap=300,
                              min_R_var=1e-4, out: torch.Tensor | None = None, timers: dict | None = None,
                              inflate_vars: bool = False, inflate_vars_kwargs: dict | None = None,
-                             cams=None, trace_cap: int = 0) -> MulticamResult:
+                             cams=None, trace_cap: int = 0, pca=None) -> MulticamResult:
     """ensemble_kalman_smoother_multicam (eks/multicam_smoother.py:279-551) for S sessions at once, every per-frame
     stage on the device.  raw: (S, M, V, T, K, 3) CUDA tensor.  cams = None: linear PCA-latent model; cams = (V, 29)
     packed camera parameters: calibrated pinhole EKF (triangulation on the device, geometric initialisation of the
@@ -414,8 +414,13 @@ def multicam_smooth_sessions(raw: torch.Tensor, smooth_param=None, spans=None, q
     with stage('center'):
         ymean, n_good, ws = ops.mc_center(yv, vv, S, K, T, quantile_keep_pca)
     with stage('pca'):
-        mom = ops.mc_pca_moments(yv, ymean, T, ws).cpu().numpy()
-        pca_mean, comps = pca_from_moments(mom, O, L)
+        if pca is None:
+            mom = ops.mc_pca_moments(yv, ymean, T, ws).cpu().numpy()
+            pca_mean, comps = pca_from_moments(mom, O, L)
+        else:   # a fitted PCA supplied by the caller (pca_object of the reference, eks/stats.py:52-56): one for all keypoints
+            pm_, cp_ = np.asarray(pca[0], dtype=np.float64), np.asarray(pca[1], dtype=np.float64)
+            assert pm_.shape == (O,) and cp_.shape == (L, O), 'pca = (mean_ (2V,), components_ (n_latent, 2V))'
+            pca_mean, comps = np.tile(pm_, (B, 1)), np.tile(cp_, (B, 1, 1))
         C = torch.as_tensor(np.ascontiguousarray(np.swapaxes(comps, 1, 2)), device=dev).to(dtype).contiguous()
         pm = torch.as_tensor(pca_mean, device=dev).to(dtype).contiguous()
     with stage('latent_init'):

@@ -276,3 +276,29 @@ def test_shared_s_block_of_linear_sequences_through_the_lag_path():
     assert s[0] == s[1]
     np.testing.assert_allclose(s, s_o, rtol=1e-5)
     np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-6)
+
+
+def test_pca_object_runs_on_the_device_and_equals_the_host_prestage(monkeypatch):
+    """pca_object (a fitted sklearn PCA shared by all keypoints, eks/stats.py:52-56): the device pipeline takes its
+    mean_ / components_ instead of fitting per keypoint; same results as the host pre-stage (NumPy centring +
+    sklearn transform + run_kalman_smoother)."""
+    import eks_b200
+    from sklearn.decomposition import PCA
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    from test_gpu_multicam_pipeline import synth_multicam
+    raw = synth_multicam(M=4, V=2, K=2, T=900, seed=17)
+    rng = np.random.default_rng(1)
+    lat = np.cumsum(rng.normal(0, 0.3, (4000, 3)), axis=0)
+    pca = PCA(n_components=3).fit(lat @ rng.standard_normal((3, 4)))
+    eks_b200.set_precision('float64')
+    try:
+        dfs_d, s_d, _ = ensemble_kalman_smoother_multicam(_ma(raw), ['a', 'b'], ['c0', 'c1'], quantile_keep_pca=80.0,
+                                                          pca_object=pca)
+        monkeypatch.setenv('EKS_B200_HOST_PRESTAGE', '1')
+        dfs_h, s_h, _ = ensemble_kalman_smoother_multicam(_ma(raw), ['a', 'b'], ['c0', 'c1'], quantile_keep_pca=80.0,
+                                                          pca_object=pca)
+    finally:
+        eks_b200.set_precision('float32')
+    np.testing.assert_allclose(s_d, s_h, rtol=1e-6)
+    for a, b in zip(dfs_d, dfs_h):
+        np.testing.assert_allclose(a.to_numpy(), b.to_numpy(), rtol=1e-6, atol=1e-7)
