@@ -15,6 +15,7 @@ from eks_b200.core import (  # noqa: F401
     run_kalman_smoother,
     set_precision,
 )
+from eks_b200.ibl_paw_multicam_smoother import fit_eks_multicam_ibl_paw  # noqa: F401
 from eks_b200.ibl_pupil_smoother import (  # noqa: F401
     ensemble_kalman_smoother_ibl_pupil,
     fit_eks_pupil,

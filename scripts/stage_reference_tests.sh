@@ -7,7 +7,7 @@ SRC=${1:-/root/reference/tests}
 DST="$(dirname "$0")/../oracle/_ref/reference_tests"
 mkdir -p "$DST"
 for f in test_core.py test_singlecam_smoother.py test_ibl_pupil_smoother.py test_multicam_smoother.py \
-         test_marker_array.py test_utils.py test_stats.py; do
+         test_marker_array.py test_utils.py test_stats.py test_ibl_paw_multicam_smoother.py; do
   cp "$SRC/$f" "$DST/$f"
 done
 echo "staged $(ls "$DST" | wc -l) files into $DST"

@@ -33,5 +33,5 @@ import eks_b200  # noqa: E402
 
 sys.modules['eks'] = eks_b200
 for _sub in ('marker_array', 'utils', 'stats', 'core', 'ibl_pupil_smoother', 'singlecam_smoother',
-             'multicam_smoother'):
+             'multicam_smoother', 'ibl_paw_multicam_smoother'):
     sys.modules['eks.' + _sub] = importlib.import_module('eks_b200.' + _sub)

@@ -287,3 +287,48 @@ def test_lag_statistics_path_with_one_offset_span_fp64():
     assert list(res.iters[0].cpu().numpy()) == list(ref['info']['iters'])
     np.testing.assert_allclose(res.s_finals[0].cpu().numpy(), ref['s_finals'], rtol=RTOL64)
     _check(_cam_out(res), ref['cam_out'], RTOL64, 'one offset span')
+
+
+def test_fit_eks_multicam_ibl_paw(tmp_path):
+    """fit_eks_multicam_ibl_paw (reference eks/ibl_paw_multicam_smoother.py:82-256) end to end on synthetic IBL-style
+    files: left / right seed CSVs + timestamp files, right camera on its own clock; the call must equal the multi-camera
+    smoother run on the aligned MarkerArray the driver is documented to build."""
+    import pandas as pd
+    from eks_b200.ibl_paw_multicam_smoother import fit_eks_multicam_ibl_paw
+    from eks_b200.marker_array import MarkerArray
+    from eks_b200.multicam_smoother import ensemble_kalman_smoother_multicam
+    from eks_b200.utils import make_dlc_pandas_index
+    rng = np.random.default_rng(5)
+    T, M, width = 700, 2, 128
+    t_left = np.arange(T) / 60.0
+    t_right = np.arange(T + 40) / 60.0 * 0.97 - 0.05                        # different rate and offset
+    lat = np.cumsum(rng.normal(0, 0.4, (T + 80, 2, 2)), axis=0) + 60.0       # (frames, paw, xy) in the left camera's frame
+    at = lambda ts: np.stack([np.stack([np.interp(ts, np.arange(T + 80) / 60.0 - 0.1, lat[:, p, c]) for c in range(2)], 1)
+                              for p in range(2)], 1)                         # (len(ts), paw, xy)
+    idx = make_dlc_pandas_index(['paw_l', 'paw_r'])
+    for m in range(M):
+        xl = at(t_left) + rng.normal(0, 0.3, (T, 2, 2))
+        left = np.concatenate([np.concatenate([xl[:, p], np.full((T, 1), 0.95)], 1) for p in range(2)], 1)
+        xr = at(t_right) + rng.normal(0, 0.3, (T + 40, 2, 2))
+        xr[..., 0] = width - xr[..., 0]                                      # the right camera is mirrored ...
+        right = np.concatenate([np.concatenate([xr[:, p], np.full((T + 40, 1), 0.95)], 1) for p in (1, 0)], 1)   # ... and swaps paws
+        pd.DataFrame(left, columns=idx).to_csv(tmp_path / f'sess.left.rng={m}.csv')
+        pd.DataFrame(right, columns=idx).to_csv(tmp_path / f'sess.right.rng={m}.csv')
+    np.save(tmp_path / 'sess.timestamps.left.npy', t_left)
+    np.save(tmp_path / 'sess.timestamps.right.npy', t_right)
+    out_dir = tmp_path / 'out'
+    dfs, s, input_dfs_list, bps = fit_eks_multicam_ibl_paw(str(tmp_path), str(out_dir), smooth_param=5.0, var_mode='var')
+    assert bps == ['paw_l', 'paw_r'] and (out_dir / 'multicam_left_results.csv').exists() and list(s) == [5.0, 5.0]
+    n = len(input_dfs_list[0][0])
+    assert 0 < n <= T and dfs[0].shape == (n, 2 * 9)
+    # after alignment both cameras see the same trajectory: the smoothed x of the two cameras agree to the noise level
+    assert np.abs(dfs[0].to_numpy()[:, 0] - dfs[1].to_numpy()[:, 0]).mean() < 1.0
+    arr = np.zeros((M, 2, n, 2, 3))
+    for c in range(2):
+        for m in range(M):
+            arr[m, c, :, :, :2] = input_dfs_list[c][m].to_numpy().reshape(n, 2, 2)
+    ref, _, _ = ensemble_kalman_smoother_multicam(MarkerArray(arr, data_fields=['x', 'y', 'likelihood']),
+                                                  ['paw_l', 'paw_r'], ['left', 'right'], smooth_param=5.0, var_mode='var',
+                                                  inflate_vars_kwargs={'likelihoods': None})
+    for a, b in zip(dfs, ref):
+        np.testing.assert_allclose(a.to_numpy(), b.to_numpy(), rtol=1e-6, atol=1e-6)

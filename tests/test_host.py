@@ -337,3 +337,52 @@ def test_fast_csv_writer_equals_pandas_to_csv(tmp_path):
     odd = pd.DataFrame({'s': ['x', 'y'], 'v': [1.0, 2.0]})
     write_dlc_csv(odd, str(tmp_path / 'odd.csv'))
     assert open(tmp_path / 'odd.csv').read() == odd.to_csv()
+
+
+def test_ibl_paw_alignment_equals_the_reference_loop(monkeypatch, tmp_path):
+    """fit_eks_multicam_ibl_paw's host stage (vectorised resampling of the right camera onto the left camera's
+    timestamps, x flip, paw swap, zero likelihoods) against a loop restatement of eks/ibl_paw_multicam_smoother.py:
+    178-236 on the bundled data/ibl-paw.  The smoother itself is replaced by a stub: no device needed."""
+    import pandas as pd
+    data = os.environ.get('EKS_DATA_DIR', '/root/reference/data') + '/ibl-paw'
+    if not os.path.isdir(data):
+        pytest.skip(f'{data} not present (build container only)')
+    from scipy.interpolate import interp1d
+    from eks_b200 import ibl_paw_multicam_smoother as paw
+    from eks_b200.io import convert_lp_dlc
+    captured = {}
+
+    def stub(marker_array, keypoint_names, camera_names, **kw):
+        captured['ma'], captured['kw'] = marker_array, kw
+        T = marker_array.shape[2]
+        cols = pd.MultiIndex.from_product([['s'], keypoint_names, ['x']])
+        return [pd.DataFrame(np.zeros((T, len(keypoint_names))), columns=cols) for _ in camera_names], [1.0, 1.0], None
+    monkeypatch.setattr(paw, 'ensemble_kalman_smoother_multicam', stub)
+    dfs, s, input_dfs_list, bodyparts = paw.fit_eks_multicam_ibl_paw(data, str(tmp_path), var_mode='var')
+    assert bodyparts == ['paw_l', 'paw_r'] and captured['kw']['inflate_vars_kwargs'] == {'likelihoods': None}
+    ma = captured['ma']
+    assert list(ma.data_fields) == ['x', 'y', 'likelihood'] and np.all(ma.array[..., 2] == 0)
+    # loop restatement for the first model (files in os.listdir order, as the product and the reference read them)
+    names = os.listdir(data)
+    left = [n for n in names if 'timestamps' not in n and 'left' in n][0]
+    right = [n for n in names if 'timestamps' not in n and 'left' not in n][0]
+    tl = np.load(os.path.join(data, [n for n in names if 'timestamps' in n and 'left' in n][0]))
+    tr = np.load(os.path.join(data, [n for n in names if 'timestamps' in n and 'left' not in n][0]))
+    L = convert_lp_dlc(pd.read_csv(os.path.join(data, left), header=[0, 1, 2], index_col=0), bodyparts).to_numpy()
+    R = convert_lp_dlc(pd.read_csv(os.path.join(data, right), header=[0, 1, 2], index_col=0), bodyparts).to_numpy()
+    R = R[:, [3, 4, 5, 0, 1, 2]]                                   # right camera: paws swapped
+    f = [interp1d(tr, R[:, j]) for j in range(6)]
+    rows_l, rows_r = [], []
+    for i, ts in enumerate(tl):
+        if ts > tr[-1] or ts < tr[0]:
+            continue
+        rows_l.append(L[i, [0, 1, 3, 4]])
+        r = np.array([f[j](ts) for j in [0, 1, 3, 4]])
+        r[0], r[2] = 128 - r[0], 128 - r[2]
+        rows_r.append(r)
+    ref_l, ref_r = np.asarray(rows_l), np.asarray(rows_r)
+    assert ma.shape[2] == len(ref_l)
+    got_l = ma.array[0, 0, :, :, :2].reshape(len(ref_l), 4)       # (T, [paw_l x y, paw_r x y])
+    got_r = ma.array[0, 1, :, :, :2].reshape(len(ref_r), 4)
+    np.testing.assert_allclose(got_l, ref_l, rtol=0, atol=0)
+    np.testing.assert_allclose(got_r, ref_r, rtol=1e-12, atol=1e-10)

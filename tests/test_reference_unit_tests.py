@@ -18,7 +18,7 @@ CANDIDATES = [os.environ.get('EKS_REFERENCE_TESTS'), '/root/reference/tests',
               os.path.join(ROOT, 'oracle', '_ref', 'reference_tests')]
 REF_TESTS = next((c for c in CANDIDATES if c and os.path.isdir(c)), None)
 
-CPU_FILES = ['test_marker_array.py', 'test_utils.py', 'test_stats.py']
+CPU_FILES = ['test_marker_array.py', 'test_utils.py', 'test_stats.py', 'test_ibl_paw_multicam_smoother.py']
 GPU_FILES = ['test_core.py', 'test_singlecam_smoother.py', 'test_ibl_pupil_smoother.py', 'test_multicam_smoother.py']
 
 
